@@ -1,0 +1,170 @@
+"""TEST INFRASTRUCTURE ONLY -- drive the loaded reference (``oracle.ref_shim``) over a
+``parakeet_slam_b200.scenario.Scenario`` and record everything parity needs.
+
+The frame loop is ``simple_driver``-style: the control is constant, the clock
+advances ``dt`` per frame and every frame is one ``FastSLAM.cam_cb`` call
+(reference ``prkt_core_v2.py:59-137``), which performs the motion update
+(``:75-77``), association + EKF + weighting (``:84-124``) and the low-variance
+resample (``:137``).  ``match_features_to_scan`` and ``low_variance_resample`` are
+wrapped (not replaced) to record association ids, pre-resample weights and
+ancestor indices.
+"""
+from __future__ import annotations
+
+import random as _pyrandom
+import warnings
+
+import numpy as np
+
+from parakeet_slam_b200.rosless import clock
+from parakeet_slam_b200.scenario import Scenario, scan_from_observations
+
+from . import ref_shim
+
+
+class _View(object):
+    """Stands in for ``CamSlam360``: ``cam_cb`` only reads ``last_sensor_reading``
+    (reference ``prkt_core_v2.py:82``)."""
+
+    def __init__(self):
+        self.last_sensor_reading = None
+
+
+def heading_of(ref, particle) -> float:
+    return float(ref.utils.quaternion_to_heading(particle.state.pose.pose.orientation))
+
+
+def pose_of(ref, particle):
+    p = particle.state.pose.pose.position
+    return (float(np.asarray(p.x).reshape(-1)[0]), float(np.asarray(p.y).reshape(-1)[0]),
+            heading_of(ref, particle))
+
+
+def build_reference_filter(ref, scn: Scenario, num_particles=None, known_map=True):
+    """``FastSLAM`` with M particles (the reference hard-codes 50, ``:41``) preloaded with the
+    scenario's true landmarks, covar ``preset_covar * I5`` (``prkt_ros.py:33-37``)."""
+    core = ref.core
+    M = scn.num_particles if num_particles is None else num_particles
+    feats = []
+    if known_map:
+        for row in scn.landmarks:
+            f = core.Feature(mean=ref.matrix.Matrix([float(v) for v in row]),
+                             covar=ref.matrix.Matrix(np.identity(5) * scn.preset_covar))
+            f.__immutable__ = bool(scn.immutable)
+            feats.append(f)
+    clock.set(0.0)
+    fs = core.FastSLAM(feats)
+    if M != fs.num_particles:
+        fs.num_particles = M
+        fs.particles = [core.FilterParticle() for _ in range(M)]
+        for particle in fs.particles:
+            particle.load_feature_list(feats)
+    return fs
+
+
+def landmark_state(fs, n_slots):
+    """[M, n, 5] means, [M, n, 5, 5] covars, [M, n] update counts for ids 1..n_slots."""
+    M = len(fs.particles)
+    mean = np.zeros((M, n_slots, 5))
+    cov = np.zeros((M, n_slots, 5, 5))
+    cnt = np.zeros((M, n_slots), dtype=np.int64)
+    for i, p in enumerate(fs.particles):
+        for id_, f in p.feature_set.items():
+            mean[i, id_ - 1] = np.asarray(f.mean, dtype=np.float64).reshape(5)
+            cov[i, id_ - 1] = np.asarray(f.covar, dtype=np.float64)
+            cnt[i, id_ - 1] = f.update_count
+    return mean, cov, cnt
+
+
+def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmarks_at=(),
+                  ref=None, spawn=False, known_map=True, timing=None):
+    """Run the reference over ``frames`` frames.  Returns a dict of numpy traces:
+
+    ``pose_pre``  [T, M, 3] pose after motion, before resampling (the pose the
+                  measurement update saw), ``pose_post`` [T, M, 3] after resampling,
+    ``assoc`` [T, M, K] ids, ``weight`` [T, M] pre-resample weights, ``ancestors``
+    [T, M], ``summary`` [T, 3], ``next_id`` [T, M] (after resampling),
+    ``lm_mean``/``lm_cov``/``lm_count`` dicts keyed by frame.
+    """
+    import time
+
+    if ref is None:
+        ref = ref_shim.load_reference(with_ros_node=False)
+        if spawn:
+            ref_shim.apply_spawn_patches(ref)
+    core = ref.core
+    T = scn.frames if frames is None else frames
+    M = scn.num_particles if num_particles is None else num_particles
+    K = scn.obs_per_frame
+
+    fs = build_reference_filter(ref, scn, num_particles=M, known_map=known_map)
+    twist = ref.msgs.Twist()
+    twist.linear.x = scn.v
+    twist.angular.z = scn.w
+    fs.last_control = twist
+
+    np.random.seed(scn.motion_seed)
+    _pyrandom.seed(scn.meta.get("resample_seed", 12345))
+    # the reference does ``from random import random`` at import time (``:28``); that is the
+    # module-level function of the global Random instance, so seeding the module works.
+
+    trace = dict(pose_pre=np.zeros((T, M, 3)), pose_post=np.zeros((T, M, 3)),
+                 assoc=np.zeros((T, M, K), dtype=np.int32), weight=np.zeros((T, M)),
+                 ancestors=np.zeros((T, M), dtype=np.int32), summary=np.zeros((T, 3)),
+                 next_id=np.zeros((T, M), dtype=np.int64), lm_mean={}, lm_cov={}, lm_count={},
+                 frame_seconds=np.zeros(T))
+
+    rec = {}
+    orig_match = core.FilterParticle.match_features_to_scan
+
+    def match_wrapper(self, scan):
+        out = orig_match(self, scan)
+        rec["assoc"].append([int(pair[0]) for pair in out])
+        rec["pose"].append(pose_of(ref, self))
+        return out
+
+    orig_resample = core.FastSLAM.low_variance_resample
+
+    def resample_wrapper(self):
+        old = list(self.particles)
+        rec["weight"] = [float(np.asarray(p.weight).reshape(-1)[0]) for p in old]
+        for idx, p in enumerate(old):
+            p._trace_index = idx
+        orig_resample(self)
+        rec["ancestors"] = [p._trace_index for p in self.particles]
+
+    core.FilterParticle.match_features_to_scan = match_wrapper
+    core.FastSLAM.low_variance_resample = resample_wrapper
+    view = _View()
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for t in range(T):
+                rec["assoc"], rec["pose"] = [], []
+                clock.advance_nsec(int(round(scn.dt * 1e9)))
+                view.last_sensor_reading = scan_from_observations(scn.observations[t], ref.msgs)
+                t0 = time.perf_counter()
+                fs.cam_cb(view)
+                trace["frame_seconds"][t] = time.perf_counter() - t0
+                trace["assoc"][t] = np.asarray(rec["assoc"], dtype=np.int32).reshape(M, K)
+                trace["pose_pre"][t] = np.asarray(rec["pose"])
+                trace["weight"][t] = rec["weight"]
+                anc = rec["ancestors"]
+                if len(anc) != M:
+                    raise RuntimeError("reference emitted %d != %d particles" % (len(anc), M))
+                trace["ancestors"][t] = anc
+                trace["pose_post"][t] = [pose_of(ref, p) for p in fs.particles]
+                trace["summary"][t] = [float(v) for v in fs.summary()]
+                trace["next_id"][t] = [p.next_id for p in fs.particles]
+                if t in record_landmarks_at:
+                    mean, cov, cnt = landmark_state(fs, scn.num_landmarks)
+                    trace["lm_mean"][t], trace["lm_cov"][t], trace["lm_count"][t] = mean, cov, cnt
+                if timing is not None and timing(t, trace["frame_seconds"][: t + 1]):
+                    trace["frames_run"] = t + 1
+                    break
+    finally:
+        core.FilterParticle.match_features_to_scan = orig_match
+        core.FastSLAM.low_variance_resample = orig_resample
+    trace.setdefault("frames_run", T)
+    trace["filter"] = fs
+    return trace

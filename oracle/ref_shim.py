@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE ONLY -- loader that runs the UNMODIFIED reference sources.
+
+Nothing in ``parakeet_slam_b200/`` may import this package.  Only ``tests/``,
+``oracle/make_golden.py``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
+baseline leg use ``oracle/``.
+
+The reference (``/root/reference/src/prkt_core_v2.py`` etc.) is Python 2 + ROS
+Indigo.  It is read from where it lies (never copied into this repo), given two
+textual Py2->3 substitutions (``xrange(`` -> ``range(`` for ``prkt_core_v2.py:159``
+and ``.iteritems()`` -> ``.items()`` for ``prkt_core_v2.py:579``) and executed on
+top of the fake ROS modules of ``parakeet_slam_b200.rosless``.  The resulting
+classes ARE the reference implementation; golden vectors under ``tests/golden``
+are produced from them by ``oracle/make_golden.py``.
+
+``/root/reference`` exists only in the development container, so everything here
+degrades to ``available() == False`` on the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REFERENCE_SRC = os.environ.get("PARAKEET_REFERENCE_SRC", "/root/reference/src")
+
+_PY2_SUBSTITUTIONS = (("xrange(", "range("), (".iteritems()", ".items()"))
+_REF_MODULE_NAMES = ("matrix", "utils", "prkt_core_v2", "prkt_ros")
+
+
+def available(src_dir: str = REFERENCE_SRC) -> bool:
+    return os.path.isfile(os.path.join(src_dir, "prkt_core_v2.py"))
+
+
+class ReferenceModules(object):
+    """Namespace holding the loaded reference modules."""
+
+    def __init__(self):
+        self.matrix = None
+        self.utils = None
+        self.core = None      # prkt_core_v2
+        self.ros = None       # prkt_ros (CamSlam360)
+        self.rospy = None
+        self.msgs = None
+
+
+def _exec_source(name: str, path: str, extra_globals=None) -> types.ModuleType:
+    with open(path, "r") as fh:
+        text = fh.read()
+    for old, new in _PY2_SUBSTITUTIONS:
+        text = text.replace(old, new)
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    if extra_globals:
+        mod.__dict__.update(extra_globals)
+    sys.modules[name] = mod
+    code = compile(text, path, "exec")
+    exec(code, mod.__dict__)
+    return mod
+
+
+def load_reference(src_dir: str = REFERENCE_SRC, with_ros_node: bool = True) -> ReferenceModules:
+    """Load matrix/utils/prkt_core_v2 (and prkt_ros) from ``src_dir``.
+
+    The fake ROS modules are installed into ``sys.modules`` only while the
+    reference files execute their imports; the reference module names
+    (``matrix``, ``utils``, ``prkt_core_v2``, ``prkt_ros``) are removed from
+    ``sys.modules`` afterwards so they never shadow the product's drop-in
+    ``prkt_core_v2`` module.
+    """
+    if not available(src_dir):
+        raise RuntimeError("reference sources not found under %r" % (src_dir,))
+    from parakeet_slam_b200 import rosless
+
+    saved = {n: sys.modules.get(n) for n in _REF_MODULE_NAMES}
+    saved_fake = {n: sys.modules.get(n) for n in rosless._FAKE_NAMES}
+    fakes = rosless.build_modules()
+    sys.modules.update(fakes)
+    out = ReferenceModules()
+    out.rospy = fakes["rospy"]
+    out.msgs = rosless.messages
+    try:
+        out.matrix = _exec_source("matrix", os.path.join(src_dir, "matrix.py"))
+        out.utils = _exec_source("utils", os.path.join(src_dir, "utils.py"))
+        out.core = _exec_source("prkt_core_v2", os.path.join(src_dir, "prkt_core_v2.py"))
+        if with_ros_node:
+            out.ros = _exec_source("prkt_ros", os.path.join(src_dir, "prkt_ros.py"))
+    finally:
+        for n, mod in saved.items():
+            if mod is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = mod
+        for n, mod in saved_fake.items():
+            if mod is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = mod
+    return out
+
+
+def load_reference_tests(ref: ReferenceModules, src_dir: str = REFERENCE_SRC) -> types.ModuleType:
+    """Load the reference's own unittest module (``test_prkt_ros2.py``) bound to
+    an already loaded set of reference modules, so its 23 cases can be run as a
+    self-check of this shim."""
+    from parakeet_slam_b200 import rosless
+
+    names = {"matrix": ref.matrix, "utils": ref.utils, "prkt_core_v2": ref.core,
+             "prkt_ros": ref.ros}
+    saved = {n: sys.modules.get(n) for n in list(names) + list(rosless._FAKE_NAMES)}
+    fakes = rosless.build_modules()
+    fakes["rospy"] = ref.rospy
+    sys.modules.update(fakes)
+    sys.modules.update({k: v for k, v in names.items() if v is not None})
+    try:
+        mod = _exec_source("_ref_test_prkt_ros2", os.path.join(src_dir, "test_prkt_ros2.py"))
+    finally:
+        sys.modules.pop("_ref_test_prkt_ros2", None)
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+    return mod
+
+
+# --------------------------------------------------------------------------------------
+# Spawn-mode oracle: the reference module with exactly three monkey-patches.
+# --------------------------------------------------------------------------------------
+def apply_spawn_patches(ref: ReferenceModules, gate: float = 300.0 ** 0.5) -> None:
+    """Make the dead new-landmark path of the reference reachable (finding F5).
+
+    P1 ``find_nearest_reading`` iterates ``hypothesis_set`` (what its docstring
+       describes, ``prkt_core_v2.py:565-590``) and returns +id when the minimum
+       distance is <= ``gate`` (sqrt(300), mirroring the colour gate ``:441``),
+       else -id (or 0 when there is nothing to compare with).
+    P2 ``add_orphaned_reading`` stores a copy of the pose instead of aliasing
+       ``particle.state`` (``:745``).
+    P3 ``cross_readings`` output is coerced to Python floats before
+       ``Matrix([...])`` (``:665-672``), because poses become shape-(1,) arrays
+       after the first motion step (``:185-186, 203-204``).
+    Everything else that runs is reference code.
+    """
+    import copy
+
+    core = ref.core
+    FilterParticle = core.FilterParticle
+
+    def find_nearest_reading(self, state, blob):
+        min_dist_id = 0
+        min_dist = float("inf")
+        for id_, reading in self.hypothesis_set.items():
+            d = self.reading_distance_function(reading[0], reading[1], state, blob)
+            if d < min_dist:
+                min_dist = d
+                min_dist_id = id_
+        if min_dist_id == 0:
+            return 0
+        if min_dist <= gate:
+            return min_dist_id
+        return -min_dist_id
+
+    def add_orphaned_reading(self, state, blob):
+        self.hypothesis_set[self.next_id] = ((copy.deepcopy(state), blob,))
+        self.next_id += 1
+
+    orig_cross = FilterParticle.cross_readings
+
+    def cross_readings(self, old_reading, new_reading):
+        res = orig_cross(self, old_reading, new_reading)
+        if res is None:
+            return None
+        return (float(res[0]), float(res[1]))
+
+    FilterParticle.find_nearest_reading = find_nearest_reading
+    FilterParticle.add_orphaned_reading = add_orphaned_reading
+    FilterParticle.cross_readings = cross_readings
