@@ -1,0 +1,209 @@
+/*
+ * parakeet_b200.h -- C ABI of libparakeet_b200.so, the B200 (sm_100a) FastSLAM 1.0 hot path.
+ *
+ * This is the drop-in boundary for the particle-filter path of buckbaskin/parakeet_slam
+ * (reference file src/prkt_core_v2.py).  The reference is pure Python with no FFI of its
+ * own, so each entry point names the reference method whose per-particle loop it replaces
+ * (file:line relative to /root/reference/src).  The Python binding a maintainer would add is
+ * a ctypes stub -- see INTEGRATION.md and parakeet_slam_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends
+ *     in _host; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - the library never allocates or frees persistent device memory: the caller owns all
+ *     state (PyTorch tensors on the Python side) and passes a workspace where one is needed
+ *   - every function returns 0 on success or a negative PK_E* code; pk_last_error() gives a
+ *     thread-local message.  No C++ exception crosses the boundary.
+ *   - all work is asynchronous on `stream`; nothing here synchronises the device
+ *
+ * Device data layout (see DESIGN.md "Data layout in HBM")
+ *   pose4   double[M][4]    x, y, heading (as read back through the quaternion), weight
+ *   aux2    int[M][2]       n_live landmarks, next_id            (travels with the particle)
+ *   slot    int[M]          index of the particle's landmark block in the pool
+ *   pool    bytes           n_slots blocks of pk_block_bytes(capacity, dtype); one block =
+ *                           [hot: capacity x HOT][cold: capacity x COLD]
+ *                             f32: HOT 16 B = r,g,b (float), meta (int)
+ *                                  COLD 64 B = x,y, Sp[2][2], Sc[3][3] (15 float), id (int)
+ *                             f64: HOT 32 B = r,g,b (double), meta (int), pad
+ *                                  COLD 128 B = x,y, Sp[2][2], Sc[3][3] (15 double), id, pad
+ *                           meta = update_count | PK_META_IMMUTABLE | PK_META_POTENTIAL
+ *                           The 5x5 landmark covariance of the reference is stored as its two
+ *                           diagonal blocks; the cross blocks are exactly zero in every state the
+ *                           reference can reach (H has exact zeros, prkt_core_v2.py:799-802).
+ */
+#ifndef PARAKEET_B200_H
+#define PARAKEET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+#define PK_OK 0
+#define PK_EINVAL (-1)   /* bad argument (null pointer, size, dtype, K > PK_MAX_OBS ...) */
+#define PK_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define PK_EARCH (-3)    /* device is not sm_100 */
+
+#define PK_DTYPE_F32 0   /* landmark storage fp32 (arithmetic is fp64 either way) */
+#define PK_DTYPE_F64 1   /* landmark storage fp64: the parity instantiation */
+
+#define PK_MAX_OBS 64        /* blobs per frame handled by one pk_measurement_update */
+#define PK_SCAN_BLOCK 1024   /* particles per weight-scan block (fixed: results must not depend on the shard count) */
+
+#define PK_META_COUNT_MASK 0x00ffffff
+#define PK_META_IMMUTABLE  0x10000000   /* Feature.__immutable__   (prkt_core_v2.py:883, prkt_ros.py:41) */
+#define PK_META_POTENTIAL  0x20000000   /* lives in potential_features, id < 0 (prkt_core_v2.py:287, 679) */
+
+/* indices into the stats array written by pk_measurement_update (uint64 each) */
+#define PK_STAT_MATCHED 0        /* (particle, blob) pairs with id != 0 */
+#define PK_STAT_UNMATCHED 1      /* pairs with id == 0 (orphaned readings, prkt_core_v2.py:92-95) */
+#define PK_STAT_EVALUATED 2      /* exact likelihood evaluations (survivors of the colour pre-filter) */
+#define PK_STAT_FLAGS 3          /* OR of PK_FLAG_* */
+#define PK_STAT_SAME_LANDMARK 4  /* updates that had to wait for an earlier blob on the same landmark */
+#define PK_STAT_PROMOTED 5       /* potential -> full promotions (prkt_core_v2.py:114-118) */
+#define PK_NUM_STATS 8
+
+#define PK_FLAG_SINGULAR_COV 1u      /* a landmark covariance block had det <= 0 (SciPy would raise) */
+#define PK_FLAG_NONFINITE_WEIGHT 2u  /* a particle weight became NaN/Inf */
+#define PK_FLAG_REPROMOTED 4u        /* a blob hit a landmark promoted earlier in the same frame
+                                        (the reference raises KeyError there, prkt_core_v2.py:98,312) */
+
+/* Literals of the reference, gathered in one struct (SURVEY.md section 5 "Config / flags"). */
+typedef struct pk_params {
+    double bearing_gate;     /* 0.5 rad      prkt_core_v2.py:433 */
+    double position_gate;    /* pi/2         prkt_core_v2.py:474 */
+    double color_gate;       /* 300          prkt_core_v2.py:441 */
+    double no_match_weight;  /* 0.1          prkt_core_v2.py:857 */
+    double qt_diag;          /* 0.1          prkt_core_v2.py:50-53 (Qt = qt_diag * I4) */
+    int promote_count;       /* 5            prkt_core_v2.py:114 (promote when update_count > 5) */
+    int reserved;
+} pk_params;
+
+int pk_version(void);
+const char* pk_last_error(void);
+int pk_default_params(pk_params* out);
+/* 0 if the current device is sm_100 (B200); PK_EARCH otherwise, PK_ECUDA if there is none. */
+int pk_check_device(void);
+
+/* ---- layout ------------------------------------------------------------------------------ */
+int pk_hot_bytes(int dtype);
+int pk_cold_bytes(int dtype);
+long long pk_block_bytes(int capacity, int dtype);
+
+/* ---- construction: FastSLAM.__init__ / FilterParticle.__init__ / load_feature_list
+ *      (prkt_core_v2.py:38-57, 279-299) -------------------------------------------------------- */
+/* pose <- (0,0,0), weight <- 1, slot[i] <- i, aux <- (n_live, next_id) */
+int pk_init_particles(double* pose4, int* slot, int* aux2, long long M, int n_live, int next_id,
+                      void* stream);
+/* Write one map (n landmarks given as fp64 SoA device arrays mean5[n][5], covp[n][4],
+ * covc[n][9], meta[n], ids[n]) into blocks [slot_lo, slot_hi) of the pool. */
+int pk_map_broadcast(void* pool, int capacity, int dtype, long long slot_lo, long long slot_hi,
+                     int n, const double* mean5, const double* covp, const double* covc,
+                     const int* meta, const int* ids, void* stream);
+/* Per-particle maps <-> fp64 SoA arrays shaped [count][capacity][...] for particles
+ * [p_lo, p_lo+count) (particles[i].feature_set views, tests, checkpoints). */
+int pk_map_export(const void* pool, int capacity, int dtype, const int* slot, long long p_lo,
+                  long long count, double* mean5, double* covp, double* covc, int* meta, int* ids,
+                  void* stream);
+int pk_map_import(void* pool, int capacity, int dtype, const int* slot, long long p_lo,
+                  long long count, const double* mean5, const double* covp, const double* covc,
+                  const int* meta, const int* ids, void* stream);
+
+/* ---- K1 motion: FastSLAM.motion_update / motion_model (prkt_core_v2.py:148-208) and the
+ *      quaternion heading round trip (utils.py:8-35) ------------------------------------------ */
+/* noise3 != NULL: standard normals [M][3] standing for the three numpy normal() draws
+ * (injected-noise parity mode).  noise3 == NULL: Philox4x32-10 counter RNG keyed by `seed`,
+ * counter = (particle_offset + i, frame), Box-Muller. */
+int pk_motion_update(double* pose4, long long M, const double* noise3, unsigned long long seed,
+                     unsigned long long frame, long long particle_offset, double v, double w,
+                     double dt, void* stream);
+
+/* ---- K2 fused measurement update: the per-particle body of FastSLAM.cam_cb
+ *      (prkt_core_v2.py:84-124): match_features_to_scan / match_one / probability_of_match /
+ *      prob_position_match / closest_point / prob_color_match (:317-544), generate_measurement,
+ *      measurement_jacobian, measurement_covariance, inverse, kalman_gain (:748-833, 859-877),
+ *      Feature.update_mean / update_covar (:897-930), importance_factor, no_match_weight
+ *      (:835-857), potential-feature promotion (:109-118), orphan counting (:740-746) ---------- */
+/* obs_host: K rows of (bearing, r, g, b), HOST memory, read before the call returns.
+ * Writes weight (pose4[i][3]), assoc[M][K] (reference ids: >0 full, <0 potential, 0 unseen),
+ * updates the pool and aux2, accumulates stats[PK_NUM_STATS] (caller zeroes them). */
+int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool, int capacity,
+                          int dtype, long long M, const double* obs_host, int K,
+                          const pk_params* params, int* assoc, unsigned long long* stats,
+                          void* stream);
+
+/* ---- K3/K4 weight normaliser + systematic resampling plan:
+ *      FastSLAM.low_variance_resample (prkt_core_v2.py:210-252) ------------------------------- */
+long long pk_num_scan_blocks(long long M);
+/* K3a: per-block (PK_SCAN_BLOCK particles) inclusive prefix sums of the weights, fp64, and the
+ * block totals.  cumsum[M], block_sums[pk_num_scan_blocks(M)]. */
+int pk_weight_scan(const double* pose4, long long M, double* cumsum, double* block_sums,
+                   void* stream);
+/* K3b: fold ALL block totals of ALL shards (nb_total of them, in global order; on one GPU this is
+ * the block_sums array itself) into double-double block prefixes and the resampling thresholds.
+ * plan: double[PK_PLAN_DOUBLES] (total, range, u0 ...); block_prefix[nb_total][2];
+ * block_count[nb_total+1] (outputs emitted before each block, monotone). */
+#define PK_PLAN_DOUBLES 8
+int pk_resample_thresholds(const double* all_block_sums, long long nb_total, long long M_total,
+                           double u01, double* plan, double* block_prefix, long long* block_count,
+                           void* stream);
+/* K4: for the local particles (global index particle_offset + i, scan blocks starting at
+ * block_offset) compute each one's run of output slots [out_lo[i], out_lo[i]+offspring[i]) and
+ * write ancestors[k - out_offset] = particle_offset + i for every output k of the local output
+ * window [out_offset, out_offset + n_out).  big_runs: workspace of >= 4 + 3*M_local int64. */
+int pk_resample_ancestors(const double* cumsum, long long M_local, long long particle_offset,
+                          long long block_offset, const double* plan, const double* block_prefix,
+                          const long long* block_count, long long M_total, long long out_offset,
+                          long long n_out, long long* out_lo, int* offspring, long long* ancestors,
+                          long long* big_runs, void* stream);
+
+/* ---- K5 copy-on-resample: the deepcopy(particle) of prkt_core_v2.py:243 ---------------------- */
+long long pk_gather_workspace_bytes(long long M);
+/* Single-GPU form.  ancestors[M] ascending (int64, local indices).  Survivors keep their landmark
+ * block; every extra copy of a particle is written into the block of a particle that died
+ * (#copies == #dead).  pose/aux are permuted out of place.  n_copied_out (device int64) receives
+ * the number of blocks copied. */
+int pk_resample_gather(const long long* ancestors, const int* offspring, long long M,
+                       const double* pose4_in, double* pose4_out, const int* aux2_in,
+                       int* aux2_out, const int* slot_in, int* slot_out, void* pool, int capacity,
+                       int dtype, void* workspace, long long* n_copied_out, void* stream);
+/* Raw block mover (also used by the sharded path to pack / unpack migrating particles): copies n
+ * landmark blocks src_base[src_slot[i]] -> dst_base[dst_slot[i]] (n = min(*n_dev, n_max) when
+ * n_dev != NULL) staged through shared memory with TMA bulk copies.  n_live (nullable) limits
+ * each copy to the live landmarks of the block. */
+int pk_copy_blocks(const void* src_base, void* dst_base, int capacity, int dtype, const int* src_slot,
+                   const int* dst_slot, const int* n_live, long long n_max, const long long* n_dev,
+                   void* stream);
+
+/* ---- K6 queries: FastSLAM.summary (prkt_core_v2.py:254-276); best particle is additive ------- */
+/* out5[0..3] = sum x, sum y, sum sin(theta), sum cos(theta); out5[4] = M.  The caller finishes
+ * (x/M, y/M, atan2) after an optional cross-shard all-reduce.  workspace: 5*1024 doubles. */
+int pk_summary_partial(const double* pose4, long long M, double* out5, double* workspace,
+                       void* stream);
+/* best[0] = max weight, best[1] = index of its first occurrence (as double). workspace 2*1024. */
+int pk_best_particle(const double* pose4, long long M, double* best2, double* workspace,
+                     void* stream);
+
+/* ---- probes: the per-landmark math one triple per thread (back the scalar helper methods of
+ *      FilterParticle -- probability_of_match prkt_core_v2.py:383-455, the EKF pieces :748-930 --
+ *      and pin the device arithmetic against the reference's known-answer vectors) ------------- */
+/* pose3[n][3] (x,y,heading), blob4[n][4] (bearing,r,g,b), dir2[n][2] = unit((cos b, sin b, 0)),
+ * landmark mean5[n][5], covp[n][4], covc[n][9]  ->  out[n] = probability_of_match */
+int pk_probe_likelihood(const double* pose3, const double* blob4, const double* dir2,
+                        const double* mean5, const double* covp, const double* covc, long long n,
+                        const pk_params* params, double* out, void* stream);
+/* One EKF update per thread: pose2[n][2], blob4[n][4], landmark (mean5, covp, covc, meta nullable)
+ * -> updated landmark and the weight factor (importance_factor, or no_match_weight if potential). */
+int pk_probe_ekf(const double* pose2, const double* blob4, const double* mean5, const double* covp,
+                 const double* covc, const int* meta, long long n, const pk_params* params,
+                 double* mean5_out, double* covp_out, double* covc_out, double* factor_out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAKEET_B200_H */

@@ -1,0 +1,594 @@
+"""Drop-in replacement for the reference's ``prkt_core_v2`` module
+(``/root/reference/src/prkt_core_v2.py``): same class names, constructor, methods and
+attributes (``FastSLAM``, ``FilterParticle``, ``Feature``), with every per-particle loop
+executed by hand-written sm_100a CUDA kernels reached through the C ABI of
+``libparakeet_b200.so`` (``include/parakeet_b200.h``).
+
+Filter state lives in PyTorch CUDA tensors (structure described in DESIGN.md); the library only
+receives raw pointers.  There is no CPU path: constructing ``FastSLAM`` without a CUDA device
+or without the shared library raises.
+
+Reference behaviour that is kept on purpose (SURVEY.md findings F2-F8): association of all
+blobs before any update, fp64-underflow match decision, world-frame predicted bearing in the
+EKF update, ``[+dy/q, +dx/q]`` Jacobian row, Frobenius norm in the importance factor, no angle
+wrapping, systematic resampling every frame with one ``random.random()`` draw, motion noise as
+three NumPy normals per particle in index order from the global legacy stream, the previous
+control being integrated by ``motion_update``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import random as _pyrandom
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._ros import Odometry, Quaternion, Twist, now as _ros_now
+
+__all__ = ["FastSLAM", "FilterParticle", "Feature", "ParticleList", "Matrix"]
+
+
+def Matrix(array_like):
+    """``matrix.Matrix`` of the reference (``matrix.py:6-9``): a NumPy array."""
+    return np.array(array_like)
+
+
+# --------------------------------------------------------------------------------------------
+# Heading <-> quaternion on the host, for the message views only (utils.py:8-35)
+# --------------------------------------------------------------------------------------------
+def heading_to_quaternion(heading):
+    """``utils.heading_to_quaternion`` (``utils.py:21-35``): quaternion_from_euler(0,0,h)."""
+    q = Quaternion()
+    q.x = 0.0
+    q.y = 0.0
+    q.z = math.sin(float(heading) / 2.0)
+    q.w = math.cos(float(heading) / 2.0)
+    return q
+
+
+# --------------------------------------------------------------------------------------------
+# Feature  (prkt_core_v2.py:881-930)
+# --------------------------------------------------------------------------------------------
+class Feature(object):
+    """Landmark container with the reference's attributes.  Inside a running filter the landmark
+    state lives on the device; ``Feature`` objects are what goes in (presets) and what comes
+    out (``particles[i].feature_set``)."""
+
+    def __init__(self, mean=None, covar=None):
+        self.__immutable__ = False
+        if mean is None:
+            mean = Matrix([0, 0, 0, 0, 0])
+        if covar is None:
+            covar = Matrix(np.identity(5, dtype=int))
+        self.mean = mean
+        self.covar = covar
+        self.identity = np.identity(covar.shape[0])
+        self.update_count = 0
+
+    # The two update methods are part of the reference's public surface (:897-930).  A filter
+    # never calls them -- the fused kernel does this arithmetic -- they act on this host object.
+    def update_mean(self, kalman_gain, measure, expected_measure):
+        if self.__immutable__:
+            return None
+        delz = _blob_to_matrix(measure) - _blob_to_matrix(expected_measure)
+        self.mean = self.mean + np.dot(kalman_gain, delz)
+        self.update_count += 1
+
+    def update_covar(self, kalman_gain, bigH):
+        if self.__immutable__:
+            return None
+        adjust = np.subtract(self.identity, np.dot(kalman_gain, bigH))
+        self.covar = np.dot(adjust, self.covar)
+        self.update_count += 1
+
+
+def _blob_to_matrix(blob):
+    """``matrix.blob_to_matrix`` (``matrix.py:35-39``)."""
+    if hasattr(blob, "bearing"):
+        return np.array([blob.bearing, blob.color.r, blob.color.g, blob.color.b])
+    return blob
+
+
+def _feature_arrays(features, capacity, first_id=1):
+    """Features -> fp64 SoA arrays (mean5, covp, covc, meta, ids) of length ``capacity``."""
+    n = len(features)
+    mean5 = np.zeros((capacity, 5))
+    covp = np.zeros((capacity, 4))
+    covc = np.zeros((capacity, 9))
+    meta = np.zeros(capacity, dtype=np.int32)
+    ids = np.zeros(capacity, dtype=np.int32)
+    for j, f in enumerate(features):
+        mean = np.asarray(f.mean, dtype=np.float64).reshape(-1)
+        cov = np.asarray(f.covar, dtype=np.float64)
+        if mean.shape != (5,) or cov.shape != (5, 5):
+            raise ValueError("Feature %d: mean must have 5 entries and covar must be 5x5" % j)
+        if np.any(cov[:2, 2:] != 0.0) or np.any(cov[2:, :2] != 0.0):
+            raise ValueError(
+                "Feature %d: the device stores the landmark covariance as its position (2x2) and "
+                "colour (3x3) blocks; non-zero cross terms are not representable (the reference "
+                "never produces them, prkt_core_v2.py:799-802)" % j)
+        mean5[j] = mean
+        covp[j] = cov[:2, :2].reshape(4)
+        covc[j] = cov[2:, 2:].reshape(9)
+        count = int(getattr(f, "update_count", 0)) & _lib.PK_META_COUNT_MASK
+        meta[j] = count | (_lib.PK_META_IMMUTABLE if getattr(f, "__immutable__", False) else 0)
+        ids[j] = first_id + j
+    return n, mean5, covp, covc, meta, ids
+
+
+def _feature_from_arrays(mean5, covp, covc, meta):
+    cov = np.zeros((5, 5))
+    cov[:2, :2] = covp.reshape(2, 2)
+    cov[2:, 2:] = covc.reshape(3, 3)
+    f = Feature(mean=np.array(mean5, dtype=np.float64), covar=cov)
+    f.update_count = int(meta) & _lib.PK_META_COUNT_MASK
+    f.__immutable__ = bool(int(meta) & _lib.PK_META_IMMUTABLE)
+    return f
+
+
+# --------------------------------------------------------------------------------------------
+# FilterParticle  (prkt_core_v2.py:278-879) -- host-side view / container
+# --------------------------------------------------------------------------------------------
+class FilterParticle(object):
+    """One particle as the reference exposes it: ``state`` (Odometry), ``weight``,
+    ``feature_set`` {id>0: Feature}, ``potential_features`` {id<0: Feature},
+    ``hypothesis_set``, ``next_id`` (``:279-292``).  Objects returned by
+    ``FastSLAM.particles[i]`` are snapshots copied from the device."""
+
+    def __init__(self, state=None):
+        if state is None:
+            state = Odometry()
+            state.pose.pose.position.x = 0.0
+            state.pose.pose.position.y = 0.0
+            state.pose.pose.orientation = heading_to_quaternion(0.0)
+        self.state = state
+        self.feature_set = {}
+        self.potential_features = {}
+        self.weight = 1
+        self.hypothesis_set = {}
+        self.next_id = 1
+
+    def load_feature_list(self, features):
+        """``:294-299``"""
+        for feature in features:
+            self.feature_set[self.next_id] = feature
+            self.next_id += 1
+
+    def get_feature_by_id(self, id_):
+        """``:301-315`` -- raises KeyError for an unknown id."""
+        if id_ < 0:
+            return self.potential_features[int(id_)]
+        return self.feature_set[id_]
+
+    def no_match_weight(self):
+        """``:851-857``"""
+        return 0.1
+
+    @property
+    def heading(self):
+        q = self.state.pose.pose.orientation
+        n = q.z * q.z + q.w * q.w
+        if n < np.finfo(float).eps * 4.0:
+            return 0.0
+        return math.atan2(2.0 * q.z * q.w / n, 1.0 - 2.0 * q.z * q.z / n)
+
+    # -- scalar helpers of the reference, evaluated on the device through the probe ABI ----------
+    def probability_of_match(self, state, blob, feature):
+        """``:383-455`` for one (state, blob, feature) triple, computed by the same device
+        function the fused kernel uses (``pk_probe_likelihood``)."""
+        from .probe import probability_of_match
+        return probability_of_match(state, blob, feature)
+
+    def match_one(self, state, blob):
+        """``:353-381``: arg-max over ``feature_set`` then ``potential_features`` in insertion
+        order, strict ``>`` from 0.0."""
+        from .probe import probability_of_match_many
+        features = list(self.feature_set.items()) + list(self.potential_features.items())
+        if not features:
+            return 0
+        vals = probability_of_match_many(state, blob, [f for _, f in features])
+        max_match, max_match_id = 0.0, 0
+        for (id_, _), v in zip(features, vals):
+            if v > max_match:
+                max_match, max_match_id = v, id_
+        return max_match_id
+
+    def match_features_to_scan(self, scan):
+        """``:317-351``"""
+        return [(self.match_one(self.state, blob), blob) for blob in scan.observes]
+
+    def add_orphaned_reading(self, state, blob):
+        """``:740-746``"""
+        self.hypothesis_set[self.next_id] = ((state, blob,))
+        self.next_id += 1
+
+
+class ParticleList(object):
+    """``FastSLAM.particles``: a read-only sequence whose items are fetched from the device on
+    access (copying a million Python objects per frame is what the reference spends 76 % of its
+    time on; the device keeps particles as structure-of-arrays instead)."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def __len__(self):
+        return self._owner.num_particles
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("particle index out of range")
+        return self._owner._particle_view(i)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+# --------------------------------------------------------------------------------------------
+# FastSLAM  (prkt_core_v2.py:37-276)
+# --------------------------------------------------------------------------------------------
+class FastSLAM(object):
+    """``FastSLAM(preset_features=[])`` as in the reference (``:38``).  Keyword-only extras:
+
+    ``num_particles`` (reference hard-codes 50, ``:41``), ``capacity`` (landmark slots per
+    particle, default ``len(preset_features)``), ``dtype`` ``"f64"`` (parity, default) or
+    ``"f32"`` (landmark storage for throughput), ``noise`` ``"numpy"`` (three normals per particle
+    from NumPy's global legacy stream, exactly what ``motion_model`` consumes ``:185-193``),
+    ``"philox"`` (on-device counter RNG) or a callable ``f(M) -> [M,3]`` standard normals;
+    ``uniform`` callable for the resampling draw (default ``random.random`` as ``:226``);
+    ``clock`` callable returning a ROS-like time (default ``rospy.Time.now``).
+    """
+
+    def __init__(self, preset_features=[], *, num_particles=50, capacity=None, dtype="f64",
+                 device=None, noise="numpy", seed=0, uniform=None, clock=None, params=None):
+        import torch
+
+        _lib.require_device()
+        self._torch = torch
+        self._lib = _lib.load()
+        self._lock = threading.RLock()
+        self._clock = clock if clock is not None else _ros_now
+        self._device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+
+        self.last_control = Twist()                    # :39
+        self.last_update = self._clock()               # :40
+        self.num_particles = int(num_particles)        # :41
+        self.Qt = Matrix([[.1, 0, 0, 0], [0, .1, 0, 0], [0, 0, .1, 0], [0, 0, 0, .1]])  # :50-53
+        self.params = params if params is not None else _lib.default_params()
+
+        if dtype not in ("f32", "f64"):
+            raise ValueError("dtype must be 'f32' or 'f64'")
+        self.dtype = dtype
+        self._dt = _lib.PK_DTYPE_F64 if dtype == "f64" else _lib.PK_DTYPE_F32
+        self._noise = noise
+        if not (noise in ("numpy", "philox") or callable(noise)):
+            raise ValueError("noise must be 'numpy', 'philox' or a callable")
+        self._seed = int(seed)
+        self._frame = 0
+        self._uniform = uniform if uniform is not None else _pyrandom.random
+        self.particle_offset = 0       # global index of local particle 0 (sharded filters)
+
+        preset_features = list(preset_features)
+        n = len(preset_features)
+        self.capacity = int(capacity) if capacity is not None else n
+        if self.capacity < n:
+            raise ValueError("capacity smaller than the preset map")
+        self._alloc()
+        self._load_presets(preset_features)
+        self.particles = ParticleList(self)           # :42-49
+        self.last_stats = {}
+        self.last_assoc = None
+        self.last_ancestors = None
+        self.keep_trace = False
+
+    # -- allocation ------------------------------------------------------------------------------
+    def _alloc(self):
+        torch, M, dev = self._torch, self.num_particles, self._device
+        lib = self._lib
+        self.block_bytes = int(lib.pk_block_bytes(self.capacity, self._dt))
+        f64, i32, i64 = torch.float64, torch.int32, torch.int64
+        self._pose = [torch.zeros((M, 4), dtype=f64, device=dev) for _ in range(2)]
+        self._aux = [torch.zeros((M, 2), dtype=i32, device=dev) for _ in range(2)]
+        self._slot = [torch.zeros((M,), dtype=i32, device=dev) for _ in range(2)]
+        self._cur = 0
+        self._pool = torch.zeros((max(1, M * self.block_bytes),), dtype=torch.uint8, device=dev)
+        nb = int(lib.pk_num_scan_blocks(max(M, 1)))
+        self._nb = nb
+        self._cumsum = torch.zeros((max(M, 1),), dtype=f64, device=dev)
+        self._block_sums = torch.zeros((nb,), dtype=f64, device=dev)
+        self._plan = torch.zeros((_lib.PK_PLAN_DOUBLES,), dtype=f64, device=dev)
+        self._block_prefix = torch.zeros((nb, 2), dtype=f64, device=dev)
+        self._block_count = torch.zeros((nb + 1,), dtype=i64, device=dev)
+        self._out_lo = torch.zeros((max(M, 1),), dtype=i64, device=dev)
+        self._offspring = torch.zeros((max(M, 1),), dtype=i32, device=dev)
+        self._ancestors = torch.zeros((max(M, 1),), dtype=i64, device=dev)
+        self._big_runs = torch.zeros((4 + 3 * (M // 16 + 2),), dtype=i64, device=dev)
+        self._gather_ws = torch.zeros((max(256, int(lib.pk_gather_workspace_bytes(max(M, 1)))),),
+                                      dtype=torch.uint8, device=dev)
+        self._n_copied = torch.zeros((1,), dtype=i64, device=dev)
+        self._stats = torch.zeros((_lib.PK_NUM_STATS,), dtype=i64, device=dev)
+        self._red_ws = torch.zeros((5 * 1024,), dtype=f64, device=dev)
+        self._out5 = torch.zeros((5,), dtype=f64, device=dev)
+        self._best2 = torch.zeros((2,), dtype=f64, device=dev)
+        self._assoc = None
+        self._noise_pinned = None
+        self._noise_dev = None
+
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self._device).cuda_stream)
+
+    @property
+    def pose(self):
+        """Device tensor [M,4]: x, y, heading, weight (current buffer)."""
+        return self._pose[self._cur]
+
+    @property
+    def aux(self):
+        return self._aux[self._cur]
+
+    @property
+    def slot(self):
+        return self._slot[self._cur]
+
+    def _load_presets(self, features):
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        n, mean5, covp, covc, meta, ids = _feature_arrays(features, max(self.capacity, 1))
+        with torch.cuda.device(self._device):
+            _lib.check(lib.pk_init_particles(_lib.ptr(self.pose), _lib.ptr(self.slot), _lib.ptr(self.aux), M, n,
+                                             1 + n, self._stream()), "pk_init_particles")
+            if n and M:
+                d = [torch.from_numpy(a).to(self._device) for a in (mean5, covp, covc, meta, ids)]
+                _lib.check(lib.pk_map_broadcast(_lib.ptr(self._pool), self.capacity, self._dt, 0, M, n,
+                                                *[_lib.ptr(t) for t in d], self._stream()), "pk_map_broadcast")
+                torch.cuda.current_stream(self._device).synchronize()
+
+    # -- frame driver: cam_cb (:59-137) ------------------------------------------------------------
+    def cam_cb(self, ros_view):
+        """One measurement frame: motion update with the last control (``:75-77``), association
+        of all blobs then the sequential EKF updates and weight product (``:84-124``), then the
+        low-variance resample (``:137``)."""
+        with self._lock:
+            if self.num_particles == 0:
+                return
+            self.motion_update(self.last_control)
+            scan = ros_view.last_sensor_reading
+            obs = self._scan_to_array(scan)
+            self.measurement_update(obs)
+            self.low_variance_resample()
+
+    @staticmethod
+    def _scan_to_array(scan):
+        """K x (bearing, r, g, b) from ``scan.observes`` (``:344``, ``matrix.py:35-39``)."""
+        if scan is None:
+            raise AttributeError("'NoneType' object has no attribute 'observes'")
+        if isinstance(scan, np.ndarray):
+            return np.ascontiguousarray(scan, dtype=np.float64).reshape(-1, 4)
+        blobs = scan.observes
+        obs = np.empty((len(blobs), 4), dtype=np.float64)
+        for k, b in enumerate(blobs):
+            obs[k, 0] = b.bearing
+            obs[k, 1] = b.color.r
+            obs[k, 2] = b.color.g
+            obs[k, 3] = b.color.b
+        return obs
+
+    def measurement_update(self, obs):
+        """The per-particle body of ``cam_cb`` (``:73, :84-124``) for a ``[K,4]`` host array of
+        blobs, as ONE fused kernel.  Also the v1 core's name for the same step
+        (``prkt_core.py:159-236``)."""
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 4)
+        K = obs.shape[0]
+        if K > _lib.PK_MAX_OBS:
+            raise ValueError("at most %d blobs per frame (got %d)" % (_lib.PK_MAX_OBS, K))
+        with self._lock, torch.cuda.device(self._device):
+            if self._assoc is None or self._assoc.shape[1] != K:
+                self._assoc = torch.zeros((M, max(K, 1)), dtype=torch.int32, device=self._device)
+            self._stats.zero_()
+            _lib.check(lib.pk_measurement_update(
+                _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
+                self.capacity, self._dt, M, obs.ctypes.data, K, ctypes.byref(self.params),
+                _lib.ptr(self._assoc), _lib.ptr(self._stats), self._stream()), "pk_measurement_update")
+            self._last_K = K
+            if self.keep_trace:
+                self.last_assoc = self._assoc[:, :K].clone()
+                self.last_weight = self.pose[:, 3].clone()
+                self.last_pose_pre = self.pose[:, :3].clone()
+
+    cam_observation_update = measurement_update       # v1 lineage name (prkt_core.py:205)
+
+    # -- motion: motion_update / motion_model (:148-208) -------------------------------------------
+    def motion_update(self, new_twist):
+        """``:148-166``: integrate the PREVIOUS control over ``now - last_update`` for every
+        particle, then store the new control."""
+        with self._lock:
+            dt = self._clock() - self.last_update                     # :158
+            self._motion_all(self.last_control, dt.to_sec())          # :159-163
+            self.last_update = self.last_update + dt                  # :165
+            self.last_control = new_twist                             # :166
+
+    def _draw_noise(self, M):
+        if self._noise == "philox":
+            return None
+        if self._noise == "numpy":
+            z = np.random.standard_normal((M, 3))
+        else:
+            z = np.ascontiguousarray(self._noise(M), dtype=np.float64)
+            if z.shape != (M, 3):
+                raise ValueError("noise callable must return an [M,3] array")
+        return z
+
+    def _motion_all(self, twist, dt):
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        if M == 0:
+            return
+        v = float(twist.linear.x)                                     # :176
+        w = float(twist.angular.z)                                    # :177
+        with torch.cuda.device(self._device):
+            z = self._draw_noise(M)
+            nptr = 0
+            if z is not None:
+                if self._noise_pinned is None:
+                    self._noise_pinned = torch.empty((M, 3), dtype=torch.float64, pin_memory=True)
+                    self._noise_dev = torch.empty((M, 3), dtype=torch.float64, device=self._device)
+                self._noise_pinned.numpy()[...] = z
+                self._noise_dev.copy_(self._noise_pinned, non_blocking=True)
+                nptr = _lib.ptr(self._noise_dev)
+            _lib.check(lib.pk_motion_update(_lib.ptr(self.pose), M, nptr, self._seed, self._frame,
+                                            self.particle_offset, v, w, float(dt), self._stream()),
+                       "pk_motion_update")
+            self._frame += 1
+            if z is not None:
+                # the pinned staging buffer is reused next frame
+                torch.cuda.current_stream(self._device).synchronize()
+
+    def motion_model(self, particle, twist, dt):
+        """``:168-208`` for ONE host-side particle (the form ``test_prkt_ros2.py:53`` calls):
+        returns a new ``FilterParticle``; the arithmetic runs in the motion kernel."""
+        import copy
+        torch, lib = self._torch, self._lib
+        dt = dt.to_sec()                                              # :174
+        new_particle = copy.deepcopy(particle)                        # :181
+        pos = particle.state.pose.pose.position
+        heading = particle.heading if isinstance(particle, FilterParticle) else FilterParticle.heading.fget(particle)
+        with self._lock, torch.cuda.device(self._device):
+            rec = torch.tensor([[float(pos.x), float(pos.y), float(heading), 1.0]], dtype=torch.float64,
+                               device=self._device)
+            z = self._draw_noise(1)
+            zt = None if z is None else torch.from_numpy(z).to(self._device)
+            _lib.check(lib.pk_motion_update(_lib.ptr(rec), 1, _lib.ptr(zt), self._seed, self._frame, 0,
+                                            float(twist.linear.x), float(twist.angular.z), float(dt),
+                                            self._stream()), "pk_motion_update")
+            out = rec.cpu().numpy()[0]
+        new_particle.state.pose.pose.position.x = float(out[0])
+        new_particle.state.pose.pose.position.y = float(out[1])
+        new_particle.state.pose.pose.orientation = heading_to_quaternion(float(out[2]))
+        return new_particle
+
+    # -- resampling: low_variance_resample (:210-252) ----------------------------------------------
+    def low_variance_resample(self):
+        """Systematic resampling, every frame, one uniform draw (``:226``)."""
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        if M == 0:
+            return
+        with self._lock, torch.cuda.device(self._device):
+            u01 = float(self._uniform())
+            st = self._stream()
+            cur, nxt = self._cur, 1 - self._cur
+            _lib.check(lib.pk_weight_scan(_lib.ptr(self._pose[cur]), M, _lib.ptr(self._cumsum),
+                                          _lib.ptr(self._block_sums), st), "pk_weight_scan")
+            _lib.check(lib.pk_resample_thresholds(_lib.ptr(self._block_sums), self._nb, M, u01,
+                                                  _lib.ptr(self._plan), _lib.ptr(self._block_prefix),
+                                                  _lib.ptr(self._block_count), st), "pk_resample_thresholds")
+            _lib.check(lib.pk_resample_ancestors(_lib.ptr(self._cumsum), M, 0, 0, _lib.ptr(self._plan),
+                                                 _lib.ptr(self._block_prefix), _lib.ptr(self._block_count), M, 0, M,
+                                                 _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
+                                                 _lib.ptr(self._ancestors), _lib.ptr(self._big_runs), st),
+                       "pk_resample_ancestors")
+            _lib.check(lib.pk_resample_gather(_lib.ptr(self._ancestors), _lib.ptr(self._offspring), M,
+                                              _lib.ptr(self._pose[cur]), _lib.ptr(self._pose[nxt]),
+                                              _lib.ptr(self._aux[cur]), _lib.ptr(self._aux[nxt]),
+                                              _lib.ptr(self._slot[cur]), _lib.ptr(self._slot[nxt]),
+                                              _lib.ptr(self._pool), self.capacity, self._dt,
+                                              _lib.ptr(self._gather_ws), _lib.ptr(self._n_copied), st),
+                       "pk_resample_gather")
+            self._cur = nxt
+            if self.keep_trace:
+                self.last_ancestors = self._ancestors.clone()
+
+    # -- queries -------------------------------------------------------------------------------------
+    def summary(self):
+        """``:254-276``: unweighted mean x, mean y and circular-mean heading."""
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        with self._lock, torch.cuda.device(self._device):
+            _lib.check(lib.pk_summary_partial(_lib.ptr(self.pose), M, _lib.ptr(self._out5), _lib.ptr(self._red_ws),
+                                              self._stream()), "pk_summary_partial")
+            s = self._out5.cpu().numpy()
+        count = float(M)
+        return (float(s[0] / count), float(s[1] / count), math.atan2(float(s[2]), float(s[3])),)
+
+    def best_particle(self):
+        """Additive API: (index, weight) of the first particle with the largest weight (weights
+        are those of the last measurement update; after resampling they are the ancestors')."""
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        with self._lock, torch.cuda.device(self._device):
+            _lib.check(lib.pk_best_particle(_lib.ptr(self.pose), M, _lib.ptr(self._best2), _lib.ptr(self._red_ws),
+                                            self._stream()), "pk_best_particle")
+            b = self._best2.cpu().numpy()
+        return int(b[1]), float(b[0])
+
+    def stats(self):
+        """Counters of the last measurement update (matched / unmatched pairs, exact likelihood
+        evaluations, flags) and the number of landmark blocks copied by the last resample."""
+        s = self._stats.cpu().numpy()
+        return dict(matched=int(s[_lib.PK_STAT_MATCHED]), unmatched=int(s[_lib.PK_STAT_UNMATCHED]),
+                    evaluated=int(s[_lib.PK_STAT_EVALUATED]), flags=int(s[_lib.PK_STAT_FLAGS]),
+                    same_landmark=int(s[_lib.PK_STAT_SAME_LANDMARK]), promoted=int(s[_lib.PK_STAT_PROMOTED]),
+                    blocks_copied=int(self._n_copied.item()))
+
+    def export_maps(self, lo=0, count=None):
+        """Landmark state of particles [lo, lo+count) as fp64 NumPy arrays
+        (mean [c,N,5], covp [c,N,2,2], covc [c,N,3,3], meta [c,N], ids [c,N], n_live [c])."""
+        torch, lib = self._torch, self._lib
+        count = self.num_particles - lo if count is None else count
+        N = max(self.capacity, 1)
+        dev = self._device
+        with self._lock, torch.cuda.device(dev):
+            mean5 = torch.zeros((count, N, 5), dtype=torch.float64, device=dev)
+            covp = torch.zeros((count, N, 4), dtype=torch.float64, device=dev)
+            covc = torch.zeros((count, N, 9), dtype=torch.float64, device=dev)
+            meta = torch.zeros((count, N), dtype=torch.int32, device=dev)
+            ids = torch.zeros((count, N), dtype=torch.int32, device=dev)
+            if self.capacity and count:
+                _lib.check(lib.pk_map_export(_lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self.slot), lo,
+                                             count, _lib.ptr(mean5), _lib.ptr(covp), _lib.ptr(covc), _lib.ptr(meta),
+                                             _lib.ptr(ids), self._stream()), "pk_map_export")
+            nlive = self.aux[lo:lo + count, 0].cpu().numpy()
+            return (mean5.cpu().numpy(), covp.cpu().numpy().reshape(count, N, 2, 2),
+                    covc.cpu().numpy().reshape(count, N, 3, 3), meta.cpu().numpy(), ids.cpu().numpy(), nlive)
+
+    def get_map(self, i):
+        """Additive API: ``{id: Feature}`` of particle ``i`` (full and potential landmarks)."""
+        p = self._particle_view(i)
+        out = dict(p.feature_set)
+        out.update(p.potential_features)
+        return out
+
+    def _particle_view(self, i):
+        mean5, covp, covc, meta, ids, nlive = self.export_maps(i, 1)
+        rec = self.pose[i].cpu().numpy()
+        aux = self.aux[i].cpu().numpy()
+        p = FilterParticle()
+        p.state.pose.pose.position.x = float(rec[0])
+        p.state.pose.pose.position.y = float(rec[1])
+        p.state.pose.pose.orientation = heading_to_quaternion(float(rec[2]))
+        p.weight = float(rec[3])
+        p.next_id = int(aux[1])
+        for j in range(int(nlive[0])):
+            f = _feature_from_arrays(mean5[0, j], covp[0, j], covc[0, j], meta[0, j])
+            if int(meta[0, j]) & _lib.PK_META_POTENTIAL:
+                p.potential_features[int(ids[0, j])] = f
+            else:
+                p.feature_set[int(ids[0, j])] = f
+        return p
+
+    def state_dict(self):
+        """Checkpoint of the device state (host tensors)."""
+        return dict(pose=self.pose.cpu(), aux=self.aux.cpu(), slot=self.slot.cpu(), pool=self._pool.cpu(),
+                    frame=self._frame, capacity=self.capacity, dtype=self.dtype)
+
+    def load_state_dict(self, sd):
+        if sd["capacity"] != self.capacity or sd["dtype"] != self.dtype:
+            raise ValueError("checkpoint layout mismatch")
+        self.pose.copy_(sd["pose"])
+        self.aux.copy_(sd["aux"])
+        self.slot.copy_(sd["slot"])
+        self._pool.copy_(sd["pool"])
+        self._frame = int(sd["frame"])

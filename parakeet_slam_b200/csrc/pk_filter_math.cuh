@@ -1,0 +1,163 @@
+// fp64 per-landmark math shared by the fused measurement kernel (pk_measure.cu) and the
+// single-call probe entry points (pk_probe.cu): probability_of_match and one EKF update.
+#pragma once
+
+#include <math.h>
+
+#include "pk_common.cuh"
+
+namespace pk {
+
+constexpr double kLog2Pi = 1.8378770664093453;  // math.log(2*pi)
+
+// ---------------------------------------------------------------------------------------------
+// probability_of_match, exact fp64 (reference :383-455 with :457-544 inlined).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double match_likelihood(const Landmark& L, double px, double py, double pth, double beta,
+                                                   double orr, double og, double ob, double dirx, double diry,
+                                                   const pk_params& prm, unsigned& flags) {
+    // colour gate :425-427, :441
+    double dr = orr - L.r, dg = og - L.g, db = ob - L.b;
+    double cdist = dr * dr + dg * dg + db * db;
+    if (fabs(cdist) > prm.color_gate) return 0.0;
+    // bearing gate :408-415, :433
+    double dx = L.x - px, dy = L.y - py;
+    double pse = atan2(dy, dx);
+    double del = beta - (pse - pth);
+    if (fabs(del) > prm.bearing_gate) return 0.0;
+    // prob_position_match :473-475 (robot-frame bearing used as if world frame, finding F4c)
+    if (fabs(pse - beta) > prm.position_gate) return 0.0;
+    // closest_point :509-522
+    double t = dx * dirx + dy * diry;
+    double nx = (t < 0.0) ? px : px + dirx * t;
+    double ny = (t < 0.0) ? py : py + diry * t;
+    double ex = nx - L.x, ey = ny - L.y;
+    // 2-D pdf, covariance symmetrised from the LOWER triangle (scipy eigh(lower=True)) :482-490
+    double a = L.sp[0], b10 = L.sp[2], d = L.sp[3];
+    double det2 = a * d - b10 * b10;
+    double maha2 = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det2;
+    double bp = exp(-0.5 * (2.0 * kLog2Pi + log(det2) + maha2));
+    // 3-D colour pdf :530-544, lower triangle
+    double A = L.sc[0], B = L.sc[3], C = L.sc[6], D = L.sc[4], E = L.sc[7], F = L.sc[8];
+    double c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
+    double c11 = A * F - C * C, c12 = B * C - A * E, c22 = A * D - B * B;
+    double det3 = A * c00 + B * c01 + C * c02;
+    double maha3 = (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0 * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
+    double cp = exp(-0.5 * (3.0 * kLog2Pi + log(det3) + maha3));
+    if (!(det2 > 0.0) || !(det3 > 0.0)) flags |= PK_FLAG_SINGULAR_COV;
+    // :439, :446, :455
+    return (500.0 * bp) * (500.0 * cp) / 250000.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One EKF update of landmark j with blob k, block form of reference :98-124.
+// Returns the weight factor; writes the landmark back unless it is immutable.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double py, double beta, double orr, double og,
+                                                double ob, const pk_params& prm, int& id_out, unsigned& flags,
+                                                int& promoted, bool& changed_out) {
+    id_out = L.id;
+    const double qt = prm.qt_diag;
+    // measurement_jacobian :785-797 (sign and order as written, finding F4b)
+    double dx = L.x - px, dy = L.y - py;
+    double q = dx * dx + dy * dy;
+    double hx = (q == 0.0) ? 0.0 : dy / q;
+    double hy = (q == 0.0) ? 0.0 : dx / q;
+    // generate_measurement :871 -- world-frame bearing, no heading subtraction (finding F4a)
+    double zb = atan2(dy, dx);
+    double a = L.sp[0], b = L.sp[1], c = L.sp[2], d = L.sp[3];
+    // measurement_covariance :817-819   Q = H Sigma H^T + Qt = diag(s) (+) Sc
+    double t0 = hx * a + hy * c, t1 = hx * b + hy * d;
+    double s = t0 * hx + t1 * hy + qt;
+    double S00 = L.sc[0] + qt, S01 = L.sc[1], S02 = L.sc[2];
+    double S10 = L.sc[3], S11 = L.sc[4] + qt, S12 = L.sc[5];
+    double S20 = L.sc[6], S21 = L.sc[7], S22 = L.sc[8] + qt;
+    // inverse(Q) :102 -- 1x1 block and general 3x3 block
+    double inv_s = 1.0 / s;
+    double C00 = S11 * S22 - S12 * S21, C01 = S12 * S20 - S10 * S22, C02 = S10 * S21 - S11 * S20;
+    double detS = S00 * C00 + S01 * C01 + S02 * C02;
+    if (!(detS != 0.0)) flags |= PK_FLAG_SINGULAR_COV;
+    double idet = 1.0 / detS;
+    double I00 = C00 * idet, I01 = (S02 * S21 - S01 * S22) * idet, I02 = (S01 * S12 - S02 * S11) * idet;
+    double I10 = C01 * idet, I11 = (S00 * S22 - S02 * S20) * idet, I12 = (S02 * S10 - S00 * S12) * idet;
+    double I20 = C02 * idet, I21 = (S01 * S20 - S00 * S21) * idet, I22 = (S00 * S11 - S01 * S10) * idet;
+    // innovation :911 / :846 -- no angle wrapping (finding F4e)
+    double d0 = beta - zb, d1 = orr - L.r, d2 = og - L.g, d3 = ob - L.b;
+    // importance_factor :844-849 with the PRE-update Q and z-hat; Frobenius norm of Q (F4d)
+    double fro = sqrt(s * s + S00 * S00 + S01 * S01 + S02 * S02 + S10 * S10 + S11 * S11 + S12 * S12 + S20 * S20 +
+                      S21 * S21 + S22 * S22);
+    double y1 = d1 * I00 + d2 * I10 + d3 * I20;  // (delz^T Qinv) colour part
+    double y2 = d1 * I01 + d2 * I11 + d3 * I21;
+    double y3 = d1 * I02 + d2 * I12 + d3 * I22;
+    double maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
+    double factor = (1.0 / sqrt(2.0 * 3.141592653589793 * fro)) * exp(-0.5 * maha);
+
+    bool changed = false;
+    if (!(L.meta & PK_META_IMMUTABLE)) {
+        // kalman_gain :833   K = Sigma H^T Qinv
+        double kp0 = (a * hx + b * hy) * inv_s, kp1 = (c * hx + d * hy) * inv_s;
+        const double* sc = L.sc;
+        double K00 = sc[0] * I00 + sc[1] * I10 + sc[2] * I20, K01 = sc[0] * I01 + sc[1] * I11 + sc[2] * I21,
+               K02 = sc[0] * I02 + sc[1] * I12 + sc[2] * I22;
+        double K10 = sc[3] * I00 + sc[4] * I10 + sc[5] * I20, K11 = sc[3] * I01 + sc[4] * I11 + sc[5] * I21,
+               K12 = sc[3] * I02 + sc[4] * I12 + sc[5] * I22;
+        double K20 = sc[6] * I00 + sc[7] * I10 + sc[8] * I20, K21 = sc[6] * I01 + sc[7] * I11 + sc[8] * I21,
+               K22 = sc[6] * I02 + sc[7] * I12 + sc[8] * I22;
+        // update_mean :909-914
+        L.x += kp0 * d0;
+        L.y += kp1 * d0;
+        L.r += K00 * d1 + K01 * d2 + K02 * d3;
+        L.g += K10 * d1 + K11 * d2 + K12 * d3;
+        L.b += K20 * d1 + K21 * d2 + K22 * d3;
+        // update_covar :926-930   Sigma <- (I - K H) Sigma
+        double m00 = 1.0 - kp0 * hx, m01 = -(kp0 * hy), m10 = -(kp1 * hx), m11 = 1.0 - kp1 * hy;
+        L.sp[0] = m00 * a + m01 * c;
+        L.sp[1] = m00 * b + m01 * d;
+        L.sp[2] = m10 * a + m11 * c;
+        L.sp[3] = m10 * b + m11 * d;
+        double A00 = 1.0 - K00, A01 = -K01, A02 = -K02;
+        double A10 = -K10, A11 = 1.0 - K11, A12 = -K12;
+        double A20 = -K20, A21 = -K21, A22 = 1.0 - K22;
+        double n0 = A00 * sc[0] + A01 * sc[3] + A02 * sc[6], n1 = A00 * sc[1] + A01 * sc[4] + A02 * sc[7],
+               n2 = A00 * sc[2] + A01 * sc[5] + A02 * sc[8];
+        double n3 = A10 * sc[0] + A11 * sc[3] + A12 * sc[6], n4 = A10 * sc[1] + A11 * sc[4] + A12 * sc[7],
+               n5 = A10 * sc[2] + A11 * sc[5] + A12 * sc[8];
+        double n6 = A20 * sc[0] + A21 * sc[3] + A22 * sc[6], n7 = A20 * sc[1] + A21 * sc[4] + A22 * sc[7],
+               n8 = A20 * sc[2] + A21 * sc[5] + A22 * sc[8];
+        L.sc[0] = n0; L.sc[1] = n1; L.sc[2] = n2;
+        L.sc[3] = n3; L.sc[4] = n4; L.sc[5] = n5;
+        L.sc[6] = n6; L.sc[7] = n7; L.sc[8] = n8;
+        int cnt = (L.meta & PK_META_COUNT_MASK) + 2;  // :914 and :930, +1 each
+        if (cnt > PK_META_COUNT_MASK) cnt = PK_META_COUNT_MASK;
+        L.meta = (L.meta & ~PK_META_COUNT_MASK) | cnt;
+        changed = true;
+    }
+    if (id_out < 0) {
+        // potential feature :109-118: weight as if unseen; promote when update_count > 5
+        factor = prm.no_match_weight;
+        if (L.meta & PK_META_POTENTIAL) {
+            if ((L.meta & PK_META_COUNT_MASK) > prm.promote_count) {
+                L.meta &= ~PK_META_POTENTIAL;
+                L.id = -L.id;
+                promoted += 1;
+                changed = true;
+            }
+        }
+    }
+    changed_out = changed;
+    return factor;
+}
+
+template <typename T>
+__device__ __forceinline__ double ekf_update(unsigned char* block, int capacity, int j, double px, double py,
+                                             double beta, double orr, double og, double ob, const pk_params& prm,
+                                             int& id_out, unsigned& flags, int& promoted) {
+    Landmark L;
+    load_landmark<T>(block, capacity, j, L);
+    bool changed = false;
+    const double factor = ekf_update_lm(L, px, py, beta, orr, og, ob, prm, id_out, flags, promoted, changed);
+    if (changed) store_landmark<T>(block, capacity, j, L);
+    return factor;
+}
+
+}  // namespace pk

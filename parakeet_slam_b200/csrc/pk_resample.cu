@@ -1,0 +1,654 @@
+// K3/K4/K5/K6 -- weight normaliser, systematic (low-variance) resampling plan, copy-on-resample
+// gather and the pose summary.
+//
+// Replaces FastSLAM.low_variance_resample (reference prkt_core_v2.py:210-252) and
+// FastSLAM.summary (:254-276).  The reference sweeps the particle list once with a running
+// `step` (:238-250); that is `ancestor[k] = min{ i : C_i >= u0 + k*r }` with C the prefix sum of
+// the weights, r = sum/M, u0 = random()*r (SURVEY.md finding F6).  Here:
+//
+//   K3a  one warp per block of PK_SCAN_BLOCK particles: fp64 inclusive prefix sums that are
+//        monotone by construction (each lane folds 32 consecutive weights left to right, lane
+//        bases are a left fold of the lane totals);
+//   K3b  one CTA folds the block totals of ALL shards, in global block order and with a fixed
+//        tree, into double-double block prefixes -> total, r, u0 and the number of outputs emitted
+//        before every block.  Nothing depends on how many GPUs the particles are spread over;
+//   K4   one thread per particle: its run of output slots is [N(C_{i-1}), N(C_i)) with
+//        N(C) = #{k : u0 + k*r <= C}, evaluated in double-double against the block prefix.  No
+//        search, no atomics on the common path; runs longer than 16 go to a fill kernel;
+//   K5   survivors keep their landmark block; each additional copy goes into the block of a
+//        particle that died (an exclusive scan of the dead flags pairs them up), moved by TMA
+//        bulk copies global -> shared -> global.  This is the deepcopy of :243.
+#include "pk_common.cuh"
+
+namespace pk {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kScanWarps = 4;
+constexpr int kGroupBlocks = 32;   // scan blocks folded sequentially by one thread in K3b
+constexpr int kMaxScanGroups = 1024;
+
+__device__ __forceinline__ int padded(int e) { return e + (e >> 5); }
+
+// ---------------------------------------------------------------------------------------------
+// K3a
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanWarps * 32)
+weight_scan_kernel(const double* __restrict__ pose4, long long M, double* __restrict__ cumsum,
+                   double* __restrict__ block_sums, long long nb) {
+    __shared__ double sm[kScanWarps][PK_SCAN_BLOCK + 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long blk = (long long)blockIdx.x * kScanWarps + warp;
+    if (blk >= nb) return;
+    const long long base = blk * PK_SCAN_BLOCK;
+    const int n = (int)min((long long)PK_SCAN_BLOCK, M - base);
+    double* s = sm[warp];
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+        const int e = it * 32 + lane;
+        s[padded(e)] = (e < n) ? pose4[4 * (base + e) + 3] : 0.0;
+    }
+    __syncwarp();
+    double run = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const int e = padded(32 * lane + j);
+        run = __dadd_rn(run, s[e]);   // left fold, as sum_ += weight (:218-220)
+        s[e] = run;
+    }
+    const double total = run;
+    double b = 0.0;
+    for (int l = 0; l < 31; ++l) {
+        const double t = __shfl_sync(kFullMask, total, l);
+        if (lane > l) b = __dadd_rn(b, t);
+    }
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const int e = padded(32 * lane + j);
+        s[e] = __dadd_rn(b, s[e]);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+        const int e = it * 32 + lane;
+        if (e < n) cumsum[base + e] = s[padded(e)];
+    }
+    if (lane == 31) block_sums[blk] = __dadd_rn(b, total);
+}
+
+// number of outputs k in [0, M) with u0 + k*r <= P + c   (P double-double block prefix)
+__device__ __forceinline__ long long count_le(dd P, double c, double u0, double r, long long M) {
+    if (!(r > 0.0)) return M;  // all-zero weights: step == 0 <= 0, particle 0 is emitted M times (:239)
+    const dd t = dd_add_d(P, c);
+    const double x = (t.hi - u0) + t.lo;
+    double kq = floor(x / r);
+    if (!(kq >= -1.0)) kq = -1.0;
+    if (kq > (double)(M - 1)) kq = (double)(M - 1);
+    long long k = (long long)kq;
+    auto pred = [&](long long kk) { return (fma((double)kk, r, u0) - t.hi) <= t.lo; };
+    for (int it = 0; it < 64 && k + 1 < M && pred(k + 1); ++it) ++k;
+    for (int it = 0; it < 64 && k >= 0 && !pred(k); ++it) --k;
+    return k + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b  (single CTA of 1024 threads)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_total, double u01,
+                  double* __restrict__ plan, double* __restrict__ block_prefix, long long* __restrict__ block_count) {
+    __shared__ double g_hi[kMaxScanGroups], g_lo[kMaxScanGroups];
+    __shared__ long long g_cnt[kMaxScanGroups];
+    __shared__ double s_r, s_u0;
+    const int t = threadIdx.x;
+    const long long ngroups = (nb + kGroupBlocks - 1) / kGroupBlocks;
+    const long long b0 = (long long)t * kGroupBlocks;
+    const long long b1 = min(nb, b0 + kGroupBlocks);
+    // phase A: per-thread sequential double-double fold of its group's block totals
+    dd acc{0.0, 0.0};
+    if (t < ngroups) {
+        for (long long b = b0; b < b1; ++b) {
+            block_prefix[2 * b] = acc.hi;  // local exclusive prefix for now
+            block_prefix[2 * b + 1] = acc.lo;
+            acc = dd_add_d(acc, sums[b]);
+        }
+        g_hi[t] = acc.hi;
+        g_lo[t] = acc.lo;
+    }
+    __syncthreads();
+    // phase B: one thread folds the group totals in order
+    if (t == 0) {
+        dd run{0.0, 0.0};
+        for (long long g = 0; g < ngroups; ++g) {
+            const dd cur{g_hi[g], g_lo[g]};
+            g_hi[g] = run.hi;
+            g_lo[g] = run.lo;
+            run = dd_add(run, cur);
+        }
+        const double total = run.hi + run.lo;
+        const double r = total / (double)M_total;  // range_ = sum_/float(len(particles)) :225
+        const double u0 = u01 * r;                 // step = random()*range_             :226
+        s_r = r;
+        s_u0 = u0;
+        plan[0] = total;
+        plan[1] = r;
+        plan[2] = u0;
+        plan[3] = run.hi;
+        plan[4] = run.lo;
+        plan[5] = (double)M_total;
+        plan[6] = u01;
+        plan[7] = 0.0;
+    }
+    __syncthreads();
+    // phase C: global block prefixes, and the emitted-output count at the end of every block
+    const double r = s_r, u0 = s_u0;
+    long long runmax = 0;
+    if (t < ngroups) {
+        const dd gb{g_hi[t], g_lo[t]};
+        for (long long b = b0; b < b1; ++b) {
+            const dd P = dd_add(gb, dd{block_prefix[2 * b], block_prefix[2 * b + 1]});
+            block_prefix[2 * b] = P.hi;
+            block_prefix[2 * b + 1] = P.lo;
+            const long long e = count_le(P, sums[b], u0, r, M_total);
+            runmax = max(runmax, e);
+            block_count[b + 1] = runmax;  // local running max for now
+        }
+        g_cnt[t] = runmax;
+    }
+    __syncthreads();
+    if (t == 0) {
+        long long run = 0;
+        for (long long g = 0; g < ngroups; ++g) {
+            const long long cur = g_cnt[g];
+            g_cnt[g] = run;
+            run = max(run, cur);
+        }
+        block_count[0] = 0;
+    }
+    __syncthreads();
+    if (t < ngroups) {
+        const long long gbase = g_cnt[t];
+        for (long long b = b0; b < b1; ++b) {
+            long long v = max(block_count[b + 1], gbase);
+            if (b == nb - 1) v = M_total;  // every output slot is assigned
+            block_count[b + 1] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4
+// ---------------------------------------------------------------------------------------------
+constexpr int kInlineRun = 16;
+
+__global__ void __launch_bounds__(256)
+ancestors_kernel(const double* __restrict__ cumsum, long long M_local, long long particle_offset, long long block_offset,
+                 const double* __restrict__ plan, const double* __restrict__ block_prefix,
+                 const long long* __restrict__ block_count, long long M_total, long long out_offset, long long n_out,
+                 long long* __restrict__ out_lo, int* __restrict__ offspring, long long* __restrict__ ancestors,
+                 long long* __restrict__ big_runs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M_local) return;
+    const double r = plan[1], u0 = plan[2];
+    const long long b = block_offset + i / PK_SCAN_BLOCK;
+    const int within = (int)(i % PK_SCAN_BLOCK);
+    const dd P{block_prefix[2 * b], block_prefix[2 * b + 1]};
+    const long long c_lo = block_count[b], c_hi = block_count[b + 1];
+    const long long gi = particle_offset + i;
+    const bool last = (within == PK_SCAN_BLOCK - 1) || (gi == M_total - 1);
+    long long hi = last ? c_hi : min(max(count_le(P, cumsum[i], u0, r, M_total), c_lo), c_hi);
+    long long lo = (within == 0) ? c_lo : min(max(count_le(P, cumsum[i - 1], u0, r, M_total), c_lo), c_hi);
+    if (hi < lo) hi = lo;
+    out_lo[i] = lo;
+    offspring[i] = (int)(hi - lo);
+    const long long klo = max(lo, out_offset), khi = min(hi, out_offset + n_out);
+    if (khi - klo <= kInlineRun) {
+        for (long long k = klo; k < khi; ++k) ancestors[k - out_offset] = gi;
+    } else {
+        const unsigned long long idx = atomicAdd(reinterpret_cast<unsigned long long*>(big_runs), 1ull);
+        big_runs[4 + 3 * idx + 0] = gi;
+        big_runs[4 + 3 * idx + 1] = klo - out_offset;
+        big_runs[4 + 3 * idx + 2] = khi - out_offset;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fill_runs_kernel(const long long* __restrict__ big_runs, long long* __restrict__ ancestors) {
+    const long long n = big_runs[0];
+    for (long long run = blockIdx.x; run < n; run += gridDim.x) {
+        const long long gi = big_runs[4 + 3 * run], klo = big_runs[4 + 3 * run + 1], khi = big_runs[4 + 3 * run + 2];
+        for (long long k = klo + threadIdx.x; k < khi; k += blockDim.x) ancestors[k] = gi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: pairing of extra copies with dead particles' blocks
+// ---------------------------------------------------------------------------------------------
+// G1: one warp per 1024 particles: exclusive count of dead particles inside the block + block total
+__global__ void __launch_bounds__(kScanWarps * 32)
+dead_scan_kernel(const int* __restrict__ offspring, long long M, int* __restrict__ dead_excl, int* __restrict__ block_dead,
+                 long long nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long blk = (long long)blockIdx.x * kScanWarps + warp;
+    if (blk >= nb) return;
+    const long long base = blk * PK_SCAN_BLOCK;
+    int run = 0;
+    for (int it = 0; it < 32; ++it) {
+        const long long i = base + it * 32 + lane;
+        const int dead = (i < M && offspring[i] == 0) ? 1 : 0;
+        const unsigned bal = __ballot_sync(kFullMask, dead);
+        if (i < M) dead_excl[i] = run + __popc(bal & lanemask_lt());
+        run += __popc(bal);
+    }
+    if (lane == 0) block_dead[blk] = run;
+}
+
+// G2: exclusive scan of the block totals (single CTA)
+__global__ void __launch_bounds__(1024)
+block_offsets_kernel(const int* __restrict__ block_dead, long long nb, int* __restrict__ block_off,
+                     long long* __restrict__ total_out) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const long long per = (nb + 1023) / 1024;
+    const long long b0 = t * per, b1 = min(nb, b0 + per);
+    int s = 0;
+    for (long long b = b0; b < b1; ++b) s += block_dead[b];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int run = 0;
+        for (int q = 0; q < 1024; ++q) {
+            const int cur = part[q];
+            part[q] = run;
+            run += cur;
+        }
+        if (total_out) *total_out = run;
+    }
+    __syncthreads();
+    int run = part[t];
+    for (long long b = b0; b < b1; ++b) {
+        block_off[b] = run;
+        run += block_dead[b];
+    }
+}
+
+// G3: dead particle i donates its block: free_list[rank of i among the dead] = slot[i]
+__global__ void __launch_bounds__(256)
+free_list_kernel(const int* __restrict__ offspring, const int* __restrict__ slot_in, long long M,
+                 int* __restrict__ dead_excl, const int* __restrict__ block_off, int* __restrict__ free_list) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int g = dead_excl[i] + block_off[i / PK_SCAN_BLOCK];
+    dead_excl[i] = g;  // now global
+    if (offspring[i] == 0) free_list[g] = slot_in[i];
+}
+
+// G4: per output slot k: permute pose/aux, keep or allocate a landmark block
+__global__ void __launch_bounds__(256)
+assign_kernel(const long long* __restrict__ ancestors, long long M, const double* __restrict__ pose_in,
+              double* __restrict__ pose_out, const int* __restrict__ aux_in, int* __restrict__ aux_out,
+              const int* __restrict__ slot_in, int* __restrict__ slot_out, const int* __restrict__ dead_excl,
+              const int* __restrict__ free_list, int* __restrict__ copy_src, int* __restrict__ copy_dst,
+              int* __restrict__ copy_nlive) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const long long a = ancestors[k];
+    const double2* src = reinterpret_cast<const double2*>(pose_in + 4 * a);
+    double2* dst = reinterpret_cast<double2*>(pose_out + 4 * k);
+    dst[0] = src[0];
+    dst[1] = src[1];
+    const int2 ax = reinterpret_cast<const int2*>(aux_in)[a];
+    reinterpret_cast<int2*>(aux_out)[k] = ax;
+    const bool first = (k == 0) || (ancestors[k - 1] != a);
+    if (first) {
+        slot_out[k] = slot_in[a];
+    } else {
+        // outputs before k: k; of those, one per live ancestor <= a keeps its block
+        const long long alive_before = a - dead_excl[a];
+        const long long nidx = k - alive_before - 1;
+        const int d = free_list[nidx];
+        slot_out[k] = d;
+        copy_src[nidx] = slot_in[a];
+        copy_dst[nidx] = d;
+        copy_nlive[nidx] = ax.x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// G5: block mover.  One warp per CTA, one elected lane drives a 4-deep ring of 4 KiB shared
+// memory buffers: cp.async.bulk global->shared (mbarrier complete_tx), then cp.async.bulk
+// shared->global (bulk group).  The chunk stream runs across items, so the pipeline never drains
+// between landmark blocks.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCopyBufs = 4;
+constexpr int kCopyChunk = 4096;
+
+__global__ void __launch_bounds__(32)
+copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __restrict__ dst_base, long long block_b,
+                   int hot_b, int cold_b, int capacity, const int* __restrict__ src_slot, const int* __restrict__ dst_slot,
+                   const int* __restrict__ nlive, long long n_max, const long long* __restrict__ n_dev) {
+    __shared__ __align__(128) unsigned char buf[kCopyBufs][kCopyChunk];
+    __shared__ uint64_t bar[kCopyBufs];
+    if (threadIdx.x != 0) return;
+    long long n = n_dev ? *n_dev : n_max;
+    if (n > n_max) n = n_max;
+    for (int b = 0; b < kCopyBufs; ++b) mbar_init(&bar[b], 1);
+    mbar_fence_init();
+
+    // chunk stream state: issue side (li_*) and drain side (ld_*)
+    struct Cursor {
+        long long item;
+        int seg;        // 0 = hot range, 1 = cold range
+        long long off;  // offset inside the segment
+    };
+    auto seg_len = [&](long long item, int seg) -> long long {
+        const int nl = nlive ? min(nlive[item], capacity) : capacity;
+        return (long long)nl * (seg == 0 ? hot_b : cold_b);
+    };
+    auto seg_base = [&](int seg) -> long long { return seg == 0 ? 0 : (long long)capacity * hot_b; };
+    auto advance = [&](Cursor& c, long long stride) {
+        // move to the next chunk, skipping empty segments; item strides over the grid
+        c.off += kCopyChunk;
+        while (c.item < n && c.off >= seg_len(c.item, c.seg)) {
+            c.off = 0;
+            if (++c.seg > 1) {
+                c.seg = 0;
+                c.item += stride;
+            }
+        }
+    };
+    const long long stride = gridDim.x;
+    Cursor ci{(long long)blockIdx.x, 0, -(long long)kCopyChunk}, cd = ci;
+    advance(ci, stride);
+    advance(cd, stride);
+    long long issued = 0, drained = 0;
+    while (cd.item < n) {
+        // keep up to kCopyBufs-1 loads in flight
+        while (ci.item < n && issued < drained + (kCopyBufs - 1)) {
+            const int b = (int)(issued % kCopyBufs);
+            if (issued >= kCopyBufs) tma_store_wait_read0();  // the store that last read this buffer
+            const long long len = seg_len(ci.item, ci.seg);
+            const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - ci.off);
+            const unsigned char* s = src_base + (size_t)src_slot[ci.item] * block_b + seg_base(ci.seg) + ci.off;
+            mbar_arrive_expect_tx(&bar[b], bytes);
+            tma_load_1d(buf[b], s, bytes, &bar[b]);
+            ++issued;
+            advance(ci, stride);
+        }
+        const int b = (int)(drained % kCopyBufs);
+        mbar_wait(&bar[b], (unsigned)((drained / kCopyBufs) & 1));
+        const long long len = seg_len(cd.item, cd.seg);
+        const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - cd.off);
+        unsigned char* d = dst_base + (size_t)dst_slot[cd.item] * block_b + seg_base(cd.seg) + cd.off;
+        tma_store_1d(d, buf[b], bytes);
+        tma_store_commit();
+        ++drained;
+        advance(cd, stride);
+    }
+    tma_store_wait0();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 summary / best particle
+// ---------------------------------------------------------------------------------------------
+constexpr int kRedBlocks = 1024;
+
+__global__ void __launch_bounds__(256)
+summary_partial_kernel(const double* __restrict__ pose4, long long M, double* __restrict__ ws) {
+    __shared__ double sh[4][8];
+    double sx = 0.0, sy = 0.0, ss = 0.0, sc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        const double2 xy = *reinterpret_cast<const double2*>(pose4 + 4 * i);
+        const double th = pose4[4 * i + 2];
+        double s, c;
+        sincos(th, &s, &c);
+        sx += xy.x;  // :267-271
+        sy += xy.y;
+        ss += s;
+        sc += c;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(kFullMask, sx, o);
+        sy += __shfl_xor_sync(kFullMask, sy, o);
+        ss += __shfl_xor_sync(kFullMask, ss, o);
+        sc += __shfl_xor_sync(kFullMask, sc, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[0][warp] = sx;
+        sh[1][warp] = sy;
+        sh[2][warp] = ss;
+        sh[3][warp] = sc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double a = 0.0;
+        for (int w = 0; w < 8; ++w) a += sh[threadIdx.x][w];
+        ws[threadIdx.x * kRedBlocks + blockIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+summary_final_kernel(const double* __restrict__ ws, int nblocks, long long M, double* __restrict__ out5) {
+    // four warps, one per quantity; fixed-order reduction of the per-block partials
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double a = 0.0;
+    for (int b = lane; b < nblocks; b += 32) a += ws[q * kRedBlocks + b];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
+    if (lane == 0) out5[q] = a;
+    if (threadIdx.x == 0) out5[4] = (double)M;
+}
+
+__global__ void __launch_bounds__(256)
+best_partial_kernel(const double* __restrict__ pose4, long long M, double* __restrict__ ws) {
+    __shared__ double shv[8];
+    __shared__ long long shi[8];
+    double bv = -1.0;
+    long long bi = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        const double w = pose4[4 * i + 3];
+        if (w > bv) {  // strict: first maximum wins within a thread (indices ascend)
+            bv = w;
+            bi = i;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(kFullMask, bv, o);
+        const long long oi = __shfl_xor_sync(kFullMask, bi, o);
+        if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        shv[warp] = bv;
+        shi[warp] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (shv[w] > bv || (shv[w] == bv && shi[w] >= 0 && (bi < 0 || shi[w] < bi))) {
+                bv = shv[w];
+                bi = shi[w];
+            }
+        ws[blockIdx.x] = bv;
+        ws[kRedBlocks + blockIdx.x] = (double)bi;
+    }
+}
+
+__global__ void best_final_kernel(const double* __restrict__ ws, int nblocks, double* __restrict__ best2) {
+    if (threadIdx.x != 0) return;
+    double bv = -1.0, bi = -1.0;
+    for (int b = 0; b < nblocks; ++b) {
+        const double v = ws[b], i = ws[kRedBlocks + b];
+        if (v > bv || (v == bv && i >= 0.0 && (bi < 0.0 || i < bi))) {
+            bv = v;
+            bi = i;
+        }
+    }
+    best2[0] = bv;
+    best2[1] = bi;
+}
+
+static long long num_blocks(long long M) { return (M + PK_SCAN_BLOCK - 1) / PK_SCAN_BLOCK; }
+
+struct GatherWs {
+    int *dead_excl, *block_dead, *block_off, *free_list, *copy_src, *copy_dst, *copy_nlive;
+    size_t bytes;
+};
+static GatherWs carve(void* ws, long long M) {
+    GatherWs g;
+    const long long nb = num_blocks(M);
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    unsigned char* base = (unsigned char*)ws;
+    auto take = [&](size_t n) {
+        int* p = (int*)(base + off);
+        off += align(n * sizeof(int));
+        return p;
+    };
+    g.dead_excl = take((size_t)M);
+    g.block_dead = take((size_t)nb);
+    g.block_off = take((size_t)nb + 1);
+    g.free_list = take((size_t)M);
+    g.copy_src = take((size_t)M);
+    g.copy_dst = take((size_t)M);
+    g.copy_nlive = take((size_t)M);
+    g.bytes = off;
+    return g;
+}
+
+}  // namespace pk
+
+using namespace pk;
+
+extern "C" {
+
+long long pk_num_scan_blocks(long long M) { return num_blocks(M); }
+
+int pk_weight_scan(const double* pose4, long long M, double* cumsum, double* block_sums, void* stream) {
+    PK_CHECK_ARG(pose4 && cumsum && block_sums, "null pointer");
+    PK_CHECK_ARG(M > 0, "M <= 0");
+    const long long nb = num_blocks(M);
+    const long long grid = (nb + kScanWarps - 1) / kScanWarps;
+    weight_scan_kernel<<<(unsigned)grid, kScanWarps * 32, 0, (cudaStream_t)stream>>>(pose4, M, cumsum, block_sums, nb);
+    PK_LAUNCH_CHECK("weight_scan_kernel");
+    return PK_OK;
+}
+
+int pk_resample_thresholds(const double* all_block_sums, long long nb_total, long long M_total, double u01, double* plan,
+                           double* block_prefix, long long* block_count, void* stream) {
+    PK_CHECK_ARG(all_block_sums && plan && block_prefix && block_count, "null pointer");
+    PK_CHECK_ARG(nb_total > 0 && M_total > 0, "sizes");
+    PK_CHECK_ARG(nb_total <= (long long)kGroupBlocks * kMaxScanGroups, "more than 2^25 particles in one filter");
+    thresholds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(all_block_sums, nb_total, M_total, u01, plan, block_prefix,
+                                                           block_count);
+    PK_LAUNCH_CHECK("thresholds_kernel");
+    return PK_OK;
+}
+
+int pk_resample_ancestors(const double* cumsum, long long M_local, long long particle_offset, long long block_offset,
+                          const double* plan, const double* block_prefix, const long long* block_count,
+                          long long M_total, long long out_offset, long long n_out, long long* out_lo, int* offspring,
+                          long long* ancestors, long long* big_runs, void* stream) {
+    PK_CHECK_ARG(cumsum && plan && block_prefix && block_count && out_lo && offspring && ancestors && big_runs,
+                 "null pointer");
+    PK_CHECK_ARG(M_local > 0 && M_total >= M_local, "sizes");
+    PK_CHECK_ARG(particle_offset % PK_SCAN_BLOCK == 0, "particle_offset must be a multiple of PK_SCAN_BLOCK");
+    cudaStream_t st = (cudaStream_t)stream;
+    PK_CUDA(cudaMemsetAsync(big_runs, 0, 4 * sizeof(long long), st));
+    const int threads = 256;
+    ancestors_kernel<<<(unsigned)((M_local + threads - 1) / threads), threads, 0, st>>>(
+        cumsum, M_local, particle_offset, block_offset, plan, block_prefix, block_count, M_total, out_offset, n_out,
+        out_lo, offspring, ancestors, big_runs);
+    PK_LAUNCH_CHECK("ancestors_kernel");
+    fill_runs_kernel<<<num_sms() * 2, 256, 0, st>>>(big_runs, ancestors);
+    PK_LAUNCH_CHECK("fill_runs_kernel");
+    return PK_OK;
+}
+
+long long pk_gather_workspace_bytes(long long M) {
+    if (M <= 0) return 0;
+    return (long long)carve(nullptr, M).bytes;
+}
+
+static int copy_blocks_launch(const void* src, void* dst, int capacity, int dtype, const int* src_slot,
+                              const int* dst_slot, const int* nlive, long long n_max, const long long* n_dev,
+                              cudaStream_t st) {
+    long long grid = (long long)num_sms() * 12;
+    if (grid > n_max) grid = n_max;
+    if (grid < 1) return PK_OK;
+    copy_blocks_kernel<<<(unsigned)grid, 32, 0, st>>>((const unsigned char*)src, (unsigned char*)dst,
+                                                     (long long)block_bytes(capacity, dtype), (int)hot_bytes(dtype),
+                                                     (int)cold_bytes(dtype), capacity, src_slot, dst_slot, nlive, n_max,
+                                                     n_dev);
+    PK_LAUNCH_CHECK("copy_blocks_kernel");
+    return PK_OK;
+}
+
+int pk_resample_gather(const long long* ancestors, const int* offspring, long long M, const double* pose4_in,
+                       double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
+                       void* pool, int capacity, int dtype, void* workspace, long long* n_copied_out, void* stream) {
+    PK_CHECK_ARG(ancestors && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out && pool &&
+                     workspace && n_copied_out,
+                 "null pointer");
+    PK_CHECK_ARG(M > 0 && M < (1ll << 31), "M");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(pose4_in != pose4_out && slot_in != slot_out && aux2_in != aux2_out, "gather is out of place");
+    cudaStream_t st = (cudaStream_t)stream;
+    GatherWs g = carve(workspace, M);
+    const long long nb = num_blocks(M);
+    dead_scan_kernel<<<(unsigned)((nb + kScanWarps - 1) / kScanWarps), kScanWarps * 32, 0, st>>>(offspring, M, g.dead_excl,
+                                                                                                 g.block_dead, nb);
+    PK_LAUNCH_CHECK("dead_scan_kernel");
+    block_offsets_kernel<<<1, 1024, 0, st>>>(g.block_dead, nb, g.block_off, n_copied_out);
+    PK_LAUNCH_CHECK("block_offsets_kernel");
+    const int threads = 256;
+    const unsigned grid = (unsigned)((M + threads - 1) / threads);
+    free_list_kernel<<<grid, threads, 0, st>>>(offspring, slot_in, M, g.dead_excl, g.block_off, g.free_list);
+    PK_LAUNCH_CHECK("free_list_kernel");
+    assign_kernel<<<grid, threads, 0, st>>>(ancestors, M, pose4_in, pose4_out, aux2_in, aux2_out, slot_in, slot_out,
+                                            g.dead_excl, g.free_list, g.copy_src, g.copy_dst, g.copy_nlive);
+    PK_LAUNCH_CHECK("assign_kernel");
+    if (capacity > 0)
+        return copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, M, n_copied_out, st);
+    return PK_OK;
+}
+
+int pk_copy_blocks(const void* pool_src, void* pool_dst, int capacity, int dtype, const int* src_slot,
+                   const int* dst_slot, const int* n_live, long long n_max, const long long* n_dev, void* stream) {
+    PK_CHECK_ARG(pool_src && pool_dst && src_slot && dst_slot, "null pointer");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(capacity > 0 && n_max >= 0, "sizes");
+    if (n_max == 0) return PK_OK;
+    return copy_blocks_launch(pool_src, pool_dst, capacity, dtype, src_slot, dst_slot, n_live, n_max, n_dev,
+                              (cudaStream_t)stream);
+}
+
+int pk_summary_partial(const double* pose4, long long M, double* out5, double* workspace, void* stream) {
+    PK_CHECK_ARG(pose4 && out5 && workspace, "null pointer");
+    PK_CHECK_ARG(M > 0, "M <= 0");
+    long long blocks = (M + 255) / 256;
+    if (blocks > kRedBlocks) blocks = kRedBlocks;
+    cudaStream_t st = (cudaStream_t)stream;
+    summary_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(pose4, M, workspace);
+    PK_LAUNCH_CHECK("summary_partial_kernel");
+    summary_final_kernel<<<1, 128, 0, st>>>(workspace, (int)blocks, M, out5);
+    PK_LAUNCH_CHECK("summary_final_kernel");
+    return PK_OK;
+}
+
+int pk_best_particle(const double* pose4, long long M, double* best2, double* workspace, void* stream) {
+    PK_CHECK_ARG(pose4 && best2 && workspace, "null pointer");
+    PK_CHECK_ARG(M > 0, "M <= 0");
+    long long blocks = (M + 255) / 256;
+    if (blocks > kRedBlocks) blocks = kRedBlocks;
+    cudaStream_t st = (cudaStream_t)stream;
+    best_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(pose4, M, workspace);
+    PK_LAUNCH_CHECK("best_partial_kernel");
+    best_final_kernel<<<1, 32, 0, st>>>(workspace, (int)blocks, best2);
+    PK_LAUNCH_CHECK("best_final_kernel");
+    return PK_OK;
+}
+
+}  // extern "C"
