@@ -42,48 +42,43 @@ int cuda_fail(cudaError_t e, const char* what);
 int num_sms();
 
 // ---------------------------------------------------------------------------------------------
-// Landmark record layout.  One particle's map ("block") = [hot x capacity][cold x capacity].
-// The hot part is all the association pre-filter needs (colour mean + meta) and is what the
-// fused kernel streams through shared memory; the cold part (position, covariance blocks, id) is
-// fetched only for the few landmarks that survive the colour gate.  A cold record is exactly two
-// (f32) / four (f64) 32-byte DRAM sectors.
+// Landmark record layout.  One particle's map ("block") = [hot region][cold region].
+//
+//   hot   4 B / landmark: a colour KEY -- r,g,b rounded and clamped to bytes (top byte zero).
+//         It is all the association pre-filter needs and the only part of the map the fused
+//         kernel streams for every landmark (256 B per particle at 64 landmarks).
+//   cold  80 B (f32) / 160 B (f64) per landmark: colour mean, position mean, the two covariance
+//         blocks, id and update_count.  Fetched only for the few landmarks whose key survives
+//         the colour gate.  Colours come first so the exact colour test reads one sector.
+//
+// 4 + 80 = 84 B per landmark in f32 and 4 + 160 = 164 B in f64 -- SURVEY.md 8(d)'s R32 / R64.
 // ---------------------------------------------------------------------------------------------
-struct alignas(16) HotF {
-    float r, g, b;
-    int meta;
-};
 struct alignas(16) ColdF {
-    float x, y;
+    float r, g, b, x, y;
     float sp[4];  // position covariance block, row-major [[a,b],[c,d]]
     float sc[9];  // colour covariance block, row-major
     int id;       // reference landmark id (>0 full, <0 potential)
-};
-struct alignas(16) HotD {
-    double r, g, b;
-    int meta;
-    int pad;
+    int meta;     // Feature.update_count | PK_META_IMMUTABLE | PK_META_POTENTIAL
 };
 struct alignas(16) ColdD {
-    double x, y;
+    double r, g, b, x, y;
     double sp[4];
     double sc[9];
     int id;
-    int pad;
+    int meta;
+    int pad[2];
 };
-static_assert(sizeof(HotF) == 16 && sizeof(ColdF) == 64, "f32 record layout");
-static_assert(sizeof(HotD) == 32 && sizeof(ColdD) == 128, "f64 record layout");
+static_assert(sizeof(ColdF) == 80 && sizeof(ColdD) == 160, "cold record layout");
 
 template <typename T>
 struct Rec;
 template <>
 struct Rec<float> {
-    using Hot = HotF;
     using Cold = ColdF;
     static constexpr int kDtype = PK_DTYPE_F32;
 };
 template <>
 struct Rec<double> {
-    using Hot = HotD;
     using Cold = ColdD;
     static constexpr int kDtype = PK_DTYPE_F64;
 };
@@ -93,14 +88,16 @@ struct Landmark {
     double x, y, r, g, b;
     double sp[4];
     double sc[9];
-    int meta;
+    int meta;  // update_count | PK_META_IMMUTABLE | PK_META_POTENTIAL
     int id;
 };
 
-__host__ __device__ inline size_t hot_bytes(int dtype) { return dtype == PK_DTYPE_F64 ? sizeof(HotD) : sizeof(HotF); }
+__host__ __device__ inline size_t hot_bytes(int) { return 4; }
 __host__ __device__ inline size_t cold_bytes(int dtype) { return dtype == PK_DTYPE_F64 ? sizeof(ColdD) : sizeof(ColdF); }
+// hot region padded to 16 B so the cold records and TMA bulk copies stay 16-byte aligned
+__host__ __device__ inline size_t hot_region_bytes(int capacity) { return ((size_t)capacity * 4 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t block_bytes(int capacity, int dtype) {
-    return (size_t)capacity * (hot_bytes(dtype) + cold_bytes(dtype));
+    return hot_region_bytes(capacity) + (size_t)capacity * cold_bytes(dtype);
 }
 
 #ifdef __CUDACC__
@@ -111,71 +108,111 @@ __host__ __device__ inline size_t block_bytes(int capacity, int dtype) {
 __device__ __forceinline__ int4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const int4*>(p)); }
 __device__ __forceinline__ void stcg16(void* p, int4 v) { __stcg(reinterpret_cast<int4*>(p), v); }
 
-template <typename T>
-__device__ __forceinline__ void load_landmark(const unsigned char* block, int capacity, int j, Landmark& L);
-
-template <>
-__device__ __forceinline__ void load_landmark<float>(const unsigned char* block, int capacity, int j, Landmark& L) {
-    const unsigned char* hp = block + (size_t)j * sizeof(HotF);
-    const unsigned char* cp = block + (size_t)capacity * sizeof(HotF) + (size_t)j * sizeof(ColdF);
-    int4 h = ldcg16(hp);
-    int4 c0 = ldcg16(cp), c1 = ldcg16(cp + 16), c2 = ldcg16(cp + 32), c3 = ldcg16(cp + 48);
-    L.r = (double)__int_as_float(h.x);
-    L.g = (double)__int_as_float(h.y);
-    L.b = (double)__int_as_float(h.z);
-    L.meta = h.w;
-    L.x = (double)__int_as_float(c0.x);
-    L.y = (double)__int_as_float(c0.y);
-    L.sp[0] = (double)__int_as_float(c0.z);
-    L.sp[1] = (double)__int_as_float(c0.w);
-    L.sp[2] = (double)__int_as_float(c1.x);
-    L.sp[3] = (double)__int_as_float(c1.y);
-    L.sc[0] = (double)__int_as_float(c1.z);
-    L.sc[1] = (double)__int_as_float(c1.w);
-    L.sc[2] = (double)__int_as_float(c2.x);
-    L.sc[3] = (double)__int_as_float(c2.y);
-    L.sc[4] = (double)__int_as_float(c2.z);
-    L.sc[5] = (double)__int_as_float(c2.w);
-    L.sc[6] = (double)__int_as_float(c3.x);
-    L.sc[7] = (double)__int_as_float(c3.y);
-    L.sc[8] = (double)__int_as_float(c3.z);
-    L.id = c3.w;
-}
-
 __device__ __forceinline__ double i4lo(int4 v) { return __hiloint2double(v.y, v.x); }
 __device__ __forceinline__ double i4hi(int4 v) { return __hiloint2double(v.w, v.z); }
 __device__ __forceinline__ int4 mk_i4(double a, double b) {
     return make_int4(__double2loint(a), __double2hiint(a), __double2loint(b), __double2hiint(b));
 }
 
+// colour key: each channel clamped to [0,255] and rounded to nearest (NaN -> 0)
+__device__ __forceinline__ unsigned color_key(double r, double g, double b) {
+    const unsigned kr = (unsigned)__double2int_rn(fmin(fmax(r, 0.0), 255.0));
+    const unsigned kg = (unsigned)__double2int_rn(fmin(fmax(g, 0.0), 255.0));
+    const unsigned kb = (unsigned)__double2int_rn(fmin(fmax(b, 0.0), 255.0));
+    return kr | (kg << 8) | (kb << 16);
+}
+template <typename T>
+__device__ __forceinline__ const unsigned char* cold_ptr(const unsigned char* block, int capacity, int j) {
+    return block + hot_region_bytes(capacity) + (size_t)j * sizeof(typename Rec<T>::Cold);
+}
+
+// colour mean only (first 16 B / 32 B of the cold record) -- the exact colour gate
+template <typename T>
+__device__ __forceinline__ void load_colour(const unsigned char* block, int capacity, int j, double& r, double& g, double& b);
 template <>
-__device__ __forceinline__ void load_landmark<double>(const unsigned char* block, int capacity, int j, Landmark& L) {
-    const unsigned char* hp = block + (size_t)j * sizeof(HotD);
-    const unsigned char* cp = block + (size_t)capacity * sizeof(HotD) + (size_t)j * sizeof(ColdD);
-    int4 h0 = ldcg16(hp), h1 = ldcg16(hp + 16);
-    L.r = i4lo(h0);
-    L.g = i4hi(h0);
-    L.b = i4lo(h1);
-    L.meta = h1.z;
-    int4 c[8];
+__device__ __forceinline__ void load_colour<float>(const unsigned char* block, int capacity, int j, double& r, double& g, double& b) {
+    const int4 c0 = ldcg16(cold_ptr<float>(block, capacity, j));
+    r = (double)__int_as_float(c0.x);
+    g = (double)__int_as_float(c0.y);
+    b = (double)__int_as_float(c0.z);
+}
+template <>
+__device__ __forceinline__ void load_colour<double>(const unsigned char* block, int capacity, int j, double& r, double& g, double& b) {
+    const unsigned char* cp = cold_ptr<double>(block, capacity, j);
+    const int4 c0 = ldcg16(cp), c1 = ldcg16(cp + 16);
+    r = i4lo(c0);
+    g = i4hi(c0);
+    b = i4lo(c1);
+}
+
+// cold record (as int4 words in registers) -> fp64 working copy
+template <typename T>
+__device__ __forceinline__ void decode_cold(const int4* c, Landmark& L);
+template <>
+__device__ __forceinline__ void decode_cold<float>(const int4* c, Landmark& L) {
+    L.r = (double)__int_as_float(c[0].x);
+    L.g = (double)__int_as_float(c[0].y);
+    L.b = (double)__int_as_float(c[0].z);
+    L.x = (double)__int_as_float(c[0].w);
+    L.y = (double)__int_as_float(c[1].x);
+    L.sp[0] = (double)__int_as_float(c[1].y);
+    L.sp[1] = (double)__int_as_float(c[1].z);
+    L.sp[2] = (double)__int_as_float(c[1].w);
+    L.sp[3] = (double)__int_as_float(c[2].x);
+    L.sc[0] = (double)__int_as_float(c[2].y);
+    L.sc[1] = (double)__int_as_float(c[2].z);
+    L.sc[2] = (double)__int_as_float(c[2].w);
+    L.sc[3] = (double)__int_as_float(c[3].x);
+    L.sc[4] = (double)__int_as_float(c[3].y);
+    L.sc[5] = (double)__int_as_float(c[3].z);
+    L.sc[6] = (double)__int_as_float(c[3].w);
+    L.sc[7] = (double)__int_as_float(c[4].x);
+    L.sc[8] = (double)__int_as_float(c[4].y);
+    L.id = c[4].z;
+    L.meta = c[4].w;
+}
+template <>
+__device__ __forceinline__ void decode_cold<double>(const int4* c, Landmark& L) {
+    L.r = i4lo(c[0]);
+    L.g = i4hi(c[0]);
+    L.b = i4lo(c[1]);
+    L.x = i4hi(c[1]);
+    L.y = i4lo(c[2]);
+    L.sp[0] = i4hi(c[2]);
+    L.sp[1] = i4lo(c[3]);
+    L.sp[2] = i4hi(c[3]);
+    L.sp[3] = i4lo(c[4]);
+    L.sc[0] = i4hi(c[4]);
+    L.sc[1] = i4lo(c[5]);
+    L.sc[2] = i4hi(c[5]);
+    L.sc[3] = i4lo(c[6]);
+    L.sc[4] = i4hi(c[6]);
+    L.sc[5] = i4lo(c[7]);
+    L.sc[6] = i4hi(c[7]);
+    L.sc[7] = i4lo(c[8]);
+    L.sc[8] = i4hi(c[8]);
+    L.id = c[9].x;
+    L.meta = c[9].y;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_landmark(const unsigned char* block, int capacity, int j, Landmark& L) {
+    constexpr int kWords = (int)(sizeof(typename Rec<T>::Cold) / 16);
+    const unsigned char* cp = cold_ptr<T>(block, capacity, j);
+    int4 c[kWords];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) c[i] = ldcg16(cp + 16 * i);
-    L.x = i4lo(c[0]);
-    L.y = i4hi(c[0]);
-    L.sp[0] = i4lo(c[1]);
-    L.sp[1] = i4hi(c[1]);
-    L.sp[2] = i4lo(c[2]);
-    L.sp[3] = i4hi(c[2]);
-    L.sc[0] = i4lo(c[3]);
-    L.sc[1] = i4hi(c[3]);
-    L.sc[2] = i4lo(c[4]);
-    L.sc[3] = i4hi(c[4]);
-    L.sc[4] = i4lo(c[5]);
-    L.sc[5] = i4hi(c[5]);
-    L.sc[6] = i4lo(c[6]);
-    L.sc[7] = i4hi(c[6]);
-    L.sc[8] = i4lo(c[7]);
-    L.id = c[7].z;
+    for (int i = 0; i < kWords; ++i) c[i] = ldcg16(cp + 16 * i);
+    decode_cold<T>(c, L);
+}
+
+// same, from a record staged in shared memory by a TMA bulk copy
+template <typename T>
+__device__ __forceinline__ void load_staged(const unsigned char* rec, Landmark& L) {
+    constexpr int kWords = (int)(sizeof(typename Rec<T>::Cold) / 16);
+    int4 c[kWords];
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) c[i] = *reinterpret_cast<const int4*>(rec + 16 * i);
+    decode_cold<T>(c, L);
 }
 
 template <typename T>
@@ -183,37 +220,33 @@ __device__ __forceinline__ void store_landmark(unsigned char* block, int capacit
 
 template <>
 __device__ __forceinline__ void store_landmark<float>(unsigned char* block, int capacity, int j, const Landmark& L) {
-    unsigned char* hp = block + (size_t)j * sizeof(HotF);
-    unsigned char* cp = block + (size_t)capacity * sizeof(HotF) + (size_t)j * sizeof(ColdF);
+    unsigned char* cp = const_cast<unsigned char*>(cold_ptr<float>(block, capacity, j));
 #define PK_F(v) __float_as_int((float)(v))
-    stcg16(hp, make_int4(PK_F(L.r), PK_F(L.g), PK_F(L.b), L.meta));
-    stcg16(cp, make_int4(PK_F(L.x), PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[1])));
-    stcg16(cp + 16, make_int4(PK_F(L.sp[2]), PK_F(L.sp[3]), PK_F(L.sc[0]), PK_F(L.sc[1])));
-    stcg16(cp + 32, make_int4(PK_F(L.sc[2]), PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[5])));
-    stcg16(cp + 48, make_int4(PK_F(L.sc[6]), PK_F(L.sc[7]), PK_F(L.sc[8]), L.id));
+    const float fr = (float)L.r, fg = (float)L.g, fb = (float)L.b;
+    // the key is derived from the STORED (rounded) colour so filter and exact test see one value
+    __stcg(reinterpret_cast<unsigned*>(block) + j, color_key((double)fr, (double)fg, (double)fb));
+    stcg16(cp, make_int4(__float_as_int(fr), __float_as_int(fg), __float_as_int(fb), PK_F(L.x)));
+    stcg16(cp + 16, make_int4(PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[1]), PK_F(L.sp[2])));
+    stcg16(cp + 32, make_int4(PK_F(L.sp[3]), PK_F(L.sc[0]), PK_F(L.sc[1]), PK_F(L.sc[2])));
+    stcg16(cp + 48, make_int4(PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[5]), PK_F(L.sc[6])));
+    stcg16(cp + 64, make_int4(PK_F(L.sc[7]), PK_F(L.sc[8]), L.id, L.meta));
 #undef PK_F
 }
 
 template <>
 __device__ __forceinline__ void store_landmark<double>(unsigned char* block, int capacity, int j, const Landmark& L) {
-    unsigned char* hp = block + (size_t)j * sizeof(HotD);
-    unsigned char* cp = block + (size_t)capacity * sizeof(HotD) + (size_t)j * sizeof(ColdD);
-    stcg16(hp, mk_i4(L.r, L.g));
-    int4 h1 = mk_i4(L.b, 0.0);
-    h1.z = L.meta;
-    h1.w = 0;
-    stcg16(hp + 16, h1);
-    stcg16(cp, mk_i4(L.x, L.y));
-    stcg16(cp + 16, mk_i4(L.sp[0], L.sp[1]));
-    stcg16(cp + 32, mk_i4(L.sp[2], L.sp[3]));
-    stcg16(cp + 48, mk_i4(L.sc[0], L.sc[1]));
-    stcg16(cp + 64, mk_i4(L.sc[2], L.sc[3]));
-    stcg16(cp + 80, mk_i4(L.sc[4], L.sc[5]));
-    stcg16(cp + 96, mk_i4(L.sc[6], L.sc[7]));
-    int4 t = mk_i4(L.sc[8], 0.0);
-    t.z = L.id;
-    t.w = 0;
-    stcg16(cp + 112, t);
+    unsigned char* cp = const_cast<unsigned char*>(cold_ptr<double>(block, capacity, j));
+    __stcg(reinterpret_cast<unsigned*>(block) + j, color_key(L.r, L.g, L.b));
+    stcg16(cp, mk_i4(L.r, L.g));
+    stcg16(cp + 16, mk_i4(L.b, L.x));
+    stcg16(cp + 32, mk_i4(L.y, L.sp[0]));
+    stcg16(cp + 48, mk_i4(L.sp[1], L.sp[2]));
+    stcg16(cp + 64, mk_i4(L.sp[3], L.sc[0]));
+    stcg16(cp + 80, mk_i4(L.sc[1], L.sc[2]));
+    stcg16(cp + 96, mk_i4(L.sc[3], L.sc[4]));
+    stcg16(cp + 112, mk_i4(L.sc[5], L.sc[6]));
+    stcg16(cp + 128, mk_i4(L.sc[7], L.sc[8]));
+    stcg16(cp + 144, make_int4(L.id, L.meta, 0, 0));
 }
 
 // ---------------------------------------------------------------------------------------------

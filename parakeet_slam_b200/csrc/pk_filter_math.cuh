@@ -15,7 +15,8 @@ constexpr double kLog2Pi = 1.8378770664093453;  // math.log(2*pi)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double match_likelihood(const Landmark& L, double px, double py, double pth, double beta,
                                                    double orr, double og, double ob, double dirx, double diry,
-                                                   const pk_params& prm, unsigned& flags) {
+                                                   const pk_params& prm, unsigned& flags, double& pse_out) {
+    pse_out = 0.0;
     // colour gate :425-427, :441
     double dr = orr - L.r, dg = og - L.g, db = ob - L.b;
     double cdist = dr * dr + dg * dg + db * db;
@@ -23,6 +24,7 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
     // bearing gate :408-415, :433
     double dx = L.x - px, dy = L.y - py;
     double pse = atan2(dy, dx);
+    pse_out = pse;
     double del = beta - (pse - pth);
     if (fabs(del) > prm.bearing_gate) return 0.0;
     // prob_position_match :473-475 (robot-frame bearing used as if world frame, finding F4c)
@@ -55,7 +57,8 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double py, double beta, double orr, double og,
                                                 double ob, const pk_params& prm, int& id_out, unsigned& flags,
-                                                int& promoted, bool& changed_out) {
+                                                int& promoted, bool& changed_out, bool have_zb = false,
+                                                double zb_in = 0.0) {
     id_out = L.id;
     const double qt = prm.qt_diag;
     // measurement_jacobian :785-797 (sign and order as written, finding F4b)
@@ -64,7 +67,8 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     double hx = (q == 0.0) ? 0.0 : dy / q;
     double hy = (q == 0.0) ? 0.0 : dx / q;
     // generate_measurement :871 -- world-frame bearing, no heading subtraction (finding F4a)
-    double zb = atan2(dy, dx);
+    // (the association step evaluates the same atan2(fy - sy, fx - sx), :408/:473; reuse it)
+    double zb = have_zb ? zb_in : atan2(dy, dx);
     double a = L.sp[0], b = L.sp[1], c = L.sp[2], d = L.sp[3];
     // measurement_covariance :817-819   Q = H Sigma H^T + Qt = diag(s) (+) Sc
     double t0 = hx * a + hy * c, t1 = hx * b + hy * d;

@@ -9,24 +9,29 @@
 //   importance_factor (:835-849), no_match_weight (:851-857), promotion (:109-118) and the
 //   next_id bump of add_orphaned_reading (:740-746).
 //
-// Shape of the kernel (persistent, one warp owns a *group* of consecutive particles):
-//   * the "hot" part of each particle's map (colour mean + meta, 16 B / landmark in f32) is
-//     streamed global -> shared by 1-D TMA bulk copies (cp.async.bulk + mbarrier) through a
-//     per-warp ring of tiles, several tiles ahead of the consumer;
-//   * lanes stride the landmarks of a tile and apply the colour gate (:441) to all K blobs -- the
-//     cheapest and most selective of the reference's gates, and the result of
+// Shape of the kernel (persistent, one warp owns a *group* of consecutive particles, sized so
+// that group x K blobs fills the 32 lanes):
+//   * the 4-byte colour KEYS of the group's maps are streamed global -> shared by 1-D TMA bulk
+//     copies (cp.async.bulk + mbarrier), one copy per particle issued by its own lane, through a
+//     per-warp ring of stages that runs ahead of the consumer across groups;
+//   * lanes stride the keys and screen all K blobs with two integer SIMD instructions per pair
+//     (vabsdiff4 + dp4a = squared byte distance) against a bound that provably contains the
+//     reference's colour gate (:441) -- the cheapest and most selective of its gates, and
 //     probability_of_match is 0 whenever it fails, whatever the evaluation order;
-//   * survivors (typically ~1 per blob) are compacted into a per-warp list of
-//     (particle, landmark, blob) triples and evaluated lane-parallel in fp64 exactly as the
-//     reference does (both pdfs in the linear domain, so the fp64-underflow match/no-match
-//     decision of finding F3 is reproduced, not emulated); the cold part of a landmark
-//     (position, covariance blocks, id; 64 B = two DRAM sectors) is fetched only here;
-//   * arg-max per (particle, blob) with "first maximum wins" through shared-memory atomics;
-//   * the K sequential EKF updates of the group's particles run one (particle, blob) pair per
-//     lane; pairs that hit the same landmark of the same particle are ordered in rounds so the
-//     second sees the first's result (finding F2);
+//   * each survivor (about one per blob) is entered in the candidate table of its (particle,
+//     blob) item and its cold record (80 B in f32: means, covariance blocks, id, count) is
+//     requested at once with a per-lane cp.async.bulk into a shared-memory staging area;
+//   * the warp is software-pipelined across groups: it screens group g+1 (and so has that
+//     group's records in flight) BEFORE it evaluates group g, so neither the key stream nor the
+//     scattered record fetches expose DRAM latency;
+//   * evaluation + update run one (particle, blob) item per lane: the lane evaluates its
+//     candidates in fp64 exactly as the reference does -- both pdfs in the linear domain, so the
+//     fp64-underflow match/no-match decision (finding F3) is reproduced, not emulated -- keeps
+//     the first maximum (:369-381), then applies the EKF update re-using the bearing it already
+//     computed.  Items that hit the same landmark of the same particle are ordered in rounds so
+//     the second sees the first's result (finding F2);
 //   * the weight is the scan-order product of the K factors (:124).
-// All arithmetic is fp64; the template parameter is only the landmark STORAGE type.
+// All arithmetic is fp64; the template parameter T is only the landmark STORAGE type.
 #include <math.h>
 
 #include "pk_common.cuh"
@@ -35,11 +40,12 @@
 namespace pk {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kChunk = 64;      // landmarks per tile
-constexpr int kStages = 8;      // tiles in flight per warp
+constexpr int kChunk = 64;      // keys per particle per stage
+constexpr int kStages = 2;      // key stages in flight per warp
 constexpr int kMaxGroup = 8;    // particles per group
 constexpr int kMaxItems = 64;   // group * K
-constexpr int kListCap = 128;
+constexpr int kCandPerItem = 4; // candidate slots per (particle, blob) item
+constexpr int kRecSlots = 36;   // staged cold records per group
 constexpr unsigned kFull = 0xffffffffu;
 
 struct MeasureArgs {
@@ -53,41 +59,63 @@ struct MeasureArgs {
     size_t block_bytes;
     int capacity;
     int K;
-    int group;  // particles per warp group
-    float color_gate_loose;
+    int group;        // particles per warp group
+    int key_thr;      // squared byte-distance bound of the colour screen
+    int warp_smem;    // bytes of shared memory per warp
+    int keys_off;     // offset of the key ring inside a warp's shared memory
+    int rec_off;      // offset of the record staging area
     pk_params prm;
     double beta[PK_MAX_OBS], cr[PK_MAX_OBS], cg[PK_MAX_OBS], cb[PK_MAX_OBS];
     double dirx[PK_MAX_OBS], diry[PK_MAX_OBS];  // unit((cos b, sin b, 0)) of closest_point :510
-    float crf[PK_MAX_OBS], cgf[PK_MAX_OBS], cbf[PK_MAX_OBS];
+    unsigned okey[PK_MAX_OBS];                  // colour keys of the blobs
 };
 
-template <typename T>
+// fixed part of a warp's shared memory; the key ring [kStages][group][kChunk] and the record
+// staging area [2][kRecSlots] follow at keys_off / rec_off
 struct alignas(128) WarpSmem {
-    typename Rec<T>::Hot hot[kStages][kChunk];
-    double pose[2][kMaxGroup][4];
-    unsigned long long best[kMaxItems];
-    unsigned long long best_of_j[kMaxItems];
+    double pose[4][kMaxGroup][4];
     double factor[kMaxItems];
-    int bestj[kMaxItems];
-    int list[kListCap];
-    int slot_s[2][kMaxGroup];
-    int nlive_s[2][kMaxGroup];
-    uint64_t bar[kStages];
+    int cand[2][kMaxItems][kCandPerItem];  // (staging slot + 1) << 20 | landmark index
+    int cnt[2][kMaxItems];
+    int ids[kMaxItems];
+    int bj[kMaxItems];
+    int slot_s[4][kMaxGroup];
+    int nlive_s[4][kMaxGroup];
+    int nsteps_s[4];
+    uint64_t key_bar[kStages];
+    uint64_t rec_bar[2];
 };
 
-__device__ __forceinline__ int pack_entry(int pl, int k, int j) { return (pl << 26) | (k << 20) | j; }
+// colour screen of one key against KT blobs: bit k set <=> squared byte distance <= bound
+template <int KT>
+__device__ __forceinline__ unsigned long long screen_keys(unsigned key, const MeasureArgs& A) {
+    unsigned lo = 0u, hi = 0u;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const unsigned d = __vabsdiffu4(key, A.okey[k]);
+        const int s = (int)__dp4a(d, d, 0u);
+        if (s <= A.key_thr) {
+            if (k < 32) lo |= 1u << (k & 31); else hi |= 1u << (k & 31);
+        }
+    }
+    return ((unsigned long long)hi << 32) | lo;
+}
 
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 measure_kernel(const __grid_constant__ MeasureArgs A) {
-    using Hot = typename Rec<T>::Hot;
+    using Cold = typename Rec<T>::Cold;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem<T>& S = reinterpret_cast<WarpSmem<T>*>(smem_raw)[warp];
+    unsigned char* wbase = smem_raw + (size_t)warp * A.warp_smem;
+    WarpSmem& S = *reinterpret_cast<WarpSmem*>(wbase);
+    unsigned* const key_ring = reinterpret_cast<unsigned*>(wbase + A.keys_off);  // [kStages][GP][kChunk]
+    unsigned char* const rec_area = wbase + A.rec_off;                           // [2][kRecSlots] Cold
     const unsigned lt = lanemask_lt();
 
     const int K = A.K, GP = A.group, cap = A.capacity;
+    const unsigned long long kmask = (K >= 64) ? ~0ull : ((1ull << K) - 1ull);
     const long long M = A.M;
     const long long n_groups = (M + GP - 1) / GP;
     const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
@@ -95,21 +123,22 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     const long long my_groups = (gw < n_groups) ? (n_groups - gw + total_warps - 1) / total_warps : 0;
 
     if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&S.bar[s], 1);
+        for (int s = 0; s < kStages; ++s) mbar_init(&S.key_bar[s], 1);
+        mbar_init(&S.rec_bar[0], 1);
+        mbar_init(&S.rec_bar[1], 1);
         mbar_fence_init();
     }
     __syncwarp();
 
-    // ---- producer state (warp-uniform) ------------------------------------------------------
-    long long p_git = 0, p_tiles = 0;
-    int p_pl = 0, p_chunk = 0;
-    long long c_git = 0, c_tiles = 0;
+    // ---- key producer (warp-uniform state) -----------------------------------------------------
+    long long p_git = 0, p_cnt = 0, s_git = 0, s_cnt = 0;  // producer / screen cursors
+    int p_step = 0, p_nsteps = 1;
     int nx_slot = 0, nx_nlive = 0;  // lane pl holds slot / n_live of particle pl of the next group to open
     auto fetch_info = [&](long long git) {
         nx_slot = 0;
         nx_nlive = 0;
         if (git < my_groups && lane < GP) {
-            long long p = (gw + git * total_warps) * GP + lane;
+            const long long p = (gw + git * total_warps) * GP + lane;
             if (p < M) {
                 nx_slot = A.slot[p];
                 nx_nlive = A.aux2[2 * p];
@@ -118,43 +147,45 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     };
     fetch_info(0);
 
+    // Group info buffers are indexed git & 3: group g is being evaluated, g+1 screened, g+2 may
+    // already be open in the producer.
     auto produce = [&]() {
-        while (p_git < my_groups && p_git <= c_git + 1 && p_tiles < c_tiles + kStages) {
-            const int par = (int)(p_git & 1);
-            const long long grp = gw + p_git * total_warps;
-            const long long p0 = grp * GP;
+        while (p_git < my_groups && p_git <= s_git + 1 && p_cnt < s_cnt + kStages) {
+            const int gi = (int)(p_git & 3);
+            const long long p0 = (gw + p_git * total_warps) * GP;
             const int gpn = (int)min((long long)GP, M - p0);
-            const bool first = (p_pl == 0 && p_chunk == 0);
-            if (first) {  // open the group: publish slot / n_live, prefetch the next group's
+            if (p_step == 0) {  // open the group: publish slot / n_live, prefetch the next group's
                 if (lane < kMaxGroup) {
-                    S.slot_s[par][lane] = nx_slot;
-                    S.nlive_s[par][lane] = nx_nlive;
+                    S.slot_s[gi][lane] = nx_slot;
+                    S.nlive_s[gi][lane] = nx_nlive;
                 }
+                const int maxn = __reduce_max_sync(kFull, nx_nlive);
+                p_nsteps = max(1, (maxn + kChunk - 1) / kChunk);
+                if (lane == 0) S.nsteps_s[gi] = p_nsteps;
                 fetch_info(p_git + 1);
                 __syncwarp();
             }
-            const int nlive = S.nlive_s[par][p_pl];
-            const int nch = max(1, (nlive + kChunk - 1) / kChunk);
-            const int nl = max(0, min(kChunk, nlive - p_chunk * kChunk));
-            const int stage = (int)(p_tiles % kStages);
-            if (lane == 0) {
-                const unsigned hot_b = (unsigned)(nl * (int)sizeof(Hot));
-                const unsigned pose_b = first ? (unsigned)(gpn * 32) : 0u;
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&S.bar[stage], hot_b + pose_b);
-                if (hot_b)
-                    tma_load_1d(&S.hot[stage][0],
-                                A.pool + (size_t)S.slot_s[par][p_pl] * A.block_bytes + (size_t)p_chunk * kChunk * sizeof(Hot),
-                                hot_b, &S.bar[stage]);
-                if (pose_b) tma_load_1d(&S.pose[par][0][0], A.pose4 + 4 * p0, pose_b, &S.bar[stage]);
+            const int stage = (int)(p_cnt % kStages);
+            unsigned bytes = 0;
+            if (lane < gpn) {
+                const int nl = max(0, min(kChunk, S.nlive_s[gi][lane] - p_step * kChunk));
+                bytes = ((unsigned)nl * 4u + 15u) & ~15u;
             }
-            ++p_tiles;
-            if (++p_chunk >= nch) {
-                p_chunk = 0;
-                if (++p_pl >= gpn) {
-                    p_pl = 0;
-                    ++p_git;
-                }
+            const unsigned total = __reduce_add_sync(kFull, bytes) + (p_step == 0 ? (unsigned)(gpn * 32) : 0u);
+            fence_proxy_async();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&S.key_bar[stage], total);
+                if (p_step == 0) tma_load_1d(&S.pose[gi][0][0], A.pose4 + 4 * p0, (unsigned)(gpn * 32), &S.key_bar[stage]);
+            }
+            __syncwarp();
+            if (bytes)  // every lane moves its own particle's keys
+                tma_load_1d(key_ring + ((size_t)stage * GP + lane) * kChunk,
+                            A.pool + (size_t)S.slot_s[gi][lane] * A.block_bytes + (size_t)p_step * kChunk * 4, bytes,
+                            &S.key_bar[stage]);
+            ++p_cnt;
+            if (++p_step >= p_nsteps) {
+                p_step = 0;
+                ++p_git;
             }
         }
     };
@@ -162,121 +193,150 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     unsigned long long st_matched = 0, st_unmatched = 0, st_eval = 0, st_same = 0, st_promoted = 0;
     unsigned st_flags = 0;
 
-    for (long long git = 0; git < my_groups; ++git) {
-        c_git = git;
-        const int par = (int)(git & 1);
-        const long long grp = gw + git * total_warps;
-        const long long p0 = grp * GP;
+    // ---- screen(g): colour-key screen of group g, candidate table + record prefetch -------------
+    auto screen = [&](long long git) {
+        s_git = git;
+        const int gi = (int)(git & 3), par = (int)(git & 1);
+        const long long p0 = (gw + git * total_warps) * GP;
         const int gpn = (int)min((long long)GP, M - p0);
-        const int nitems = gpn * K;
         produce();  // opens this group if it is not open yet
-        for (int w = lane; w < kMaxItems; w += 32) {
-            S.best[w] = 0ull;
-            S.best_of_j[w] = 0ull;
-            S.bestj[w] = 0x7fffffff;
-        }
+        for (int w = lane; w < kMaxItems; w += 32) S.cnt[par][w] = 0;
+        fence_proxy_async();  // the staging buffer was last read (generic proxy) two groups ago
         __syncwarp();
-        int list_n = 0;
-
-        // Exact evaluation of the listed (particle, landmark, blob) triples + running arg-max.
-        auto process_list = [&]() {
-            __syncwarp();
-            for (int base = 0; base < list_n; base += 32) {
-                const int idx = base + lane;
-                const bool active = idx < list_n;
-                double Lk = 0.0;
-                int item = 0, j = 0;
-                if (active) {
-                    const int e = S.list[idx];
-                    const int pl = e >> 26, k = (e >> 20) & 63;
-                    j = e & 0xfffff;
-                    item = pl * K + k;
-                    Landmark L;
-                    load_landmark<T>(A.pool + (size_t)S.slot_s[par][pl] * A.block_bytes, cap, j, L);
-                    Lk = match_likelihood(L, S.pose[par][pl][0], S.pose[par][pl][1], S.pose[par][pl][2], A.beta[k],
-                                          A.cr[k], A.cg[k], A.cb[k], A.dirx[k], A.diry[k], A.prm, st_flags);
-                    st_eval += 1;
-                }
-                // match_one :369-381: strict '>' from 0.0, first maximum (lowest slot) wins
-                const bool pos = active && (Lk > 0.0);
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(Lk);
-                if (pos) atomicMax(&S.best[item], bits);
-                __syncwarp();
-                const bool win = pos && (S.best[item] == bits);
-                if (win && S.best_of_j[item] != bits) S.bestj[item] = 0x7fffffff;  // winner of a smaller value: drop
-                __syncwarp();
-                if (win) atomicMin(&S.bestj[item], j);
-                __syncwarp();
-                if (win) S.best_of_j[item] = bits;
-                __syncwarp();
-            }
-            list_n = 0;
-        };
-
-        // ---- stream the hot tiles of the group's particles: colour-gate pre-filter ---------------
-        for (int pl = 0; pl < gpn; ++pl) {
-            const int nlive = S.nlive_s[par][pl];
-            const int nch = max(1, (nlive + kChunk - 1) / kChunk);
-            for (int ch = 0; ch < nch; ++ch) {
-                produce();
-                const int stage = (int)(c_tiles % kStages);
-                mbar_wait(&S.bar[stage], (unsigned)((c_tiles / kStages) & 1));
-                const int nl = max(0, min(kChunk, nlive - ch * kChunk));
-                const Hot* hot = &S.hot[stage][0];
+        unsigned char* rec = rec_area + (size_t)par * kRecSlots * sizeof(Cold);
+        int rec_n = 0;        // survivors so far (warp-uniform)
+        unsigned issued = 0;  // bytes this lane requested
+        const int nsteps = S.nsteps_s[gi];
+        for (int step = 0; step < nsteps; ++step) {
+            produce();
+            const int stage = (int)(s_cnt % kStages);
+            mbar_wait(&S.key_bar[stage], (unsigned)((s_cnt / kStages) & 1));
+            for (int pl = 0; pl < gpn; ++pl) {
+                const int nl = max(0, min(kChunk, S.nlive_s[gi][pl] - step * kChunk));
+                const unsigned* keys = key_ring + ((size_t)stage * GP + pl) * kChunk;
+                const unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
                 for (int row = 0; row * 32 < nl; ++row) {
                     const int jl = row * 32 + lane;
-                    const bool valid = jl < nl;
                     unsigned long long mask = 0ull;
-                    if (valid) {
-                        const Hot h = hot[jl];
-                        if (sizeof(T) == 4) {
-                            // fp32 screen with a loose bound; the exact fp64 test is in match_likelihood
-                            const float hr = (float)h.r, hg = (float)h.g, hb = (float)h.b;
-                            const bool big = !(fmaxf(fmaxf(fabsf(hr), fabsf(hg)), fabsf(hb)) < 4096.0f);
-                            for (int k = 0; k < K; ++k) {
-                                const float dr = A.crf[k] - hr, dg = A.cgf[k] - hg, db = A.cbf[k] - hb;
-                                const float cd = dr * dr + dg * dg + db * db;
-                                if (!(cd > A.color_gate_loose) || big) mask |= 1ull << k;
-                            }
-                        } else {
-                            const double hr = (double)h.r, hg = (double)h.g, hb = (double)h.b;
-                            for (int k = 0; k < K; ++k) {
-                                const double dr = A.cr[k] - hr, dg = A.cg[k] - hg, db = A.cb[k] - hb;
-                                const double cd = dr * dr + dg * dg + db * db;
-                                if (!(fabs(cd) > A.prm.color_gate)) mask |= 1ull << k;
-                            }
-                        }
-                    }
-                    const int j = ch * kChunk + jl;
+                    if (jl < nl) mask = screen_keys<KT>(keys[jl] & 0x00ffffffu, A) & kmask;
+                    const int j = step * kChunk + jl;
                     for (;;) {
                         const bool has = mask != 0ull;
                         const unsigned b = __ballot_sync(kFull, has);
                         if (b == 0u) break;
-                        const int n = __popc(b);
-                        if (list_n + n > kListCap) process_list();
                         if (has) {
                             const int kk = __ffsll((long long)mask) - 1;
                             mask &= mask - 1ull;
-                            S.list[list_n + __popc(b & lt)] = pack_entry(pl, kk, j);
+                            const int item = pl * K + kk;
+                            const int c = atomicAdd(&S.cnt[par][item], 1);
+                            if (c < kCandPerItem) {
+                                const int pos = rec_n + __popc(b & lt);
+                                int entry = j;
+                                if (pos < kRecSlots) {
+                                    entry |= (pos + 1) << 20;
+                                    tma_load_1d(rec + (size_t)pos * sizeof(Cold), cold_ptr<T>(block, cap, j),
+                                                (unsigned)sizeof(Cold), &S.rec_bar[par]);
+                                    issued += (unsigned)sizeof(Cold);
+                                }
+                                S.cand[par][item][c] = entry;
+                            }
                         }
-                        list_n += n;
+                        rec_n += __popc(b);
                     }
                 }
-                __syncwarp();  // every lane is done with this stage before it is refilled
-                ++c_tiles;
             }
+            __syncwarp();  // every lane is done with this key stage before it is refilled
+            ++s_cnt;
         }
-        process_list();
+        const unsigned total = __reduce_add_sync(kFull, issued);
+        if (lane == 0) mbar_arrive_expect_tx(&S.rec_bar[par], total);
+    };
 
-        // ---- sequential EKF updates (:88-124), one (particle, blob) pair per lane ------------------
+    // ---- evaluate(g): association arg-max + sequential EKF updates + weight ----------------------
+    auto evaluate = [&](long long git) {
+        const int gi = (int)(git & 3), par = (int)(git & 1);
+        const long long p0 = (gw + git * total_warps) * GP;
+        const int gpn = (int)min((long long)GP, M - p0);
+        const int nitems = gpn * K;
+        const unsigned char* rec = rec_area + (size_t)par * kRecSlots * sizeof(Cold);
+        mbar_wait(&S.rec_bar[par], (unsigned)((git >> 1) & 1));
+        const int rounds = (nitems + 31) >> 5;  // 1 unless K > 32
+        // per-lane association result of the (last) evaluated round, kept in registers
+        double best_pse = 0.0;
+        int bestj = -1, lastj = -1;
+        Landmark L;
+        // ---- association (:84, match_features_to_scan): every blob against the PRE-update map ----
         for (int ibase = 0; ibase < nitems; ibase += 32) {
             const int w = ibase + lane;
             const bool act = w < nitems;
             const int pl = act ? w / K : 0, k = act ? w % K : 0;
-            int j = -1;
-            if (act && S.best[w] != 0ull) j = S.bestj[w];
-            const bool matched = act && j >= 0;
-            const int key = matched ? (pl * cap + j) : (-1 - lane);
+            const unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
+            const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
+            const int cnt_raw = act ? S.cnt[par][w] : 0;
+            const int ncand = min(cnt_raw, kCandPerItem);
+            const int maxc = __reduce_max_sync(kFull, ncand);
+            // match_one :353-381: arg-max, strict '>' from 0.0, first (lowest slot) maximum wins
+            double best = 0.0, pse = 0.0;
+            best_pse = 0.0;
+            bestj = -1;
+            lastj = -1;
+            for (int c = 0; c < maxc; ++c) {
+                if (c < ncand) {
+                    const int e = S.cand[par][w][c];
+                    const int j = e & 0xfffff, sl = (e >> 20) - 1;
+                    if (sl >= 0) load_staged<T>(rec + (size_t)sl * sizeof(Cold), L);
+                    else load_landmark<T>(block, cap, j, L);
+                    lastj = j;
+                    const double Lk = match_likelihood(L, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
+                                                       A.diry[k], A.prm, st_flags, pse);
+                    st_eval += 1;
+                    if (Lk > best || (Lk == best && Lk > 0.0 && j < bestj)) {
+                        best = Lk;
+                        bestj = j;
+                        best_pse = pse;
+                    }
+                }
+            }
+            if (cnt_raw > kCandPerItem) {
+                // more colour-compatible landmarks than candidate slots: scan the whole map directly
+                best = 0.0;
+                bestj = -1;
+                lastj = -1;
+                const int nlive = S.nlive_s[gi][pl];
+                for (int j = 0; j < nlive; ++j) {
+                    Landmark Lj;
+                    load_landmark<T>(block, cap, j, Lj);
+                    const double Lk = match_likelihood(Lj, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
+                                                       A.diry[k], A.prm, st_flags, pse);
+                    st_eval += 1;
+                    if (Lk > best) {
+                        best = Lk;
+                        bestj = j;
+                        best_pse = pse;
+                    }
+                }
+            }
+            if (rounds > 1 && act) {
+                S.bj[w] = bestj;
+                S.factor[w] = best_pse;
+            }
+        }
+        if (rounds > 1) __syncwarp();
+        // ---- sequential updates (:88-124) in scan order -------------------------------------------
+        for (int ibase = 0; ibase < nitems; ibase += 32) {
+            const int w = ibase + lane;
+            const bool act = w < nitems;
+            const int pl = act ? w / K : 0, k = act ? w % K : 0;
+            unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
+            const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1];
+            if (rounds > 1) {
+                bestj = act ? S.bj[w] : -1;
+                best_pse = act ? S.factor[w] : 0.0;
+                lastj = -1;  // records are re-read: an earlier round may have rewritten them
+            }
+            const bool matched = act && bestj >= 0;
+            // items on the same landmark of the same particle go one after the other
+            const int key = matched ? (pl * cap + bestj) : (-1 - lane);
             const unsigned peers = __match_any_sync(kFull, key);
             const int rank = __popc(peers & lt);
             const int maxrank = __reduce_max_sync(kFull, matched ? rank : 0);
@@ -284,19 +344,23 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             int id_out = 0;
             for (int r = 0; r <= maxrank; ++r) {
                 if (matched && rank == r) {
+                    // the winner's record is in registers unless another candidate was evaluated after
+                    // it, or an earlier blob of this frame has just rewritten the landmark
+                    if (r > 0 || lastj != bestj) load_landmark<T>(block, cap, bestj, L);
                     int promoted = 0;
-                    factor = ekf_update<T>(A.pool + (size_t)S.slot_s[par][pl] * A.block_bytes, cap, j, S.pose[par][pl][0],
-                                           S.pose[par][pl][1], A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.prm, id_out,
-                                           st_flags, promoted);
+                    bool changed = false;
+                    factor = ekf_update_lm(L, px, py, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.prm, id_out, st_flags,
+                                           promoted, changed, true, best_pse);
+                    if (changed) store_landmark<T>(block, cap, bestj, L);
                     st_promoted += promoted;
                     if (r > 0) st_same += 1;
                 }
-                __syncwarp();
+                if (maxrank > 0) __syncwarp();
             }
             if (act) {
                 A.assoc[(p0 + pl) * K + k] = id_out;
                 S.factor[w] = factor;
-                S.bestj[w] = id_out;  // reuse as the id list for the orphan count below
+                S.ids[w] = id_out;
                 if (matched) st_matched += 1; else st_unmatched += 1;
             }
         }
@@ -307,7 +371,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             int orphans = 0;
             for (int k = 0; k < K; ++k) {
                 wgt *= S.factor[lane * K + k];
-                orphans += (S.bestj[lane * K + k] == 0);
+                orphans += (S.ids[lane * K + k] == 0);
             }
             if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
             A.pose4[4 * (p0 + lane) + 3] = wgt;
@@ -315,6 +379,13 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             if (orphans) A.aux2[2 * (p0 + lane) + 1] += orphans;
         }
         __syncwarp();
+    };
+
+    // ---- software pipeline over this warp's groups -----------------------------------------------
+    if (my_groups > 0) screen(0);
+    for (long long git = 0; git < my_groups; ++git) {
+        if (git + 1 < my_groups) screen(git + 1);
+        evaluate(git);
     }
 
     // ---- statistics: one atomic per warp per counter ------------------------------------------------
@@ -341,25 +412,36 @@ __global__ void reset_weight_kernel(double* __restrict__ pose4, long long M) {
     if (i < M) pose4[4 * i + 3] = 1.0;  // cam_cb :73 with an empty scan
 }
 
-template <typename T>
-static int launch_measure(const MeasureArgs& args, cudaStream_t st) {
-    static bool configured = false;
-    const size_t smem = sizeof(WarpSmem<T>) * kWarpsPerCta;
-    if (!configured) {
-        PK_CUDA(cudaFuncSetAttribute(measure_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+template <typename T, int KT>
+static int launch_measure(MeasureArgs& args, cudaStream_t st) {
+    static int configured_smem = -1;
+    auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    args.keys_off = (int)align128(sizeof(WarpSmem));
+    args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kChunk * 4);
+    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * kRecSlots * sizeof(typename Rec<T>::Cold));
+    const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
+    if ((int)smem > configured_smem) {
+        PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_smem = (int)smem;
     }
     int ctas_per_sm = 0;
-    PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T>, kWarpsPerCta * 32, smem));
+    PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T, KT>, kWarpsPerCta * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const long long n_groups = (args.M + args.group - 1) / args.group;
     long long grid = (long long)num_sms() * ctas_per_sm;
     const long long need = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    measure_kernel<T><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(args);
+    measure_kernel<T, KT><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(args);
     PK_LAUNCH_CHECK("measure_kernel");
     return PK_OK;
+}
+
+template <typename T>
+static int dispatch_measure(MeasureArgs& args, cudaStream_t st) {
+    if (args.K <= 8) return launch_measure<T, 8>(args, st);
+    if (args.K <= 32) return launch_measure<T, 32>(args, st);
+    return launch_measure<T, 64>(args, st);
 }
 
 }  // namespace pk
@@ -401,7 +483,12 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
     if (group > kMaxGroup) group = kMaxGroup;
     args.group = group;
     args.prm = *params;
-    bool obs_big = false;
+    auto key_of = [](double c) -> unsigned {
+        if (!(c == c)) return 0u;  // NaN
+        c = c < 0.0 ? 0.0 : (c > 255.0 ? 255.0 : c);
+        return (unsigned)nearbyint(c);
+    };
+    for (int k = 0; k < PK_MAX_OBS; ++k) args.okey[k] = 0u;
     for (int k = 0; k < K; ++k) {
         const double beta = obs_host[4 * k + 0];
         args.beta[k] = beta;
@@ -414,15 +501,17 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
         volatile double inv = 1.0 / length;
         args.dirx[k] = c * inv;
         args.diry[k] = s * inv;
-        args.crf[k] = (float)args.cr[k];
-        args.cgf[k] = (float)args.cg[k];
-        args.cbf[k] = (float)args.cb[k];
-        for (int q = 1; q < 4; ++q)
-            if (!(fabs(obs_host[4 * k + q]) < 4096.0)) obs_big = true;
+        args.okey[k] = key_of(args.cr[k]) | (key_of(args.cg[k]) << 8) | (key_of(args.cb[k]) << 16);
     }
-    // fp32 screen: with |colour| < 4096 the fp32 distance is within 0.1% + 0.1 of the fp64 one, so
-    // anything the exact gate would accept also passes the loose one.
-    args.color_gate_loose = obs_big ? INFINITY : (float)(params->color_gate * 1.001 + 0.25);
-    if (dtype == PK_DTYPE_F32) return launch_measure<float>(args, st);
-    return launch_measure<double>(args, st);
+    // Colour screen bound (DESIGN.md "colour keys").  Keys are the colours clamped to [0,255] and
+    // rounded, so per channel |key difference| <= |true difference| + 1.  If the exact gate accepts
+    // (sum d^2 <= gate) then sum |d| <= sqrt(3*gate) and the squared key distance is at most
+    // gate + 2*sqrt(3*gate) + 3.  Anything above that bound cannot pass the reference's gate.
+    const double g = params->color_gate;
+    double bound = -1.0;  // negative gate: nothing passes
+    if (g >= 0.0) bound = floor(g + 2.0 * sqrt(3.0 * g) + 3.0) + 1.0;
+    if (!(g == g)) bound = 2.0e9;  // NaN gate: `abs(cd) > nan` is False, everything passes
+    args.key_thr = (int)(bound > 2.0e9 ? 2.0e9 : bound);
+    if (dtype == PK_DTYPE_F32) return dispatch_measure<float>(args, st);
+    return dispatch_measure<double>(args, st);
 }

@@ -33,8 +33,9 @@ __global__ void probe_likelihood_kernel(const double* __restrict__ pose3, const 
     L.meta = 0;
     L.id = 1;
     unsigned flags = 0;
+    double pse;
     out[i] = match_likelihood(L, pose3[3 * i], pose3[3 * i + 1], pose3[3 * i + 2], blob4[4 * i], blob4[4 * i + 1],
-                              blob4[4 * i + 2], blob4[4 * i + 3], dir2[2 * i], dir2[2 * i + 1], prm, flags);
+                              blob4[4 * i + 2], blob4[4 * i + 3], dir2[2 * i], dir2[2 * i + 1], prm, flags, pse);
     if (flags && flags_out) atomicOr(flags_out, flags);
 }
 

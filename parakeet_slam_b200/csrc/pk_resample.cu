@@ -342,9 +342,10 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
     };
     auto seg_len = [&](long long item, int seg) -> long long {
         const int nl = nlive ? min(nlive[item], capacity) : capacity;
-        return (long long)nl * (seg == 0 ? hot_b : cold_b);
+        // hot keys are 4 B each: round the range up to the 16 B granularity of a bulk copy
+        return seg == 0 ? (((long long)nl * hot_b + 15) & ~15ll) : (long long)nl * cold_b;
     };
-    auto seg_base = [&](int seg) -> long long { return seg == 0 ? 0 : (long long)capacity * hot_b; };
+    auto seg_base = [&](int seg) -> long long { return seg == 0 ? 0 : (long long)hot_region_bytes(capacity); };
     auto advance = [&](Cursor& c, long long stride) {
         // move to the next chunk, skipping empty segments; item strides over the grid
         c.off += kCopyChunk;
