@@ -317,7 +317,7 @@ def run_ours(args):
         value = updates / (ms_total * 1e-3)
         # algorithmic bytes of the fused measurement kernel per particle:
         hot_b = 4                                        # colour key per landmark
-        rec_b = (80 if args.dtype == "f32" else 160) + 4  # cold record + its key
+        rec_b = (64 if args.dtype == "f32" else 160) + 4  # cold record + its key
         m_matched = matched_frac * K
         bytes_particle = 32 + 8 + hot_b * N + rec_b * eval_per_particle + rec_b * m_matched + 8 + 4 * K
         achieved = bytes_particle * M_local / (ms_measure * 1e-3) / 1e9

@@ -47,16 +47,19 @@ int num_sms();
 //   hot   4 B / landmark: a colour KEY -- r,g,b rounded and clamped to bytes (top byte zero).
 //         It is all the association pre-filter needs and the only part of the map the fused
 //         kernel streams for every landmark (256 B per particle at 64 landmarks).
-//   cold  80 B (f32) / 160 B (f64) per landmark: colour mean, position mean, the two covariance
-//         blocks, id and update_count.  Fetched only for the few landmarks whose key survives
-//         the colour gate.  Colours come first so the exact colour test reads one sector.
+//   cold  64 B (f32) / 160 B (f64) per landmark: colour mean, position mean, the two covariance
+//         blocks, id and update_count | flags.  Fetched only for the few landmarks whose key
+//         survives the colour gate.  The f32 record is exactly one 64-byte DRAM granule: it keeps
+//         the covariance blocks as their LOWER triangles (the triangle the reference's pdf reads,
+//         scipy eigh(lower=True)); the two off-diagonal copies differ only by rounding in the
+//         reference, far below fp32 resolution.  The f64 record keeps all 13 entries.
 //
-// 4 + 80 = 84 B per landmark in f32 and 4 + 160 = 164 B in f64 -- SURVEY.md 8(d)'s R32 / R64.
+// 4 + 64 = 68 B per landmark in f32 and 4 + 160 = 164 B in f64 (SURVEY.md 8(d) budgeted 84 / 164).
 // ---------------------------------------------------------------------------------------------
 struct alignas(16) ColdF {
     float r, g, b, x, y;
-    float sp[4];  // position covariance block, row-major [[a,b],[c,d]]
-    float sc[9];  // colour covariance block, row-major
+    float sp[3];  // position covariance block, lower triangle: S00, S10, S11
+    float sc[6];  // colour covariance block, lower triangle: C00, C10, C11, C20, C21, C22
     int id;       // reference landmark id (>0 full, <0 potential)
     int meta;     // Feature.update_count | PK_META_IMMUTABLE | PK_META_POTENTIAL
 };
@@ -68,7 +71,7 @@ struct alignas(16) ColdD {
     int meta;
     int pad[2];
 };
-static_assert(sizeof(ColdF) == 80 && sizeof(ColdD) == 160, "cold record layout");
+static_assert(sizeof(ColdF) == 64 && sizeof(ColdD) == 160, "cold record layout");
 
 template <typename T>
 struct Rec;
@@ -156,20 +159,20 @@ __device__ __forceinline__ void decode_cold<float>(const int4* c, Landmark& L) {
     L.x = (double)__int_as_float(c[0].w);
     L.y = (double)__int_as_float(c[1].x);
     L.sp[0] = (double)__int_as_float(c[1].y);
-    L.sp[1] = (double)__int_as_float(c[1].z);
-    L.sp[2] = (double)__int_as_float(c[1].w);
-    L.sp[3] = (double)__int_as_float(c[2].x);
-    L.sc[0] = (double)__int_as_float(c[2].y);
-    L.sc[1] = (double)__int_as_float(c[2].z);
-    L.sc[2] = (double)__int_as_float(c[2].w);
-    L.sc[3] = (double)__int_as_float(c[3].x);
-    L.sc[4] = (double)__int_as_float(c[3].y);
-    L.sc[5] = (double)__int_as_float(c[3].z);
-    L.sc[6] = (double)__int_as_float(c[3].w);
-    L.sc[7] = (double)__int_as_float(c[4].x);
-    L.sc[8] = (double)__int_as_float(c[4].y);
-    L.id = c[4].z;
-    L.meta = c[4].w;
+    L.sp[2] = (double)__int_as_float(c[1].z);
+    L.sp[1] = L.sp[2];
+    L.sp[3] = (double)__int_as_float(c[1].w);
+    L.sc[0] = (double)__int_as_float(c[2].x);
+    L.sc[3] = (double)__int_as_float(c[2].y);
+    L.sc[4] = (double)__int_as_float(c[2].z);
+    L.sc[6] = (double)__int_as_float(c[2].w);
+    L.sc[7] = (double)__int_as_float(c[3].x);
+    L.sc[8] = (double)__int_as_float(c[3].y);
+    L.sc[1] = L.sc[3];
+    L.sc[2] = L.sc[6];
+    L.sc[5] = L.sc[7];
+    L.id = c[3].z;
+    L.meta = c[3].w;
 }
 template <>
 __device__ __forceinline__ void decode_cold<double>(const int4* c, Landmark& L) {
@@ -205,15 +208,9 @@ __device__ __forceinline__ void load_landmark(const unsigned char* block, int ca
     decode_cold<T>(c, L);
 }
 
-// same, from a record staged in shared memory by a TMA bulk copy
+// same, from a record staged in shared memory by a TMA bulk copy (32-bit shared address)
 template <typename T>
-__device__ __forceinline__ void load_staged(const unsigned char* rec, Landmark& L) {
-    constexpr int kWords = (int)(sizeof(typename Rec<T>::Cold) / 16);
-    int4 c[kWords];
-#pragma unroll
-    for (int i = 0; i < kWords; ++i) c[i] = *reinterpret_cast<const int4*>(rec + 16 * i);
-    decode_cold<T>(c, L);
-}
+__device__ __forceinline__ void load_staged(uint32_t rec, Landmark& L);
 
 template <typename T>
 __device__ __forceinline__ void store_landmark(unsigned char* block, int capacity, int j, const Landmark& L);
@@ -223,13 +220,12 @@ __device__ __forceinline__ void store_landmark<float>(unsigned char* block, int 
     unsigned char* cp = const_cast<unsigned char*>(cold_ptr<float>(block, capacity, j));
 #define PK_F(v) __float_as_int((float)(v))
     const float fr = (float)L.r, fg = (float)L.g, fb = (float)L.b;
-    // the key is derived from the STORED (rounded) colour so filter and exact test see one value
+    // the key is derived from the STORED (rounded) colour so screen and exact test see one value
     __stcg(reinterpret_cast<unsigned*>(block) + j, color_key((double)fr, (double)fg, (double)fb));
     stcg16(cp, make_int4(__float_as_int(fr), __float_as_int(fg), __float_as_int(fb), PK_F(L.x)));
-    stcg16(cp + 16, make_int4(PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[1]), PK_F(L.sp[2])));
-    stcg16(cp + 32, make_int4(PK_F(L.sp[3]), PK_F(L.sc[0]), PK_F(L.sc[1]), PK_F(L.sc[2])));
-    stcg16(cp + 48, make_int4(PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[5]), PK_F(L.sc[6])));
-    stcg16(cp + 64, make_int4(PK_F(L.sc[7]), PK_F(L.sc[8]), L.id, L.meta));
+    stcg16(cp + 16, make_int4(PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[2]), PK_F(L.sp[3])));
+    stcg16(cp + 32, make_int4(PK_F(L.sc[0]), PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[6])));
+    stcg16(cp + 48, make_int4(PK_F(L.sc[7]), PK_F(L.sc[8]), L.id, L.meta));
 #undef PK_F
 }
 
@@ -291,6 +287,32 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
                  "r"(bytes)
                  : "memory");
 }
+// variants taking precomputed 32-bit shared-window addresses (no generic->shared conversion)
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d_a(uint32_t dst, const void* src_gmem, unsigned bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ int4 lds16_a(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -325,6 +347,15 @@ __device__ __forceinline__ dd dd_add(dd a, dd b) {
     s = quick_two_sum(s.hi, s.lo);
     s.lo = __dadd_rn(s.lo, t.lo);
     return quick_two_sum(s.hi, s.lo);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_staged(uint32_t rec, Landmark& L) {
+    constexpr int kWords = (int)(sizeof(typename Rec<T>::Cold) / 16);
+    int4 c[kWords];
+#pragma unroll
+    for (int i = 0; i < kWords; ++i) c[i] = lds16_a(rec + 16 * i);
+    decode_cold<T>(c, L);
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {

@@ -9,29 +9,29 @@
 //   importance_factor (:835-849), no_match_weight (:851-857), promotion (:109-118) and the
 //   next_id bump of add_orphaned_reading (:740-746).
 //
-// Shape of the kernel (persistent, one warp owns a *group* of consecutive particles, sized so
-// that group x K blobs fills the 32 lanes):
+// Shape of the kernel (persistent; one warp owns a *group* of consecutive particles sized so that
+// group x K blobs fills the 32 lanes, i.e. every lane is one (particle, blob) ITEM):
 //   * the 4-byte colour KEYS of the group's maps are streamed global -> shared by 1-D TMA bulk
 //     copies (cp.async.bulk + mbarrier), one copy per particle issued by its own lane, through a
 //     per-warp ring of stages that runs ahead of the consumer across groups;
-//   * lanes stride the keys and screen all K blobs with two integer SIMD instructions per pair
-//     (vabsdiff4 + dp4a = squared byte distance) against a bound that provably contains the
-//     reference's colour gate (:441) -- the cheapest and most selective of its gates, and
-//     probability_of_match is 0 whenever it fails, whatever the evaluation order;
-//   * each survivor (about one per blob) is entered in the candidate table of its (particle,
-//     blob) item and its cold record (80 B in f32: means, covariance blocks, id, count) is
-//     requested at once with a per-lane cp.async.bulk into a shared-memory staging area;
+//   * SCREEN: each lane scans its particle's keys against its blob's key with two integer SIMD
+//     instructions per pair (vabsdiff4 + dp4a = squared byte distance, keys read 4 at a time with
+//     LDS.128) against a bound that provably contains the reference's colour gate (:441) -- the
+//     cheapest and most selective of its gates, and probability_of_match is 0 whenever it fails,
+//     whatever the evaluation order.  Hits (about one per item) stay in registers; the lane
+//     requests the cold record of its first hit at once with its own cp.async.bulk into a fixed
+//     staging slot in shared memory;
 //   * the warp is software-pipelined across groups: it screens group g+1 (and so has that
 //     group's records in flight) BEFORE it evaluates group g, so neither the key stream nor the
 //     scattered record fetches expose DRAM latency;
-//   * evaluation + update run one (particle, blob) item per lane: the lane evaluates its
-//     candidates in fp64 exactly as the reference does -- both pdfs in the linear domain, so the
-//     fp64-underflow match/no-match decision (finding F3) is reproduced, not emulated -- keeps
-//     the first maximum (:369-381), then applies the EKF update re-using the bearing it already
-//     computed.  Items that hit the same landmark of the same particle are ordered in rounds so
-//     the second sees the first's result (finding F2);
+//   * EVALUATE: the lane evaluates its candidates in fp64 exactly as the reference does -- both
+//     pdfs in the linear domain, so the fp64-underflow match/no-match decision (finding F3) is
+//     reproduced, not emulated -- keeps the first maximum (:369-381), then applies the EKF update
+//     re-using the bearing it already computed.  Items that hit the same landmark of the same
+//     particle are ordered in rounds so the second sees the first's result (finding F2);
 //   * the weight is the scan-order product of the K factors (:124).
-// All arithmetic is fp64; the template parameter T is only the landmark STORAGE type.
+// All arithmetic is fp64; the template parameter T is only the landmark STORAGE type, R the number
+// of items a lane carries (1 when group x K <= 32, 2 for 32 < K <= 64).
 #include <math.h>
 
 #include "pk_common.cuh"
@@ -40,12 +40,11 @@
 namespace pk {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kChunk = 64;      // keys per particle per stage
-constexpr int kStages = 2;      // key stages in flight per warp
-constexpr int kMaxGroup = 8;    // particles per group
-constexpr int kMaxItems = 64;   // group * K
-constexpr int kCandPerItem = 4; // candidate slots per (particle, blob) item
-constexpr int kRecSlots = 36;   // staged cold records per group
+constexpr int kChunk = 64;           // keys per particle per stage
+constexpr int kKeyStride = kChunk + 4;  // words; +4 keeps the particles' key rows on distinct banks
+constexpr int kStages = 2;           // key stages in flight per warp
+constexpr int kMaxGroup = 8;         // particles per group
+constexpr int kMaxItems = 64;        // group * K
 constexpr unsigned kFull = 0xffffffffu;
 
 struct MeasureArgs {
@@ -70,13 +69,11 @@ struct MeasureArgs {
     unsigned okey[PK_MAX_OBS];                  // colour keys of the blobs
 };
 
-// fixed part of a warp's shared memory; the key ring [kStages][group][kChunk] and the record
-// staging area [2][kRecSlots] follow at keys_off / rec_off
+// fixed part of a warp's shared memory; the key ring [kStages][group][kKeyStride] and the record
+// staging area [2][32 * R] follow at keys_off / rec_off
 struct alignas(128) WarpSmem {
     double pose[4][kMaxGroup][4];
     double factor[kMaxItems];
-    int cand[2][kMaxItems][kCandPerItem];  // (staging slot + 1) << 20 | landmark index
-    int cnt[2][kMaxItems];
     int ids[kMaxItems];
     int bj[kMaxItems];
     int slot_s[4][kMaxGroup];
@@ -86,41 +83,47 @@ struct alignas(128) WarpSmem {
     uint64_t rec_bar[2];
 };
 
-// colour screen of one key against KT blobs: bit k set <=> squared byte distance <= bound
-template <int KT>
-__device__ __forceinline__ unsigned long long screen_keys(unsigned key, const MeasureArgs& A) {
-    unsigned lo = 0u, hi = 0u;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const unsigned d = __vabsdiffu4(key, A.okey[k]);
-        const int s = (int)__dp4a(d, d, 0u);
-        if (s <= A.key_thr) {
-            if (k < 32) lo |= 1u << (k & 31); else hi |= 1u << (k & 31);
-        }
-    }
-    return ((unsigned long long)hi << 32) | lo;
-}
+// per-item screen result, kept in registers between screen(g) and evaluate(g)
+struct Hits {
+    int cnt, c0, c1;
+};
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, int KT>
+template <typename T, int R>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 measure_kernel(const __grid_constant__ MeasureArgs A) {
     using Cold = typename Rec<T>::Cold;
+    constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + (size_t)warp * A.warp_smem;
     WarpSmem& S = *reinterpret_cast<WarpSmem*>(wbase);
-    unsigned* const key_ring = reinterpret_cast<unsigned*>(wbase + A.keys_off);  // [kStages][GP][kChunk]
-    unsigned char* const rec_area = wbase + A.rec_off;                           // [2][kRecSlots] Cold
+    const uint32_t s_base = smem_u32(wbase);
+    const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
+    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [2][32 * R] Cold
+    const uint32_t s_keybar = smem_u32(&S.key_bar[0]);
+    const uint32_t s_recbar = smem_u32(&S.rec_bar[0]);
+    const uint32_t s_pose = smem_u32(&S.pose[0][0][0]);
     const unsigned lt = lanemask_lt();
 
     const int K = A.K, GP = A.group, cap = A.capacity;
-    const unsigned long long kmask = (K >= 64) ? ~0ull : ((1ull << K) - 1ull);
+    const int key_thr = A.key_thr;
     const long long M = A.M;
     const long long n_groups = (M + GP - 1) / GP;
     const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
     const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
     const long long my_groups = (gw < n_groups) ? (n_groups - gw + total_warps - 1) / total_warps : 0;
+
+    // this lane's items: item w = r * 32 + lane -> (particle pl, blob k) within a group
+    int it_pl[R], it_k[R];
+    unsigned it_key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int w = r * 32 + lane;
+        it_pl[r] = w / K;
+        it_k[r] = w - it_pl[r] * K;
+        it_key[r] = (it_pl[r] < GP) ? A.okey[it_k[r]] : 0u;
+    }
 
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.key_bar[s], 1);
@@ -131,7 +134,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     __syncwarp();
 
     // ---- key producer (warp-uniform state) -----------------------------------------------------
-    long long p_git = 0, p_cnt = 0, s_git = 0, s_cnt = 0;  // producer / screen cursors
+    long long p_git = 0, s_git = 0;
+    unsigned p_cnt = 0, s_cnt = 0;  // stages produced / consumed
     int p_step = 0, p_nsteps = 1;
     int nx_slot = 0, nx_nlive = 0;  // lane pl holds slot / n_live of particle pl of the next group to open
     auto fetch_info = [&](long long git) {
@@ -150,7 +154,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     // Group info buffers are indexed git & 3: group g is being evaluated, g+1 screened, g+2 may
     // already be open in the producer.
     auto produce = [&]() {
-        while (p_git < my_groups && p_git <= s_git + 1 && p_cnt < s_cnt + kStages) {
+        while (p_git < my_groups && p_git <= s_git + 1 && p_cnt - s_cnt < (unsigned)kStages) {
             const int gi = (int)(p_git & 3);
             const long long p0 = (gw + p_git * total_warps) * GP;
             const int gpn = (int)min((long long)GP, M - p0);
@@ -165,7 +169,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 fetch_info(p_git + 1);
                 __syncwarp();
             }
-            const int stage = (int)(p_cnt % kStages);
+            const unsigned stage = p_cnt % kStages;
             unsigned bytes = 0;
             if (lane < gpn) {
                 const int nl = max(0, min(kChunk, S.nlive_s[gi][lane] - p_step * kChunk));
@@ -173,15 +177,15 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             }
             const unsigned total = __reduce_add_sync(kFull, bytes) + (p_step == 0 ? (unsigned)(gpn * 32) : 0u);
             fence_proxy_async();
+            const uint32_t bar = s_keybar + stage * 8u;
             if (lane == 0) {
-                mbar_arrive_expect_tx(&S.key_bar[stage], total);
-                if (p_step == 0) tma_load_1d(&S.pose[gi][0][0], A.pose4 + 4 * p0, (unsigned)(gpn * 32), &S.key_bar[stage]);
+                mbar_arrive_expect_tx_a(bar, total);
+                if (p_step == 0) tma_load_1d_a(s_pose + (uint32_t)gi * (kMaxGroup * 32), A.pose4 + 4 * p0, (unsigned)(gpn * 32), bar);
             }
             __syncwarp();
             if (bytes)  // every lane moves its own particle's keys
-                tma_load_1d(key_ring + ((size_t)stage * GP + lane) * kChunk,
-                            A.pool + (size_t)S.slot_s[gi][lane] * A.block_bytes + (size_t)p_step * kChunk * 4, bytes,
-                            &S.key_bar[stage]);
+                tma_load_1d_a(s_keys + ((stage * (unsigned)GP + (unsigned)lane) * kKeyStride) * 4u,
+                              A.pool + (size_t)S.slot_s[gi][lane] * A.block_bytes + (size_t)p_step * kChunk * 4, bytes, bar);
             ++p_cnt;
             if (++p_step >= p_nsteps) {
                 p_step = 0;
@@ -193,143 +197,155 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     unsigned long long st_matched = 0, st_unmatched = 0, st_eval = 0, st_same = 0, st_promoted = 0;
     unsigned st_flags = 0;
 
-    // ---- screen(g): colour-key screen of group g, candidate table + record prefetch -------------
-    auto screen = [&](long long git) {
+    // ---- screen(g): colour-key screen of group g + record prefetch --------------------------------
+    auto screen = [&](long long git, Hits (&H)[R]) {
         s_git = git;
         const int gi = (int)(git & 3), par = (int)(git & 1);
         const long long p0 = (gw + git * total_warps) * GP;
         const int gpn = (int)min((long long)GP, M - p0);
+        const int nitems = gpn * K;
         produce();  // opens this group if it is not open yet
-        for (int w = lane; w < kMaxItems; w += 32) S.cnt[par][w] = 0;
-        fence_proxy_async();  // the staging buffer was last read (generic proxy) two groups ago
-        __syncwarp();
-        unsigned char* rec = rec_area + (size_t)par * kRecSlots * sizeof(Cold);
-        int rec_n = 0;        // survivors so far (warp-uniform)
-        unsigned issued = 0;  // bytes this lane requested
+#pragma unroll
+        for (int r = 0; r < R; ++r) H[r] = Hits{0, -1, -1};
         const int nsteps = S.nsteps_s[gi];
         for (int step = 0; step < nsteps; ++step) {
             produce();
-            const int stage = (int)(s_cnt % kStages);
-            mbar_wait(&S.key_bar[stage], (unsigned)((s_cnt / kStages) & 1));
-            for (int pl = 0; pl < gpn; ++pl) {
-                const int nl = max(0, min(kChunk, S.nlive_s[gi][pl] - step * kChunk));
-                const unsigned* keys = key_ring + ((size_t)stage * GP + pl) * kChunk;
-                const unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
-                for (int row = 0; row * 32 < nl; ++row) {
-                    const int jl = row * 32 + lane;
-                    unsigned long long mask = 0ull;
-                    if (jl < nl) mask = screen_keys<KT>(keys[jl] & 0x00ffffffu, A) & kmask;
-                    const int j = step * kChunk + jl;
-                    for (;;) {
-                        const bool has = mask != 0ull;
-                        const unsigned b = __ballot_sync(kFull, has);
-                        if (b == 0u) break;
-                        if (has) {
-                            const int kk = __ffsll((long long)mask) - 1;
-                            mask &= mask - 1ull;
-                            const int item = pl * K + kk;
-                            const int c = atomicAdd(&S.cnt[par][item], 1);
-                            if (c < kCandPerItem) {
-                                const int pos = rec_n + __popc(b & lt);
-                                int entry = j;
-                                if (pos < kRecSlots) {
-                                    entry |= (pos + 1) << 20;
-                                    tma_load_1d(rec + (size_t)pos * sizeof(Cold), cold_ptr<T>(block, cap, j),
-                                                (unsigned)sizeof(Cold), &S.rec_bar[par]);
-                                    issued += (unsigned)sizeof(Cold);
-                                }
-                                S.cand[par][item][c] = entry;
-                            }
+            const unsigned stage = s_cnt % kStages;
+            mbar_wait_a(s_keybar + stage * 8u, (s_cnt / kStages) & 1u);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool act = (r * 32 + lane) < nitems;
+                const int pl = act ? it_pl[r] : 0;
+                const int nl = act ? max(0, min(kChunk, S.nlive_s[gi][pl] - step * kChunk)) : 0;
+                const uint32_t kp = s_keys + ((stage * (unsigned)GP + (unsigned)pl) * kKeyStride) * 4u;
+                const unsigned mykey = it_key[r];
+                unsigned lo = 0u, hi = 0u;
+#pragma unroll
+                for (int q = 0; q < kChunk / 4; ++q) {
+                    const int4 v = lds16_a(kp + 16u * q);
+                    const unsigned kk[4] = {(unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const unsigned d = __vabsdiffu4(kk[e] & 0x00ffffffu, mykey);
+                        const int sq = (int)__dp4a(d, d, 0u);
+                        const int bit = 4 * q + e;
+                        if (sq <= key_thr) {
+                            if (bit < 32) lo |= 1u << (bit & 31); else hi |= 1u << (bit & 31);
                         }
-                        rec_n += __popc(b);
                     }
+                }
+                unsigned long long m = ((unsigned long long)hi << 32) | lo;
+                m &= (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);  // keys beyond n_live are stale
+                while (m) {  // about one hit per item
+                    const int j = step * kChunk + __ffsll((long long)m) - 1;
+                    m &= m - 1ull;
+                    if (H[r].cnt == 0) H[r].c0 = j;
+                    else if (H[r].cnt == 1) H[r].c1 = j;
+                    H[r].cnt += 1;
                 }
             }
             __syncwarp();  // every lane is done with this key stage before it is refilled
             ++s_cnt;
         }
+        // request the cold record of each item's first hit into its fixed staging slot
+        fence_proxy_async();  // the slot was last read through the generic proxy two groups ago
+        unsigned issued = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (H[r].cnt > 0) {
+                const unsigned char* block = A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes;
+                tma_load_1d_a(s_rec + ((unsigned)par * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes,
+                              cold_ptr<T>(block, cap, H[r].c0), kRecBytes, s_recbar + (unsigned)par * 8u);
+                issued += kRecBytes;
+            }
+        }
         const unsigned total = __reduce_add_sync(kFull, issued);
-        if (lane == 0) mbar_arrive_expect_tx(&S.rec_bar[par], total);
+        if (lane == 0) mbar_arrive_expect_tx_a(s_recbar + (unsigned)par * 8u, total);
     };
 
     // ---- evaluate(g): association arg-max + sequential EKF updates + weight ----------------------
-    auto evaluate = [&](long long git) {
+    auto evaluate = [&](long long git, const Hits (&H)[R]) {
         const int gi = (int)(git & 3), par = (int)(git & 1);
         const long long p0 = (gw + git * total_warps) * GP;
         const int gpn = (int)min((long long)GP, M - p0);
         const int nitems = gpn * K;
-        const unsigned char* rec = rec_area + (size_t)par * kRecSlots * sizeof(Cold);
-        mbar_wait(&S.rec_bar[par], (unsigned)((git >> 1) & 1));
-        const int rounds = (nitems + 31) >> 5;  // 1 unless K > 32
+        mbar_wait_a(s_recbar + (unsigned)par * 8u, (unsigned)((git >> 1) & 1));
         // per-lane association result of the (last) evaluated round, kept in registers
         double best_pse = 0.0;
         int bestj = -1, lastj = -1;
         Landmark L;
         // ---- association (:84, match_features_to_scan): every blob against the PRE-update map ----
-        for (int ibase = 0; ibase < nitems; ibase += 32) {
-            const int w = ibase + lane;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int w = r * 32 + lane;
             const bool act = w < nitems;
-            const int pl = act ? w / K : 0, k = act ? w % K : 0;
+            const int pl = act ? it_pl[r] : 0, k = act ? it_k[r] : 0;
             const unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
-            const int cnt_raw = act ? S.cnt[par][w] : 0;
-            const int ncand = min(cnt_raw, kCandPerItem);
-            const int maxc = __reduce_max_sync(kFull, ncand);
+            const int cnt = act ? H[r].cnt : 0;
             // match_one :353-381: arg-max, strict '>' from 0.0, first (lowest slot) maximum wins
             double best = 0.0, pse = 0.0;
             best_pse = 0.0;
             bestj = -1;
             lastj = -1;
-            for (int c = 0; c < maxc; ++c) {
-                if (c < ncand) {
-                    const int e = S.cand[par][w][c];
-                    const int j = e & 0xfffff, sl = (e >> 20) - 1;
-                    if (sl >= 0) load_staged<T>(rec + (size_t)sl * sizeof(Cold), L);
-                    else load_landmark<T>(block, cap, j, L);
-                    lastj = j;
-                    const double Lk = match_likelihood(L, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
-                                                       A.diry[k], A.prm, st_flags, pse);
-                    st_eval += 1;
-                    if (Lk > best || (Lk == best && Lk > 0.0 && j < bestj)) {
-                        best = Lk;
-                        bestj = j;
-                        best_pse = pse;
-                    }
+            if (cnt > 0) {
+                load_staged<T>(s_rec + ((unsigned)par * 32u * R + (unsigned)w) * kRecBytes, L);
+                lastj = H[r].c0;
+                const double Lk = match_likelihood(L, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
+                                                   A.diry[k], A.prm, st_flags, pse);
+                st_eval += 1;
+                if (Lk > 0.0) {
+                    best = Lk;
+                    bestj = lastj;
+                    best_pse = pse;
                 }
             }
-            if (cnt_raw > kCandPerItem) {
-                // more colour-compatible landmarks than candidate slots: scan the whole map directly
-                best = 0.0;
-                bestj = -1;
-                lastj = -1;
-                const int nlive = S.nlive_s[gi][pl];
-                for (int j = 0; j < nlive; ++j) {
-                    Landmark Lj;
-                    load_landmark<T>(block, cap, j, Lj);
-                    const double Lk = match_likelihood(Lj, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
+            if (__any_sync(kFull, cnt > 1)) {
+                if (cnt == 2) {  // a second colour-compatible landmark: fetched directly
+                    load_landmark<T>(block, cap, H[r].c1, L);
+                    lastj = H[r].c1;
+                    const double Lk = match_likelihood(L, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
                                                        A.diry[k], A.prm, st_flags, pse);
                     st_eval += 1;
                     if (Lk > best) {
                         best = Lk;
-                        bestj = j;
+                        bestj = lastj;
                         best_pse = pse;
+                    }
+                } else if (cnt > 2) {  // many colour-compatible landmarks: scan the whole map in slot order
+                    best = 0.0;
+                    bestj = -1;
+                    lastj = -1;
+                    const int nlive = S.nlive_s[gi][pl];
+                    for (int j = 0; j < nlive; ++j) {
+                        Landmark Lj;
+                        load_landmark<T>(block, cap, j, Lj);
+                        const double Lk = match_likelihood(Lj, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k],
+                                                           A.dirx[k], A.diry[k], A.prm, st_flags, pse);
+                        st_eval += 1;
+                        if (Lk > best) {
+                            best = Lk;
+                            bestj = j;
+                            best_pse = pse;
+                        }
                     }
                 }
             }
-            if (rounds > 1 && act) {
+            if (R > 1 && act) {
                 S.bj[w] = bestj;
                 S.factor[w] = best_pse;
             }
         }
-        if (rounds > 1) __syncwarp();
+        if (R > 1) __syncwarp();
         // ---- sequential updates (:88-124) in scan order -------------------------------------------
-        for (int ibase = 0; ibase < nitems; ibase += 32) {
-            const int w = ibase + lane;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int w = r * 32 + lane;
             const bool act = w < nitems;
-            const int pl = act ? w / K : 0, k = act ? w % K : 0;
+            const int pl = act ? it_pl[r] : 0, k = act ? it_k[r] : 0;
             unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1];
-            if (rounds > 1) {
+            if (R > 1) {
                 bestj = act ? S.bj[w] : -1;
                 best_pse = act ? S.factor[w] : 0.0;
                 lastj = -1;  // records are re-read: an earlier round may have rewritten them
@@ -342,18 +358,18 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const int maxrank = __reduce_max_sync(kFull, matched ? rank : 0);
             double factor = A.prm.no_match_weight;  // :95 / :851-857
             int id_out = 0;
-            for (int r = 0; r <= maxrank; ++r) {
-                if (matched && rank == r) {
+            for (int q = 0; q <= maxrank; ++q) {
+                if (matched && rank == q) {
                     // the winner's record is in registers unless another candidate was evaluated after
                     // it, or an earlier blob of this frame has just rewritten the landmark
-                    if (r > 0 || lastj != bestj) load_landmark<T>(block, cap, bestj, L);
+                    if (q > 0 || lastj != bestj) load_landmark<T>(block, cap, bestj, L);
                     int promoted = 0;
                     bool changed = false;
                     factor = ekf_update_lm(L, px, py, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.prm, id_out, st_flags,
                                            promoted, changed, true, best_pse);
                     if (changed) store_landmark<T>(block, cap, bestj, L);
                     st_promoted += promoted;
-                    if (r > 0) st_same += 1;
+                    if (q > 0) st_same += 1;
                 }
                 if (maxrank > 0) __syncwarp();
             }
@@ -382,10 +398,14 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     };
 
     // ---- software pipeline over this warp's groups -----------------------------------------------
-    if (my_groups > 0) screen(0);
-    for (long long git = 0; git < my_groups; ++git) {
-        if (git + 1 < my_groups) screen(git + 1);
-        evaluate(git);
+    Hits Hcur[R], Hnext[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
+    for (long long git = -1; git < my_groups; ++git) {
+        if (git + 1 < my_groups) screen(git + 1, Hnext);
+        if (git >= 0) evaluate(git, Hcur);
+#pragma unroll
+        for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r];
     }
 
     // ---- statistics: one atomic per warp per counter ------------------------------------------------
@@ -412,36 +432,35 @@ __global__ void reset_weight_kernel(double* __restrict__ pose4, long long M) {
     if (i < M) pose4[4 * i + 3] = 1.0;  // cam_cb :73 with an empty scan
 }
 
-template <typename T, int KT>
+template <typename T, int R>
 static int launch_measure(MeasureArgs& args, cudaStream_t st) {
     static int configured_smem = -1;
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     args.keys_off = (int)align128(sizeof(WarpSmem));
-    args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kChunk * 4);
-    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * kRecSlots * sizeof(typename Rec<T>::Cold));
+    args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
+    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
     if ((int)smem > configured_smem) {
-        PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_smem = (int)smem;
     }
     int ctas_per_sm = 0;
-    PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T, KT>, kWarpsPerCta * 32, smem));
+    PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T, R>, kWarpsPerCta * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const long long n_groups = (args.M + args.group - 1) / args.group;
     long long grid = (long long)num_sms() * ctas_per_sm;
     const long long need = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    measure_kernel<T, KT><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(args);
+    measure_kernel<T, R><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(args);
     PK_LAUNCH_CHECK("measure_kernel");
     return PK_OK;
 }
 
 template <typename T>
 static int dispatch_measure(MeasureArgs& args, cudaStream_t st) {
-    if (args.K <= 8) return launch_measure<T, 8>(args, st);
-    if (args.K <= 32) return launch_measure<T, 32>(args, st);
-    return launch_measure<T, 64>(args, st);
+    if (args.K <= 32) return launch_measure<T, 1>(args, st);
+    return launch_measure<T, 2>(args, st);
 }
 
 }  // namespace pk
