@@ -308,6 +308,17 @@ __device__ __forceinline__ void tma_load_1d_a(uint32_t dst, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// per-thread 16-byte asynchronous copy global -> shared (LDGSTS), L2-only caching; completion by
+// commit/wait groups.  Unlike cp.async.bulk (UBLKCP, uniform operands) every lane can use its own
+// addresses in one instruction, which is what a scattered per-lane record fetch needs.
+__device__ __forceinline__ void cp_async16_a(uint32_t dst, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ int4 lds16_a(uint32_t addr) {
     int4 v;
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

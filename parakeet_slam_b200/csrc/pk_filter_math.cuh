@@ -8,6 +8,38 @@
 
 namespace pk {
 
+// ---------------------------------------------------------------------------------------------
+// Branch-free atan2 (fp64, <= 1.5 ulp).  libm's atan2 costs ~250 warp-instructions here because
+// its quadrant / magnitude cases diverge across the lanes of a warp.  One division: with
+// mn = min(|x|,|y|), mx = max(|x|,|y|), either t = mn/mx (t <= tan(pi/8)) or
+// t = (mn - mx)/(mn + mx) and pi/4 is added, so |t| <= tan(pi/8) < 7/16 always, where the odd
+// minimax polynomial of fdlibm's s_atan.c (aT[0..10], error < 1 ulp) applies.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pk_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool big = mn > 0.41421356237309503 * mx;
+    const double num = big ? mn - mx : mn;
+    const double den = big ? mn + mx : mx;
+    double t = num / den;
+    if (den == 0.0) t = 0.0;  // atan2(+-0, +-0): math.atan2 gives +-0 / +-pi like the selects below
+    const double z = t * t, w = z * z;
+    const double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, 1.62858201153657823623e-02, 4.97687799461593236017e-02),
+                                                         6.66107313738753120669e-02),
+                                                  9.09088713343650656196e-02),
+                                           1.42857142725034663711e-01),
+                                    3.33333333333329318027e-01);
+    const double s2 = w * fma(w, fma(w, fma(w, fma(w, -3.65315727442169155270e-02, -5.83357013379057348645e-02),
+                                                  -7.69187620504482999495e-02),
+                                           -1.11111104054623557880e-01),
+                                    -1.99999999998764832476e-01);
+    double r = t - t * (s1 + s2);
+    if (big) r = 7.85398163397448278999e-01 + (r + 3.06161699786838301793e-17);
+    if (ay > ax) r = 1.57079632679489655800e+00 - (r - 6.12323399573676603587e-17);
+    if (signbit(x)) r = 3.14159265358979311600e+00 - (r - 1.22464679914735317720e-16);
+    return copysign(r, y);
+}
+
 constexpr double kLog2Pi = 1.8378770664093453;  // math.log(2*pi)
 
 // ---------------------------------------------------------------------------------------------
@@ -23,7 +55,7 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
     if (fabs(cdist) > prm.color_gate) return 0.0;
     // bearing gate :408-415, :433
     double dx = L.x - px, dy = L.y - py;
-    double pse = atan2(dy, dx);
+    double pse = pk_atan2(dy, dx);
     pse_out = pse;
     double del = beta - (pse - pth);
     if (fabs(del) > prm.bearing_gate) return 0.0;
@@ -68,7 +100,7 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     double hy = (q == 0.0) ? 0.0 : dx / q;
     // generate_measurement :871 -- world-frame bearing, no heading subtraction (finding F4a)
     // (the association step evaluates the same atan2(fy - sy, fx - sx), :408/:473; reuse it)
-    double zb = have_zb ? zb_in : atan2(dy, dx);
+    double zb = have_zb ? zb_in : pk_atan2(dy, dx);
     double a = L.sp[0], b = L.sp[1], c = L.sp[2], d = L.sp[3];
     // measurement_covariance :817-819   Q = H Sigma H^T + Qt = diag(s) (+) Sc
     double t0 = hx * a + hy * c, t1 = hx * b + hy * d;

@@ -19,8 +19,9 @@
 //     LDS.128) against a bound that provably contains the reference's colour gate (:441) -- the
 //     cheapest and most selective of its gates, and probability_of_match is 0 whenever it fails,
 //     whatever the evaluation order.  Hits (about one per item) stay in registers; the lane
-//     requests the cold record of its first hit at once with its own cp.async.bulk into a fixed
-//     staging slot in shared memory;
+//     requests the cold record of its first hit at once into its own staging slot in shared
+//     memory with per-thread cp.async copies (a scattered, per-lane fetch -- cp.async.bulk takes
+//     warp-uniform operands and would serialise over the lanes);
 //   * the warp is software-pipelined across groups: it screens group g+1 (and so has that
 //     group's records in flight) BEFORE it evaluates group g, so neither the key stream nor the
 //     scattered record fetches expose DRAM latency;
@@ -80,7 +81,6 @@ struct alignas(128) WarpSmem {
     int nlive_s[4][kMaxGroup];
     int nsteps_s[4];
     uint64_t key_bar[kStages];
-    uint64_t rec_bar[2];
 };
 
 // per-item screen result, kept in registers between screen(g) and evaluate(g)
@@ -102,7 +102,6 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
     const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [2][32 * R] Cold
     const uint32_t s_keybar = smem_u32(&S.key_bar[0]);
-    const uint32_t s_recbar = smem_u32(&S.rec_bar[0]);
     const uint32_t s_pose = smem_u32(&S.pose[0][0][0]);
     const unsigned lt = lanemask_lt();
 
@@ -127,8 +126,6 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
 
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.key_bar[s], 1);
-        mbar_init(&S.rec_bar[0], 1);
-        mbar_init(&S.rec_bar[1], 1);
         mbar_fence_init();
     }
     __syncwarp();
@@ -247,29 +244,29 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             __syncwarp();  // every lane is done with this key stage before it is refilled
             ++s_cnt;
         }
-        // request the cold record of each item's first hit into its fixed staging slot
-        fence_proxy_async();  // the slot was last read through the generic proxy two groups ago
-        unsigned issued = 0;
+        // request the cold record of each item's first hit into the lane's own staging slot:
+        // per-lane addresses -> cp.async (LDGSTS), one commit group per screened group
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (H[r].cnt > 0) {
-                const unsigned char* block = A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes;
-                tma_load_1d_a(s_rec + ((unsigned)par * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes,
-                              cold_ptr<T>(block, cap, H[r].c0), kRecBytes, s_recbar + (unsigned)par * 8u);
-                issued += kRecBytes;
+                const unsigned char* src =
+                    cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap, H[r].c0);
+                const uint32_t dst = s_rec + ((unsigned)par * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
+#pragma unroll
+                for (unsigned q = 0; q < kRecBytes / 16u; ++q) cp_async16_a(dst + 16u * q, src + 16u * q);
             }
         }
-        const unsigned total = __reduce_add_sync(kFull, issued);
-        if (lane == 0) mbar_arrive_expect_tx_a(s_recbar + (unsigned)par * 8u, total);
+        cp_async_commit();
     };
 
     // ---- evaluate(g): association arg-max + sequential EKF updates + weight ----------------------
-    auto evaluate = [&](long long git, const Hits (&H)[R]) {
+    auto evaluate = [&](long long git, const Hits (&H)[R], bool more_in_flight) {
         const int gi = (int)(git & 3), par = (int)(git & 1);
         const long long p0 = (gw + git * total_warps) * GP;
         const int gpn = (int)min((long long)GP, M - p0);
         const int nitems = gpn * K;
-        mbar_wait_a(s_recbar + (unsigned)par * 8u, (unsigned)((git >> 1) & 1));
+        // this group's records were committed one group ago; the next group's may still be in flight
+        if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
         // per-lane association result of the (last) evaluated round, kept in registers
         double best_pse = 0.0;
         int bestj = -1, lastj = -1;
@@ -403,7 +400,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
     for (long long git = -1; git < my_groups; ++git) {
         if (git + 1 < my_groups) screen(git + 1, Hnext);
-        if (git >= 0) evaluate(git, Hcur);
+        if (git >= 0) evaluate(git, Hcur, git + 1 < my_groups);
 #pragma unroll
         for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r];
     }
