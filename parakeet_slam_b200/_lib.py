@@ -19,7 +19,8 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-LIB_PATH = os.path.join(PKG_DIR, "libparakeet_b200.so")
+LIB_PATH = os.environ.get("PARAKEET_B200_LIB") or os.path.join(PKG_DIR, "libparakeet_b200.so")
+_LIB_OVERRIDDEN = bool(os.environ.get("PARAKEET_B200_LIB"))
 SOURCES = ("pk_abi.cu", "pk_motion.cu", "pk_measure.cu", "pk_resample.cu", "pk_probe.cu")
 HEADERS = (os.path.join(CSRC_DIR, "pk_common.cuh"), os.path.join(INCLUDE_DIR, "parakeet_b200.h"))
 
@@ -57,6 +58,8 @@ def _sources():
 
 
 def needs_build() -> bool:
+    if _LIB_OVERRIDDEN:
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

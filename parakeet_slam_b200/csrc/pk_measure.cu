@@ -40,7 +40,13 @@
 
 namespace pk {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef PK_MEASURE_WARPS
+#define PK_MEASURE_WARPS 6
+#endif
+#ifndef PK_MEASURE_MINB
+#define PK_MEASURE_MINB 2
+#endif
+constexpr int kWarpsPerCta = PK_MEASURE_WARPS;
 constexpr int kChunk = 64;           // keys per particle per stage
 constexpr int kKeyStride = kChunk + 4;  // words; +4 keeps the particles' key rows on distinct banks
 constexpr int kStages = 2;           // key stages in flight per warp
@@ -90,7 +96,7 @@ struct Hits {
 
 // ---------------------------------------------------------------------------------------------
 template <typename T, int R>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PK_MEASURE_MINB)
 measure_kernel(const __grid_constant__ MeasureArgs A) {
     using Cold = typename Rec<T>::Cold;
     constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
@@ -223,7 +229,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     const unsigned kk[4] = {(unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const unsigned d = __vabsdiffu4(kk[e] & 0x00ffffffu, mykey);
+                        const unsigned d = __vabsdiffu4(kk[e], mykey);
                         const int sq = (int)__dp4a(d, d, 0u);
                         const int bit = 4 * q + e;
                         if (sq <= key_thr) {
