@@ -274,8 +274,8 @@ def run_ours(args):
     ms_total = start.elapsed_time(stop)
     st = fs.stats()
     matched_frac = st["matched"] / float(max(1, st["matched"] + st["unmatched"]))
-    eval_per_particle = st["evaluated"] / float(M_local)
-    f_dup = st["blocks_copied"] / float(M_local)
+    eval_per_particle = st["evaluated"] / float(M_total if world > 1 else M_local)
+    f_dup = st["blocks_copied"] / float(M_total if world > 1 else M_local)
     k_ms = [[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in per_step_events]
     ms_motion = sum(k[0] for k in k_ms) / steps
     ms_measure = sum(k[1] for k in k_ms) / steps

@@ -21,11 +21,12 @@
  *   aux2    int[M][2]       n_live landmarks, next_id            (travels with the particle)
  *   slot    int[M]          index of the particle's landmark block in the pool
  *   pool    bytes           n_slots blocks of pk_block_bytes(capacity, dtype); one block =
- *                           [hot: capacity x HOT][cold: capacity x COLD]
- *                             f32: HOT 16 B = r,g,b (float), meta (int)
- *                                  COLD 64 B = x,y, Sp[2][2], Sc[3][3] (15 float), id (int)
- *                             f64: HOT 32 B = r,g,b (double), meta (int), pad
- *                                  COLD 128 B = x,y, Sp[2][2], Sc[3][3] (15 double), id, pad
+ *                           [hot region: capacity x 4 B, padded to 16 B][cold region: capacity x COLD]
+ *                             hot  4 B  = colour KEY: r,g,b rounded and clamped to bytes (the only
+ *                                         part streamed for every landmark by the fused kernel)
+ *                             cold f32 64 B  = r,g,b, x,y, Sp lower triangle (3), Sc lower triangle (6)
+ *                                              as float, id, meta  (one 64-byte DRAM granule)
+ *                                  f64 160 B = r,g,b, x,y, Sp[2][2], Sc[3][3] as double, id, meta, pad
  *                           meta = update_count | PK_META_IMMUTABLE | PK_META_POTENTIAL
  *                           The 5x5 landmark covariance of the reference is stored as its two
  *                           diagonal blocks; the cross blocks are exactly zero in every state the
@@ -171,6 +172,22 @@ int pk_resample_gather(const long long* ancestors, const int* offspring, long lo
                        const double* pose4_in, double* pose4_out, const int* aux2_in,
                        int* aux2_out, const int* slot_in, int* slot_out, void* pool, int capacity,
                        int dtype, void* workspace, long long* n_copied_out, void* stream);
+/* Sharded form (particles split in contiguous ranges over ranks, one process per GPU).  The
+ * rank's Ml output slots are [n_lo incoming from lower ranks | n_loc offspring of local ancestors
+ * | the rest incoming from higher ranks].  ancestors_win[Ml]: global ancestor index per output slot
+ * (read only for the local part); offspring_local[Ml]: per local particle, its number of outputs
+ * inside this rank's window.  recv_pose / recv_aux: the incoming particles in source-rank order.
+ * Incoming particles and local duplicates take blocks freed by local particles without local
+ * offspring; unpack_dst[n_in] receives the destination block of each incoming particle (feed it
+ * to pk_copy_blocks with the receive buffer as source).  Call AFTER the outgoing particles were
+ * packed.  total_dead_out (device int64): number of freed blocks. */
+int pk_resample_gather_sharded(const long long* ancestors_win, const int* offspring_local,
+                               long long Ml, long long particle_offset, long long n_lo,
+                               long long n_loc, const double* pose4_in, double* pose4_out,
+                               const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
+                               const double* recv_pose, const int* recv_aux, void* pool,
+                               int capacity, int dtype, void* workspace, int* unpack_dst,
+                               long long* total_dead_out, void* stream);
 /* Raw block mover (also used by the sharded path to pack / unpack migrating particles): copies n
  * landmark blocks src_base[src_slot[i]] -> dst_base[dst_slot[i]] (n = min(*n_dev, n_max) when
  * n_dev != NULL) staged through shared memory with TMA bulk copies.  n_live (nullable) limits

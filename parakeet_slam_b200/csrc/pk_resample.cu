@@ -313,6 +313,58 @@ assign_kernel(const long long* __restrict__ ancestors, long long M, const double
     }
 }
 
+// G4s: sharded form of G4.  The rank's Ml output slots are [incoming from lower ranks (n_lo) |
+// offspring of local ancestors (n_loc) | incoming from higher ranks (Ml - n_lo - n_loc)] because
+// ancestors are globally ascending.  Incoming particles and local duplicates both take blocks
+// freed by local particles with no local offspring.
+__global__ void __launch_bounds__(256)
+assign_sharded_kernel(const long long* __restrict__ ancestors, long long Ml, long long particle_offset, long long n_lo,
+                      long long n_loc, const double* __restrict__ pose_in, double* __restrict__ pose_out,
+                      const int* __restrict__ aux_in, int* __restrict__ aux_out, const int* __restrict__ slot_in,
+                      int* __restrict__ slot_out, const double* __restrict__ recv_pose, const int* __restrict__ recv_aux,
+                      const int* __restrict__ dead_excl, const int* __restrict__ free_list,
+                      const long long* __restrict__ total_dead, int* __restrict__ copy_src, int* __restrict__ copy_dst,
+                      int* __restrict__ copy_nlive, int* __restrict__ unpack_dst) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Ml) return;
+    const long long n_in = Ml - n_loc;
+    const long long n_dups = *total_dead - n_in;  // local outputs that are not the first of their ancestor
+    double2* dst = reinterpret_cast<double2*>(pose_out + 4 * k);
+    if (k < n_lo || k >= n_lo + n_loc) {
+        const long long r = (k < n_lo) ? k : k - n_loc;  // index in the receive buffers (source-rank order)
+        const long long nidx = (k < n_lo) ? k : n_lo + n_dups + (k - n_lo - n_loc);
+        const double2* src = reinterpret_cast<const double2*>(recv_pose + 4 * r);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        reinterpret_cast<int2*>(aux_out)[k] = reinterpret_cast<const int2*>(recv_aux)[r];
+        const int d = free_list[nidx];
+        slot_out[k] = d;
+        unpack_dst[r] = d;
+        copy_src[nidx] = -1;  // not a pool-to-pool copy
+        copy_dst[nidx] = d;
+        copy_nlive[nidx] = 0;
+        return;
+    }
+    const long long a = ancestors[k] - particle_offset;  // local ancestor
+    const double2* src = reinterpret_cast<const double2*>(pose_in + 4 * a);
+    dst[0] = src[0];
+    dst[1] = src[1];
+    const int2 ax = reinterpret_cast<const int2*>(aux_in)[a];
+    reinterpret_cast<int2*>(aux_out)[k] = ax;
+    const bool first = (k == n_lo) || (ancestors[k - 1] != ancestors[k]);
+    if (first) {
+        slot_out[k] = slot_in[a];
+    } else {
+        const long long alive_before = a - dead_excl[a];
+        const long long nidx = n_lo + (k - n_lo) - alive_before - 1;
+        const int d = free_list[nidx];
+        slot_out[k] = d;
+        copy_src[nidx] = slot_in[a];
+        copy_dst[nidx] = d;
+        copy_nlive[nidx] = ax.x;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // G5: block mover.  One warp per CTA, one elected lane drives a 4-deep ring of 4 KiB shared
 // memory buffers: cp.async.bulk global->shared (mbarrier complete_tx), then cp.async.bulk
@@ -341,6 +393,7 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
         long long off;  // offset inside the segment
     };
     auto seg_len = [&](long long item, int seg) -> long long {
+        if (src_slot[item] < 0) return 0;  // entry not served by this launch (e.g. filled from a receive buffer)
         const int nl = nlive ? min(nlive[item], capacity) : capacity;
         // hot keys are 4 B each: round the range up to the 16 B granularity of a bulk copy
         return seg == 0 ? (((long long)nl * hot_b + 15) & ~15ll) : (long long)nl * cold_b;
@@ -613,6 +666,41 @@ int pk_resample_gather(const long long* ancestors, const int* offspring, long lo
     PK_LAUNCH_CHECK("assign_kernel");
     if (capacity > 0)
         return copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, M, n_copied_out, st);
+    return PK_OK;
+}
+
+int pk_resample_gather_sharded(const long long* ancestors_win, const int* offspring_local, long long Ml,
+                               long long particle_offset, long long n_lo, long long n_loc, const double* pose4_in,
+                               double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
+                               const double* recv_pose, const int* recv_aux, void* pool, int capacity, int dtype,
+                               void* workspace, int* unpack_dst, long long* total_dead_out, void* stream) {
+    PK_CHECK_ARG(ancestors_win && offspring_local && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out &&
+                     pool && workspace && unpack_dst && total_dead_out,
+                 "null pointer");
+    PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31), "Ml");
+    PK_CHECK_ARG(n_lo >= 0 && n_loc >= 0 && n_lo + n_loc <= Ml, "window split");
+    PK_CHECK_ARG(n_loc == Ml || (recv_pose && recv_aux), "receive buffers are NULL");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    GatherWs g = carve(workspace, Ml);
+    const long long nb = num_blocks(Ml);
+    dead_scan_kernel<<<(unsigned)((nb + kScanWarps - 1) / kScanWarps), kScanWarps * 32, 0, st>>>(offspring_local, Ml,
+                                                                                                 g.dead_excl, g.block_dead, nb);
+    PK_LAUNCH_CHECK("dead_scan_kernel");
+    block_offsets_kernel<<<1, 1024, 0, st>>>(g.block_dead, nb, g.block_off, total_dead_out);
+    PK_LAUNCH_CHECK("block_offsets_kernel");
+    const int threads = 256;
+    const unsigned grid = (unsigned)((Ml + threads - 1) / threads);
+    free_list_kernel<<<grid, threads, 0, st>>>(offspring_local, slot_in, Ml, g.dead_excl, g.block_off, g.free_list);
+    PK_LAUNCH_CHECK("free_list_kernel");
+    assign_sharded_kernel<<<grid, threads, 0, st>>>(ancestors_win, Ml, particle_offset, n_lo, n_loc, pose4_in, pose4_out,
+                                                    aux2_in, aux2_out, slot_in, slot_out, recv_pose, recv_aux, g.dead_excl,
+                                                    g.free_list, total_dead_out, g.copy_src, g.copy_dst, g.copy_nlive,
+                                                    unpack_dst);
+    PK_LAUNCH_CHECK("assign_sharded_kernel");
+    // local duplicates: pool -> pool (entries that belong to incoming particles carry src = -1 and are skipped)
+    if (capacity > 0)
+        return copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, Ml, total_dead_out, st);
     return PK_OK;
 }
 

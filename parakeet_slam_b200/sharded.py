@@ -1,0 +1,225 @@
+"""Particle-sharded FastSLAM: one process per GPU, particles split in contiguous index ranges.
+
+Motion, association, EKF updates and weighting touch only a particle's own state, so they run
+unchanged on every shard.  Two steps couple particles:
+
+* resampling -- every rank needs the global prefix of the weights.  Ranks ``all_gather`` their
+  per-block weight totals (8 B per 1024 particles) and each one folds ALL block totals in global
+  order with the same fixed tree (``pk_resample_thresholds``), so the thresholds, and therefore the
+  ancestors, are bit-identical to the single-GPU filter whatever the number of ranks.  Resampled
+  particles whose output slot lives on another rank move with one ``all_to_all_single`` per payload
+  (pose, aux, landmark blocks) straight out of / into the slot pools; the send / receive counts
+  follow from the emitted-output counts at the rank boundaries, which every rank already holds --
+  no extra count exchange;
+* ``summary()`` / ``best_particle()`` -- an all-reduce of five doubles / an all-gather of two.
+
+``plan_exchange`` is the pure host-side arithmetic of the exchange; it is tested on CPU with a
+world-size-2 ``gloo`` group (``tests/test_sharding_cpu.py``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from .core import FastSLAM
+
+
+def plan_exchange(emitted_before, particles_per_rank, rank):
+    """Exchange plan of one resampling step.
+
+    ``emitted_before[g]`` (length G+1) = number of output slots whose ancestor lives on a rank
+    < g; rank g's offspring therefore occupy the global output slots
+    ``[emitted_before[g], emitted_before[g+1])`` and output slot k is owned by rank
+    ``k // particles_per_rank``.  Returns a dict with, for ``rank``:
+
+    ``send[h]``  particles this rank sends to rank h (``send[rank]`` stay local),
+    ``recv[g]``  particles it receives from rank g,
+    ``send_start[h]`` offset of the run for rank h inside this rank's offspring list,
+    ``n_lo`` / ``n_loc`` / ``n_hi`` the split of its own output window.
+    """
+    E = [int(v) for v in emitted_before]
+    G = len(E) - 1
+    Ml = int(particles_per_rank)
+
+    def overlap(g, h):
+        lo = max(E[g], h * Ml)
+        hi = min(E[g + 1], (h + 1) * Ml)
+        return max(0, hi - lo)
+
+    send = [overlap(rank, h) for h in range(G)]
+    recv = [overlap(g, rank) for g in range(G)]
+    send_start = [max(E[rank], h * Ml) - E[rank] if send[h] else 0 for h in range(G)]
+    n_lo = sum(recv[:rank])
+    n_loc = recv[rank]
+    n_hi = sum(recv[rank + 1:])
+    assert n_lo + n_loc + n_hi == Ml, (E, Ml, rank)
+    return dict(send=send, recv=recv, send_start=send_start, n_lo=n_lo, n_loc=n_loc, n_hi=n_hi,
+                emit_lo=E[rank], emit_n=E[rank + 1] - E[rank])
+
+
+class ShardedFastSLAM(FastSLAM):
+    """``FastSLAM`` over ``torch.distributed`` (NCCL): ``num_particles`` is the GLOBAL particle count,
+    each rank holds ``num_particles / world_size`` of them (a multiple of 1024)."""
+
+    def __init__(self, preset_features=[], *, num_particles, group=None, **kw):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self._group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        M_total = int(num_particles)
+        if M_total % self.world_size or (M_total // self.world_size) % _lib.PK_SCAN_BLOCK:
+            raise ValueError("num_particles must be a multiple of world_size * %d" % _lib.PK_SCAN_BLOCK)
+        self.num_particles_total = M_total
+        super().__init__(preset_features, num_particles=M_total // self.world_size, **kw)
+        self.particle_offset = self.rank * self.num_particles
+        torch = self._torch
+        G, nb = self.world_size, self._nb
+        dev = self._device
+        self._all_sums = torch.zeros((G * nb,), dtype=torch.float64, device=dev)
+        self._all_prefix = torch.zeros((G * nb, 2), dtype=torch.float64, device=dev)
+        self._all_count = torch.zeros((G * nb + 1,), dtype=torch.int64, device=dev)
+        self._emit = torch.zeros((max(2 * self.num_particles, 1),), dtype=torch.int64, device=dev)
+        self._unpack_dst = torch.zeros((self.num_particles,), dtype=torch.int32, device=dev)
+        self._rank_idx = torch.arange(0, G * nb + 1, nb, device=dev)
+        self.last_plan = None
+
+    # noise for the parity mode: every rank draws the GLOBAL block and keeps its slice, so the
+    # stream consumed is the one a single-process filter would consume
+    def _draw_noise(self, M):
+        if self._noise == "philox":
+            return None
+        lo = self.particle_offset
+        if self._noise == "numpy":
+            z = np.random.standard_normal((self.num_particles_total, 3))
+        else:
+            z = np.ascontiguousarray(self._noise(self.num_particles_total), dtype=np.float64)
+        return np.ascontiguousarray(z[lo:lo + M])
+
+    def low_variance_resample(self):
+        torch, lib, dist = self._torch, self._lib, self._dist
+        Ml, Mt, G, me, nb = self.num_particles, self.num_particles_total, self.world_size, self.rank, self._nb
+        dev = self._device
+        with self._lock, torch.cuda.device(dev):
+            u01 = float(self._uniform())  # every rank must draw the same value (same seed / same source)
+            st = self._stream()
+            cur, nxt = self._cur, 1 - self._cur
+            pose_in, aux_in, slot_in = self._pose[cur], self._aux[cur], self._slot[cur]
+            _lib.check(lib.pk_weight_scan(_lib.ptr(pose_in), Ml, _lib.ptr(self._cumsum), _lib.ptr(self._block_sums), st),
+                       "pk_weight_scan")
+            # weight normaliser: all ranks obtain all block totals, then fold them identically
+            dist.all_gather_into_tensor(self._all_sums, self._block_sums, group=self._group)
+            _lib.check(lib.pk_resample_thresholds(_lib.ptr(self._all_sums), G * nb, Mt, u01, _lib.ptr(self._plan),
+                                                  _lib.ptr(self._all_prefix), _lib.ptr(self._all_count), st),
+                       "pk_resample_thresholds")
+            E = self._all_count[self._rank_idx].cpu().tolist()   # outputs emitted before each rank (one small D2H)
+            plan = plan_exchange(E, Ml, me)
+            self.last_plan = plan
+            if plan["emit_n"] > self._emit.numel():
+                self._emit = torch.zeros((plan["emit_n"],), dtype=torch.int64, device=dev)
+            # my particles' offspring: emit[k - emit_lo] = global ancestor index, ascending
+            _lib.check(lib.pk_resample_ancestors(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
+                                                 _lib.ptr(self._plan), _lib.ptr(self._all_prefix),
+                                                 _lib.ptr(self._all_count), Mt, plan["emit_lo"], max(plan["emit_n"], 1),
+                                                 _lib.ptr(self._out_lo), _lib.ptr(self._offspring), _lib.ptr(self._emit),
+                                                 _lib.ptr(self._big_runs), st), "pk_resample_ancestors")
+            emit = self._emit[:plan["emit_n"]]
+            # ---- pack what leaves this rank (before any block is overwritten) -------------------
+            send_counts = list(plan["send"])
+            send_counts[me] = 0
+            recv_counts = list(plan["recv"])
+            recv_counts[me] = 0
+            n_send, n_in = sum(send_counts), sum(recv_counts)
+            parts = [emit[plan["send_start"][h]:plan["send_start"][h] + send_counts[h]] for h in range(G)
+                     if send_counts[h]]
+            bb = self.block_bytes
+            if n_send:
+                src_local = (torch.cat(parts) - self.particle_offset)
+                send_pose = pose_in.index_select(0, src_local)
+                send_aux = aux_in.index_select(0, src_local)
+                send_blocks = torch.empty((n_send, max(bb, 1)), dtype=torch.uint8, device=dev)
+                if bb:
+                    src_slots = slot_in.index_select(0, src_local).contiguous()
+                    dst_idx = torch.arange(n_send, dtype=torch.int32, device=dev)
+                    _lib.check(lib.pk_copy_blocks(_lib.ptr(self._pool), _lib.ptr(send_blocks), self.capacity, self._dt,
+                                                  _lib.ptr(src_slots), _lib.ptr(dst_idx),
+                                                  _lib.ptr(send_aux[:, 0].contiguous()), n_send, None, st),
+                               "pk_copy_blocks(pack)")
+            else:
+                send_pose = torch.empty((0, 4), dtype=torch.float64, device=dev)
+                send_aux = torch.empty((0, 2), dtype=torch.int32, device=dev)
+                send_blocks = torch.empty((0, max(bb, 1)), dtype=torch.uint8, device=dev)
+            recv_pose = torch.empty((max(n_in, 1), 4), dtype=torch.float64, device=dev)
+            recv_aux = torch.empty((max(n_in, 1), 2), dtype=torch.int32, device=dev)
+            recv_blocks = torch.empty((max(n_in, 1), max(bb, 1)), dtype=torch.uint8, device=dev)
+            if G > 1:
+                # cross-shard resampled particles: payloads move rank to rank over NVLink
+                dist.all_to_all_single(recv_pose[:n_in], send_pose, recv_counts, send_counts, group=self._group)
+                dist.all_to_all_single(recv_aux[:n_in], send_aux, recv_counts, send_counts, group=self._group)
+                if bb:
+                    dist.all_to_all_single(recv_blocks[:n_in], send_blocks, recv_counts, send_counts, group=self._group)
+            # ---- local assignment: survivors keep their block, duplicates and arrivals take freed ones
+            win_lo = me * Ml
+            off_local = torch.clamp(torch.clamp(self._out_lo[:Ml] + self._offspring[:Ml], max=win_lo + Ml)
+                                    - torch.clamp(self._out_lo[:Ml], min=win_lo), min=0).to(torch.int32)
+            anc_win = torch.zeros((Ml,), dtype=torch.int64, device=dev)
+            n_lo, n_loc = plan["n_lo"], plan["n_loc"]
+            if n_loc:
+                s0 = plan["send_start"][me]
+                anc_win[n_lo:n_lo + n_loc] = emit[s0:s0 + n_loc]
+            _lib.check(lib.pk_resample_gather_sharded(
+                _lib.ptr(anc_win), _lib.ptr(off_local), Ml, self.particle_offset, n_lo, n_loc,
+                _lib.ptr(pose_in), _lib.ptr(self._pose[nxt]), _lib.ptr(aux_in), _lib.ptr(self._aux[nxt]),
+                _lib.ptr(slot_in), _lib.ptr(self._slot[nxt]), _lib.ptr(recv_pose), _lib.ptr(recv_aux),
+                _lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self._gather_ws), _lib.ptr(self._unpack_dst),
+                _lib.ptr(self._n_copied), st), "pk_resample_gather_sharded")
+            if n_in and bb:
+                src_idx = torch.arange(n_in, dtype=torch.int32, device=dev)
+                _lib.check(lib.pk_copy_blocks(_lib.ptr(recv_blocks), _lib.ptr(self._pool), self.capacity, self._dt,
+                                              _lib.ptr(src_idx), _lib.ptr(self._unpack_dst),
+                                              _lib.ptr(recv_aux[:n_in, 0].contiguous()), n_in, None, st),
+                           "pk_copy_blocks(unpack)")
+            self._cur = nxt
+            if self.keep_trace:
+                self.last_ancestors = anc_win.clone()
+            # keep the staging tensors alive until the stream has consumed them
+            self._staging = (send_pose, send_aux, send_blocks, recv_pose, recv_aux, recv_blocks, off_local, anc_win)
+
+    def summary(self):
+        torch, lib, dist = self._torch, self._lib, self._dist
+        with self._lock, torch.cuda.device(self._device):
+            _lib.check(lib.pk_summary_partial(_lib.ptr(self.pose), self.num_particles, _lib.ptr(self._out5),
+                                              _lib.ptr(self._red_ws), self._stream()), "pk_summary_partial")
+            dist.all_reduce(self._out5, group=self._group)
+            s = self._out5.cpu().numpy()
+        count = float(self.num_particles_total)
+        return (float(s[0] / count), float(s[1] / count), math.atan2(float(s[2]), float(s[3])),)
+
+    def best_particle(self):
+        torch, lib, dist = self._torch, self._lib, self._dist
+        with self._lock, torch.cuda.device(self._device):
+            _lib.check(lib.pk_best_particle(_lib.ptr(self.pose), self.num_particles, _lib.ptr(self._best2),
+                                            _lib.ptr(self._red_ws), self._stream()), "pk_best_particle")
+            mine = self._best2.clone()
+            mine[1] += self.particle_offset
+            allb = torch.zeros((self.world_size, 2), dtype=torch.float64, device=self._device)
+            dist.all_gather_into_tensor(allb.view(-1), mine, group=self._group)
+            b = allb.cpu().numpy()
+        best = max(range(self.world_size), key=lambda g: (b[g, 0], -b[g, 1]))
+        return int(b[best, 1]), float(b[best, 0])
+
+    def stats(self):
+        """Counters summed over ranks (a small all-reduce)."""
+        s = super().stats()
+        t = self._torch.tensor([s[k] for k in ("matched", "unmatched", "evaluated", "same_landmark", "promoted",
+                                               "blocks_copied")], dtype=self._torch.int64, device=self._device)
+        self._dist.all_reduce(t, group=self._group)
+        out = dict(zip(("matched", "unmatched", "evaluated", "same_landmark", "promoted", "blocks_copied"),
+                       [int(v) for v in t.cpu()]))
+        out["flags"] = s["flags"]
+        out["migrated_in"] = int(self.last_plan["n_lo"] + self.last_plan["n_hi"]) if self.last_plan else 0
+        return out

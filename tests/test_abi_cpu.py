@@ -1,0 +1,59 @@
+"""The C-ABI shared library builds for sm_100a, loads, and exports every symbol that
+include/parakeet_b200.h declares.  No compute calls: runs without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "parakeet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_typed():
+    from parakeet_slam_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), "libparakeet_b200.so does not export %s" % name
+        assert name in _lib.SIGNATURES, "no ctypes signature for %s" % name
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_layout_queries_and_error_convention():
+    from parakeet_slam_b200 import _lib
+    lib = _lib.load()
+    assert lib.pk_version() == 1
+    assert lib.pk_hot_bytes(_lib.PK_DTYPE_F32) == 4
+    assert lib.pk_cold_bytes(_lib.PK_DTYPE_F32) == 64 and lib.pk_cold_bytes(_lib.PK_DTYPE_F64) == 160
+    assert lib.pk_block_bytes(64, _lib.PK_DTYPE_F32) == 64 * 68
+    assert lib.pk_block_bytes(20, _lib.PK_DTYPE_F64) == 80 + 20 * 160
+    assert lib.pk_block_bytes(3, _lib.PK_DTYPE_F32) == 16 + 3 * 64       # key region padded to 16 B
+    assert lib.pk_num_scan_blocks(1) == 1 and lib.pk_num_scan_blocks(1025) == 2
+    p = _lib.default_params()
+    assert (p.bearing_gate, p.color_gate, p.no_match_weight, p.qt_diag, p.promote_count) == (0.5, 300.0, 0.1, 0.1, 5)
+    # argument errors are reported by return code + message, never by crashing
+    rc = lib.pk_motion_update(None, 10, None, 0, 0, 0, 0.0, 0.0, 0.0, None)
+    assert rc == -1 and b"pose4" in lib.pk_last_error()
+    rc = lib.pk_measurement_update(None, None, None, None, 4, 0, 8, None, 200, ctypes.byref(p), None, None, None)
+    assert rc == -1
+
+
+def test_product_has_no_cpu_fallback_and_does_not_import_oracle():
+    import torch
+    from parakeet_slam_b200 import core, _lib
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.ParakeetLibraryError):
+            core.FastSLAM()
+    pkg = os.path.join(ROOT, "parakeet_slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
