@@ -185,7 +185,11 @@ class ShardedFastSLAM(FastSLAM):
                            "pk_copy_blocks(unpack)")
             self._cur = nxt
             if self.keep_trace:
-                self.last_ancestors = anc_win.clone()
+                # debugging / parity traces only: assemble the global ancestor list and keep my window
+                anc_global = torch.zeros((Mt,), dtype=torch.int64, device=dev)
+                anc_global[plan["emit_lo"]:plan["emit_lo"] + plan["emit_n"]] = emit
+                dist.all_reduce(anc_global, group=self._group)
+                self.last_ancestors = anc_global[win_lo:win_lo + Ml].clone()
             # keep the staging tensors alive until the stream has consumed them
             self._staging = (send_pose, send_aux, send_blocks, recv_pose, recv_aux, recv_blocks, off_local, anc_win)
 
