@@ -64,7 +64,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -325,6 +325,14 @@ def run_ours(args):
         bytes_particle = 32 + 8 + hot_b * N + rec_b * eval_per_particle + rec_b * m_matched + 8 + 4 * K
         achieved = bytes_particle * M_local / (ms_measure * 1e-3) / 1e9
         survey_bytes = 24 + (84 if args.dtype == "f32" else 164) * (N + m_matched) + 8 + 4 * K
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+                tr = json.load(fh)["measure_kernel<float>"]
+            if (args.dtype, M_local, N, K) == (tr["dtype"], tr["particles_per_gpu"], tr["landmarks"], tr["blobs"]):
+                traffic = tr["dram_bytes"]
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -347,7 +355,9 @@ def run_ours(args):
             "roofline": {
                 "bound": "hbm", "kernel": "measure_kernel<%s>" % ("float" if args.dtype == "f32" else "double"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_kind, "traffic": None,
+                "peak_source": peak_kind, "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_kernels_ncu.csv)",
+                "algorithmic_bytes_per_launch": bytes_particle * M_local,
                 "algorithmic_bytes_per_particle": bytes_particle,
                 "survey_aos_bytes_per_particle": survey_bytes,
                 "frac_vs_survey_aos_bytes": survey_bytes * M_local / (ms_measure * 1e-3) / 1e9 / peak,
@@ -370,7 +380,7 @@ def run_ours(args):
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="landmark storage type")
