@@ -172,21 +172,28 @@ int pk_resample_gather(const long long* ancestors, const int* offspring, long lo
                        const double* pose4_in, double* pose4_out, const int* aux2_in,
                        int* aux2_out, const int* slot_in, int* slot_out, void* pool, int capacity,
                        int dtype, void* workspace, long long* n_copied_out, void* stream);
-/* Sharded form (particles split in contiguous ranges over ranks, one process per GPU).  The
- * rank's Ml output slots are [n_lo incoming from lower ranks | n_loc offspring of local ancestors
- * | the rest incoming from higher ranks].  ancestors_win[Ml]: global ancestor index per output slot
- * (read only for the local part); offspring_local[Ml]: per local particle, its number of outputs
- * inside this rank's window.  recv_pose / recv_aux: the incoming particles in source-rank order.
- * Incoming particles and local duplicates take blocks freed by local particles without local
- * offspring; unpack_dst[n_in] receives the destination block of each incoming particle (feed it
- * to pk_copy_blocks with the receive buffer as source).  Call AFTER the outgoing particles were
- * packed.  total_dead_out (device int64): number of freed blocks. */
-int pk_resample_gather_sharded(const long long* ancestors_win, const int* offspring_local,
-                               long long Ml, long long particle_offset, long long n_lo,
-                               long long n_loc, const double* pose4_in, double* pose4_out,
-                               const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
-                               const double* recv_pose, const int* recv_aux, void* pool,
-                               int capacity, int dtype, void* workspace, int* unpack_dst,
+/* ---- sharded form (particles split in contiguous index ranges over ranks, one process per GPU).
+ * A migrating particle travels as one record of pk_particle_record_bytes(): a 64-byte header
+ * (pose4, aux2) followed by its landmark block. */
+long long pk_particle_record_bytes(int capacity, int dtype);
+/* Pack the n particles whose GLOBAL indices are emit_run[0..n) (all local to this rank) into
+ * out[n][record].  workspace: 3*n ints. */
+int pk_pack_particles(const long long* emit_run, long long n, long long particle_offset,
+                      const double* pose4, const int* aux2, const int* slot, const void* pool,
+                      int capacity, int dtype, void* out, int* workspace, void* stream);
+/* The rank's Ml output slots are [n_lo arrivals from lower ranks | n_loc offspring of local
+ * ancestors | the rest arrivals from higher ranks] (ancestors ascend globally).  local_run[n_loc]:
+ * global ancestor index of each local output; out_lo / offspring: as written by
+ * pk_resample_ancestors for the local particles; recv: the arrivals' records in source-rank order.
+ * Arrivals and local duplicates take blocks freed by local particles without local offspring.
+ * Call AFTER the outgoing particles were packed.  total_dead_out (device int64): freed blocks.
+ * workspace: pk_gather_workspace_bytes(Ml). */
+int pk_resample_gather_sharded(const long long* local_run, const long long* out_lo,
+                               const int* offspring, long long Ml, long long particle_offset,
+                               long long n_lo, long long n_loc, const double* pose4_in,
+                               double* pose4_out, const int* aux2_in, int* aux2_out,
+                               const int* slot_in, int* slot_out, const void* recv, void* pool,
+                               int capacity, int dtype, void* workspace,
                                long long* total_dead_out, void* stream);
 /* Raw block mover (also used by the sharded path to pack / unpack migrating particles): copies n
  * landmark blocks src_base[src_slot[i]] -> dst_base[dst_slot[i]] (n = min(*n_dev, n_max) when

@@ -118,8 +118,10 @@ SIGNATURES = {
     "pk_resample_ancestors": (_I, [_P, _LL, _LL, _LL, _P, _P, _P, _LL, _LL, _LL, _P, _P, _P, _P, _P]),
     "pk_gather_workspace_bytes": (_LL, [_LL]),
     "pk_resample_gather": (_I, [_P, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
-    "pk_resample_gather_sharded": (_I, [_P, _P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I,
-                                        _P, _P, _P, _P]),
+    "pk_particle_record_bytes": (_LL, [_I, _I]),
+    "pk_pack_particles": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "pk_resample_gather_sharded": (_I, [_P, _P, _P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I,
+                                        _P, _P, _P]),
     "pk_copy_blocks": (_I, [_P, _P, _I, _I, _P, _P, _P, _LL, _P, _P]),
     "pk_summary_partial": (_I, [_P, _LL, _P, _P, _P]),
     "pk_best_particle": (_I, [_P, _LL, _P, _P, _P]),

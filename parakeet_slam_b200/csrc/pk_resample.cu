@@ -313,45 +313,83 @@ assign_kernel(const long long* __restrict__ ancestors, long long M, const double
     }
 }
 
+// ---- sharded path -------------------------------------------------------------------------------
+// A migrating particle travels as one RECORD: a 64-byte header (pose4: 32 B, aux2: 8 B, padding) followed
+// by its landmark block.  kHeaderBytes keeps the block 64-byte aligned inside the exchange buffer.
+constexpr int kHeaderBytes = 64;
+
+__global__ void __launch_bounds__(256)
+pack_headers_kernel(const long long* __restrict__ emit_run, long long n, long long particle_offset,
+                    const double* __restrict__ pose4, const int* __restrict__ aux2, const int* __restrict__ slot,
+                    unsigned char* __restrict__ out, long long stride, int* __restrict__ src_slot,
+                    int* __restrict__ dst_idx, int* __restrict__ nlive) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long a = emit_run[i] - particle_offset;
+    const double2* src = reinterpret_cast<const double2*>(pose4 + 4 * a);
+    double2* dst = reinterpret_cast<double2*>(out + (size_t)i * stride);
+    dst[0] = src[0];
+    dst[1] = src[1];
+    const int2 ax = reinterpret_cast<const int2*>(aux2)[a];
+    *reinterpret_cast<int2*>(out + (size_t)i * stride + 32) = ax;
+    src_slot[i] = slot[a];
+    dst_idx[i] = (int)i;
+    nlive[i] = ax.x;
+}
+
+// number of outputs of each local particle that fall inside this rank's own output window
+__global__ void __launch_bounds__(256)
+offspring_window_kernel(const long long* __restrict__ out_lo, const int* __restrict__ offspring, long long Ml,
+                        long long win_lo, int* __restrict__ offspring_local) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ml) return;
+    const long long lo = max(out_lo[i], win_lo), hi = min(out_lo[i] + offspring[i], win_lo + Ml);
+    offspring_local[i] = (int)max(0ll, hi - lo);
+}
+
 // G4s: sharded form of G4.  The rank's Ml output slots are [incoming from lower ranks (n_lo) |
 // offspring of local ancestors (n_loc) | incoming from higher ranks (Ml - n_lo - n_loc)] because
 // ancestors are globally ascending.  Incoming particles and local duplicates both take blocks
 // freed by local particles with no local offspring.
 __global__ void __launch_bounds__(256)
-assign_sharded_kernel(const long long* __restrict__ ancestors, long long Ml, long long particle_offset, long long n_lo,
+assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, long long particle_offset, long long n_lo,
                       long long n_loc, const double* __restrict__ pose_in, double* __restrict__ pose_out,
                       const int* __restrict__ aux_in, int* __restrict__ aux_out, const int* __restrict__ slot_in,
-                      int* __restrict__ slot_out, const double* __restrict__ recv_pose, const int* __restrict__ recv_aux,
+                      int* __restrict__ slot_out, const unsigned char* __restrict__ recv, long long stride,
                       const int* __restrict__ dead_excl, const int* __restrict__ free_list,
                       const long long* __restrict__ total_dead, int* __restrict__ copy_src, int* __restrict__ copy_dst,
-                      int* __restrict__ copy_nlive, int* __restrict__ unpack_dst) {
+                      int* __restrict__ copy_nlive, int* __restrict__ unpack_src, int* __restrict__ unpack_dst,
+                      int* __restrict__ unpack_nlive) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Ml) return;
     const long long n_in = Ml - n_loc;
     const long long n_dups = *total_dead - n_in;  // local outputs that are not the first of their ancestor
     double2* dst = reinterpret_cast<double2*>(pose_out + 4 * k);
     if (k < n_lo || k >= n_lo + n_loc) {
-        const long long r = (k < n_lo) ? k : k - n_loc;  // index in the receive buffers (source-rank order)
+        const long long r = (k < n_lo) ? k : k - n_loc;  // index in the receive buffer (source-rank order)
         const long long nidx = (k < n_lo) ? k : n_lo + n_dups + (k - n_lo - n_loc);
-        const double2* src = reinterpret_cast<const double2*>(recv_pose + 4 * r);
+        const double2* src = reinterpret_cast<const double2*>(recv + (size_t)r * stride);
         dst[0] = src[0];
         dst[1] = src[1];
-        reinterpret_cast<int2*>(aux_out)[k] = reinterpret_cast<const int2*>(recv_aux)[r];
+        const int2 ax = *reinterpret_cast<const int2*>(recv + (size_t)r * stride + 32);
+        reinterpret_cast<int2*>(aux_out)[k] = ax;
         const int d = free_list[nidx];
         slot_out[k] = d;
+        unpack_src[r] = (int)r;
         unpack_dst[r] = d;
+        unpack_nlive[r] = ax.x;
         copy_src[nidx] = -1;  // not a pool-to-pool copy
         copy_dst[nidx] = d;
         copy_nlive[nidx] = 0;
         return;
     }
-    const long long a = ancestors[k] - particle_offset;  // local ancestor
+    const long long a = local_run[k - n_lo] - particle_offset;  // local ancestor
     const double2* src = reinterpret_cast<const double2*>(pose_in + 4 * a);
     dst[0] = src[0];
     dst[1] = src[1];
     const int2 ax = reinterpret_cast<const int2*>(aux_in)[a];
     reinterpret_cast<int2*>(aux_out)[k] = ax;
-    const bool first = (k == n_lo) || (ancestors[k - 1] != ancestors[k]);
+    const bool first = (k == n_lo) || (local_run[k - n_lo - 1] != local_run[k - n_lo]);
     if (first) {
         slot_out[k] = slot_in[a];
     } else {
@@ -375,8 +413,8 @@ constexpr int kCopyBufs = 4;
 constexpr int kCopyChunk = 4096;
 
 __global__ void __launch_bounds__(32)
-copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __restrict__ dst_base, long long block_b,
-                   int hot_b, int cold_b, int capacity, const int* __restrict__ src_slot, const int* __restrict__ dst_slot,
+copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __restrict__ dst_base, long long src_stride,
+                   long long dst_stride, int hot_b, int cold_b, int capacity, const int* __restrict__ src_slot, const int* __restrict__ dst_slot,
                    const int* __restrict__ nlive, long long n_max, const long long* __restrict__ n_dev) {
     __shared__ __align__(128) unsigned char buf[kCopyBufs][kCopyChunk];
     __shared__ uint64_t bar[kCopyBufs];
@@ -422,7 +460,7 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
             if (issued >= kCopyBufs) tma_store_wait_read0();  // the store that last read this buffer
             const long long len = seg_len(ci.item, ci.seg);
             const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - ci.off);
-            const unsigned char* s = src_base + (size_t)src_slot[ci.item] * block_b + seg_base(ci.seg) + ci.off;
+            const unsigned char* s = src_base + (size_t)src_slot[ci.item] * src_stride + seg_base(ci.seg) + ci.off;
             mbar_arrive_expect_tx(&bar[b], bytes);
             tma_load_1d(buf[b], s, bytes, &bar[b]);
             ++issued;
@@ -432,7 +470,7 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
         mbar_wait(&bar[b], (unsigned)((drained / kCopyBufs) & 1));
         const long long len = seg_len(cd.item, cd.seg);
         const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - cd.off);
-        unsigned char* d = dst_base + (size_t)dst_slot[cd.item] * block_b + seg_base(cd.seg) + cd.off;
+        unsigned char* d = dst_base + (size_t)dst_slot[cd.item] * dst_stride + seg_base(cd.seg) + cd.off;
         tma_store_1d(d, buf[b], bytes);
         tma_store_commit();
         ++drained;
@@ -548,6 +586,7 @@ static long long num_blocks(long long M) { return (M + PK_SCAN_BLOCK - 1) / PK_S
 
 struct GatherWs {
     int *dead_excl, *block_dead, *block_off, *free_list, *copy_src, *copy_dst, *copy_nlive;
+    int *offspring_local, *unpack_src, *unpack_dst, *unpack_nlive;
     size_t bytes;
 };
 static GatherWs carve(void* ws, long long M) {
@@ -568,6 +607,10 @@ static GatherWs carve(void* ws, long long M) {
     g.copy_src = take((size_t)M);
     g.copy_dst = take((size_t)M);
     g.copy_nlive = take((size_t)M);
+    g.offspring_local = take((size_t)M);
+    g.unpack_src = take((size_t)M);
+    g.unpack_dst = take((size_t)M);
+    g.unpack_nlive = take((size_t)M);
     g.bytes = off;
     return g;
 }
@@ -628,12 +671,14 @@ long long pk_gather_workspace_bytes(long long M) {
 
 static int copy_blocks_launch(const void* src, void* dst, int capacity, int dtype, const int* src_slot,
                               const int* dst_slot, const int* nlive, long long n_max, const long long* n_dev,
-                              cudaStream_t st) {
+                              cudaStream_t st, long long src_stride = 0, long long dst_stride = 0) {
+    if (src_stride == 0) src_stride = (long long)block_bytes(capacity, dtype);
+    if (dst_stride == 0) dst_stride = (long long)block_bytes(capacity, dtype);
     long long grid = (long long)num_sms() * 12;
     if (grid > n_max) grid = n_max;
     if (grid < 1) return PK_OK;
-    copy_blocks_kernel<<<(unsigned)grid, 32, 0, st>>>((const unsigned char*)src, (unsigned char*)dst,
-                                                     (long long)block_bytes(capacity, dtype), (int)hot_bytes(dtype),
+    copy_blocks_kernel<<<(unsigned)grid, 32, 0, st>>>((const unsigned char*)src, (unsigned char*)dst, src_stride,
+                                                     dst_stride, (int)hot_bytes(dtype),
                                                      (int)cold_bytes(dtype), capacity, src_slot, dst_slot, nlive, n_max,
                                                      n_dev);
     PK_LAUNCH_CHECK("copy_blocks_kernel");
@@ -669,38 +714,74 @@ int pk_resample_gather(const long long* ancestors, const int* offspring, long lo
     return PK_OK;
 }
 
-int pk_resample_gather_sharded(const long long* ancestors_win, const int* offspring_local, long long Ml,
+long long pk_particle_record_bytes(int capacity, int dtype) {
+    return (long long)kHeaderBytes + (long long)block_bytes(capacity, dtype);
+}
+
+int pk_pack_particles(const long long* emit_run, long long n, long long particle_offset, const double* pose4,
+                      const int* aux2, const int* slot, const void* pool, int capacity, int dtype, void* out,
+                      int* workspace, void* stream) {
+    PK_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return PK_OK;
+    PK_CHECK_ARG(emit_run && pose4 && aux2 && slot && pool && out && workspace, "null pointer");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long stride = pk_particle_record_bytes(capacity, dtype);
+    int* src_slot = workspace;
+    int* dst_idx = workspace + n;
+    int* nlive = workspace + 2 * n;
+    pack_headers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emit_run, n, particle_offset, pose4, aux2, slot,
+                                                                    (unsigned char*)out, stride, src_slot, dst_idx, nlive);
+    PK_LAUNCH_CHECK("pack_headers_kernel");
+    if (capacity > 0)
+        return copy_blocks_launch(pool, (unsigned char*)out + kHeaderBytes, capacity, dtype, src_slot, dst_idx, nlive, n,
+                                  nullptr, st, 0, stride);
+    return PK_OK;
+}
+
+int pk_resample_gather_sharded(const long long* local_run, const long long* out_lo, const int* offspring, long long Ml,
                                long long particle_offset, long long n_lo, long long n_loc, const double* pose4_in,
                                double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
-                               const double* recv_pose, const int* recv_aux, void* pool, int capacity, int dtype,
-                               void* workspace, int* unpack_dst, long long* total_dead_out, void* stream) {
-    PK_CHECK_ARG(ancestors_win && offspring_local && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out &&
-                     pool && workspace && unpack_dst && total_dead_out,
+                               const void* recv, void* pool, int capacity, int dtype, void* workspace,
+                               long long* total_dead_out, void* stream) {
+    PK_CHECK_ARG(out_lo && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out && pool &&
+                     workspace && total_dead_out,
                  "null pointer");
     PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31), "Ml");
     PK_CHECK_ARG(n_lo >= 0 && n_loc >= 0 && n_lo + n_loc <= Ml, "window split");
-    PK_CHECK_ARG(n_loc == Ml || (recv_pose && recv_aux), "receive buffers are NULL");
+    PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
+    PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
     PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
     cudaStream_t st = (cudaStream_t)stream;
     GatherWs g = carve(workspace, Ml);
     const long long nb = num_blocks(Ml);
-    dead_scan_kernel<<<(unsigned)((nb + kScanWarps - 1) / kScanWarps), kScanWarps * 32, 0, st>>>(offspring_local, Ml,
+    const long long stride = pk_particle_record_bytes(capacity, dtype);
+    const int threads = 256;
+    const unsigned grid = (unsigned)((Ml + threads - 1) / threads);
+    offspring_window_kernel<<<grid, threads, 0, st>>>(out_lo, offspring, Ml, particle_offset, g.offspring_local);
+    PK_LAUNCH_CHECK("offspring_window_kernel");
+    dead_scan_kernel<<<(unsigned)((nb + kScanWarps - 1) / kScanWarps), kScanWarps * 32, 0, st>>>(g.offspring_local, Ml,
                                                                                                  g.dead_excl, g.block_dead, nb);
     PK_LAUNCH_CHECK("dead_scan_kernel");
     block_offsets_kernel<<<1, 1024, 0, st>>>(g.block_dead, nb, g.block_off, total_dead_out);
     PK_LAUNCH_CHECK("block_offsets_kernel");
-    const int threads = 256;
-    const unsigned grid = (unsigned)((Ml + threads - 1) / threads);
-    free_list_kernel<<<grid, threads, 0, st>>>(offspring_local, slot_in, Ml, g.dead_excl, g.block_off, g.free_list);
+    free_list_kernel<<<grid, threads, 0, st>>>(g.offspring_local, slot_in, Ml, g.dead_excl, g.block_off, g.free_list);
     PK_LAUNCH_CHECK("free_list_kernel");
-    assign_sharded_kernel<<<grid, threads, 0, st>>>(ancestors_win, Ml, particle_offset, n_lo, n_loc, pose4_in, pose4_out,
-                                                    aux2_in, aux2_out, slot_in, slot_out, recv_pose, recv_aux, g.dead_excl,
-                                                    g.free_list, total_dead_out, g.copy_src, g.copy_dst, g.copy_nlive,
-                                                    unpack_dst);
+    assign_sharded_kernel<<<grid, threads, 0, st>>>(local_run, Ml, particle_offset, n_lo, n_loc, pose4_in, pose4_out,
+                                                    aux2_in, aux2_out, slot_in, slot_out, (const unsigned char*)recv, stride,
+                                                    g.dead_excl, g.free_list, total_dead_out, g.copy_src, g.copy_dst,
+                                                    g.copy_nlive, g.unpack_src, g.unpack_dst, g.unpack_nlive);
     PK_LAUNCH_CHECK("assign_sharded_kernel");
-    // local duplicates: pool -> pool (entries that belong to incoming particles carry src = -1 and are skipped)
-    if (capacity > 0)
-        return copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, Ml, total_dead_out, st);
+    if (capacity > 0) {
+        // local duplicates: pool -> pool (entries that belong to incoming particles carry src = -1 and are skipped)
+        int rc = copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, Ml, total_dead_out, st);
+        if (rc != PK_OK) return rc;
+        // arrivals: exchange buffer -> pool
+        const long long n_in = Ml - n_loc;
+        if (n_in > 0)
+            return copy_blocks_launch((const unsigned char*)recv + kHeaderBytes, pool, capacity, dtype, g.unpack_src,
+                                      g.unpack_dst, g.unpack_nlive, n_in, nullptr, st, stride, 0);
+    }
     return PK_OK;
 }
 

@@ -84,7 +84,9 @@ class ShardedFastSLAM(FastSLAM):
         self._all_prefix = torch.zeros((G * nb, 2), dtype=torch.float64, device=dev)
         self._all_count = torch.zeros((G * nb + 1,), dtype=torch.int64, device=dev)
         self._emit = torch.zeros((max(2 * self.num_particles, 1),), dtype=torch.int64, device=dev)
-        self._unpack_dst = torch.zeros((self.num_particles,), dtype=torch.int32, device=dev)
+        self._record_bytes = int(self._lib.pk_particle_record_bytes(self.capacity, self._dt))
+        self._exchange_cap = 0
+        self._send_buf = self._recv_buf = self._pack_ws = None
         self._rank_idx = torch.arange(0, G * nb + 1, nb, device=dev)
         self.last_plan = None
 
@@ -127,71 +129,56 @@ class ShardedFastSLAM(FastSLAM):
                                                  _lib.ptr(self._all_count), Mt, plan["emit_lo"], max(plan["emit_n"], 1),
                                                  _lib.ptr(self._out_lo), _lib.ptr(self._offspring), _lib.ptr(self._emit),
                                                  _lib.ptr(self._big_runs), st), "pk_resample_ancestors")
-            emit = self._emit[:plan["emit_n"]]
+            emit = self._emit
             # ---- pack what leaves this rank (before any block is overwritten) -------------------
             send_counts = list(plan["send"])
             send_counts[me] = 0
             recv_counts = list(plan["recv"])
             recv_counts[me] = 0
             n_send, n_in = sum(send_counts), sum(recv_counts)
-            parts = [emit[plan["send_start"][h]:plan["send_start"][h] + send_counts[h]] for h in range(G)
-                     if send_counts[h]]
-            bb = self.block_bytes
-            if n_send:
-                src_local = (torch.cat(parts) - self.particle_offset)
-                send_pose = pose_in.index_select(0, src_local)
-                send_aux = aux_in.index_select(0, src_local)
-                send_blocks = torch.empty((n_send, max(bb, 1)), dtype=torch.uint8, device=dev)
-                if bb:
-                    src_slots = slot_in.index_select(0, src_local).contiguous()
-                    dst_idx = torch.arange(n_send, dtype=torch.int32, device=dev)
-                    _lib.check(lib.pk_copy_blocks(_lib.ptr(self._pool), _lib.ptr(send_blocks), self.capacity, self._dt,
-                                                  _lib.ptr(src_slots), _lib.ptr(dst_idx),
-                                                  _lib.ptr(send_aux[:, 0].contiguous()), n_send, None, st),
-                               "pk_copy_blocks(pack)")
-            else:
-                send_pose = torch.empty((0, 4), dtype=torch.float64, device=dev)
-                send_aux = torch.empty((0, 2), dtype=torch.int32, device=dev)
-                send_blocks = torch.empty((0, max(bb, 1)), dtype=torch.uint8, device=dev)
-            recv_pose = torch.empty((max(n_in, 1), 4), dtype=torch.float64, device=dev)
-            recv_aux = torch.empty((max(n_in, 1), 2), dtype=torch.int32, device=dev)
-            recv_blocks = torch.empty((max(n_in, 1), max(bb, 1)), dtype=torch.uint8, device=dev)
+            rec = self._record_bytes
+            self._ensure_exchange_buffers(n_send, n_in)
+            # runs for ranks below / above me are contiguous in the emit list, on either side of the local run
+            off = 0
+            for h in range(G):
+                if send_counts[h]:
+                    run = emit[plan["send_start"][h]:]
+                    _lib.check(lib.pk_pack_particles(_lib.ptr(run), send_counts[h], self.particle_offset,
+                                                     _lib.ptr(pose_in), _lib.ptr(aux_in), _lib.ptr(slot_in),
+                                                     _lib.ptr(self._pool), self.capacity, self._dt,
+                                                     self._send_buf.data_ptr() + off * rec, _lib.ptr(self._pack_ws), st),
+                               "pk_pack_particles")
+                    off += send_counts[h]
             if G > 1:
-                # cross-shard resampled particles: payloads move rank to rank over NVLink
-                dist.all_to_all_single(recv_pose[:n_in], send_pose, recv_counts, send_counts, group=self._group)
-                dist.all_to_all_single(recv_aux[:n_in], send_aux, recv_counts, send_counts, group=self._group)
-                if bb:
-                    dist.all_to_all_single(recv_blocks[:n_in], send_blocks, recv_counts, send_counts, group=self._group)
+                # cross-shard resampled particles: one record per particle, rank to rank over NVLink
+                dist.all_to_all_single(self._recv_buf[:n_in], self._send_buf[:n_send], recv_counts, send_counts,
+                                       group=self._group)
             # ---- local assignment: survivors keep their block, duplicates and arrivals take freed ones
-            win_lo = me * Ml
-            off_local = torch.clamp(torch.clamp(self._out_lo[:Ml] + self._offspring[:Ml], max=win_lo + Ml)
-                                    - torch.clamp(self._out_lo[:Ml], min=win_lo), min=0).to(torch.int32)
-            anc_win = torch.zeros((Ml,), dtype=torch.int64, device=dev)
             n_lo, n_loc = plan["n_lo"], plan["n_loc"]
-            if n_loc:
-                s0 = plan["send_start"][me]
-                anc_win[n_lo:n_lo + n_loc] = emit[s0:s0 + n_loc]
+            local_run = emit[plan["send_start"][me]:] if n_loc else None
             _lib.check(lib.pk_resample_gather_sharded(
-                _lib.ptr(anc_win), _lib.ptr(off_local), Ml, self.particle_offset, n_lo, n_loc,
-                _lib.ptr(pose_in), _lib.ptr(self._pose[nxt]), _lib.ptr(aux_in), _lib.ptr(self._aux[nxt]),
-                _lib.ptr(slot_in), _lib.ptr(self._slot[nxt]), _lib.ptr(recv_pose), _lib.ptr(recv_aux),
-                _lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self._gather_ws), _lib.ptr(self._unpack_dst),
-                _lib.ptr(self._n_copied), st), "pk_resample_gather_sharded")
-            if n_in and bb:
-                src_idx = torch.arange(n_in, dtype=torch.int32, device=dev)
-                _lib.check(lib.pk_copy_blocks(_lib.ptr(recv_blocks), _lib.ptr(self._pool), self.capacity, self._dt,
-                                              _lib.ptr(src_idx), _lib.ptr(self._unpack_dst),
-                                              _lib.ptr(recv_aux[:n_in, 0].contiguous()), n_in, None, st),
-                           "pk_copy_blocks(unpack)")
+                _lib.ptr(local_run), _lib.ptr(self._out_lo), _lib.ptr(self._offspring), Ml, self.particle_offset,
+                n_lo, n_loc, _lib.ptr(pose_in), _lib.ptr(self._pose[nxt]), _lib.ptr(aux_in), _lib.ptr(self._aux[nxt]),
+                _lib.ptr(slot_in), _lib.ptr(self._slot[nxt]), _lib.ptr(self._recv_buf), _lib.ptr(self._pool),
+                self.capacity, self._dt, _lib.ptr(self._gather_ws), _lib.ptr(self._n_copied), st),
+                "pk_resample_gather_sharded")
             self._cur = nxt
             if self.keep_trace:
                 # debugging / parity traces only: assemble the global ancestor list and keep my window
                 anc_global = torch.zeros((Mt,), dtype=torch.int64, device=dev)
-                anc_global[plan["emit_lo"]:plan["emit_lo"] + plan["emit_n"]] = emit
+                anc_global[plan["emit_lo"]:plan["emit_lo"] + plan["emit_n"]] = emit[:plan["emit_n"]]
                 dist.all_reduce(anc_global, group=self._group)
-                self.last_ancestors = anc_global[win_lo:win_lo + Ml].clone()
-            # keep the staging tensors alive until the stream has consumed them
-            self._staging = (send_pose, send_aux, send_blocks, recv_pose, recv_aux, recv_blocks, off_local, anc_win)
+                self.last_ancestors = anc_global[me * Ml:(me + 1) * Ml].clone()
+
+    def _ensure_exchange_buffers(self, n_send, n_in):
+        torch = self._torch
+        need = max(n_send, n_in, 1)
+        if need > self._exchange_cap:
+            cap = max(need, 2 * self._exchange_cap, 256)
+            self._exchange_cap = cap
+            self._send_buf = torch.empty((cap, self._record_bytes), dtype=torch.uint8, device=self._device)
+            self._recv_buf = torch.empty((cap, self._record_bytes), dtype=torch.uint8, device=self._device)
+            self._pack_ws = torch.empty((3 * cap,), dtype=torch.int32, device=self._device)
 
     def summary(self):
         torch, lib, dist = self._torch, self._lib, self._dist
