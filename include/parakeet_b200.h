@@ -131,7 +131,7 @@ int pk_motion_update(double* pose4, long long M, const double* noise3, unsigned 
  *      (:835-857), potential-feature promotion (:109-118), orphan counting (:740-746) ---------- */
 /* obs_host: K rows of (bearing, r, g, b), HOST memory, read before the call returns.
  * Writes weight (pose4[i][3]), assoc[M][K] (reference ids: >0 full, <0 potential, 0 unseen),
- * updates the pool and aux2, accumulates stats[PK_NUM_STATS] (caller zeroes them). */
+ * updates the pool and aux2, and fills stats[PK_NUM_STATS] (zeroed by the call itself). */
 int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool, int capacity,
                           int dtype, long long M, const double* obs_host, int K,
                           const pk_params* params, int* assoc, unsigned long long* stats,

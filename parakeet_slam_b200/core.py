@@ -30,6 +30,17 @@ from ._ros import Odometry, Quaternion, Twist, now as _ros_now
 __all__ = ["FastSLAM", "FilterParticle", "Feature", "ParticleList", "Matrix"]
 
 
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
 def Matrix(array_like):
     """``matrix.Matrix`` of the reference (``matrix.py:6-9``): a NumPy array."""
     return np.array(array_like)
@@ -324,6 +335,13 @@ class FastSLAM(object):
     def _stream(self):
         return ctypes.c_void_p(self._torch.cuda.current_stream(self._device).cuda_stream)
 
+    def _on_device(self):
+        """Context that makes the filter's device current (free when it already is)."""
+        torch = self._torch
+        if torch.cuda.current_device() == self._device.index:
+            return _NULL_CTX
+        return torch.cuda.device(self._device)
+
     @property
     def pose(self):
         """Device tensor [M,4]: x, y, heading, weight (current buffer)."""
@@ -340,7 +358,7 @@ class FastSLAM(object):
     def _load_presets(self, features):
         torch, lib, M = self._torch, self._lib, self.num_particles
         n, mean5, covp, covc, meta, ids = _feature_arrays(features, max(self.capacity, 1))
-        with torch.cuda.device(self._device):
+        with self._on_device():
             _lib.check(lib.pk_init_particles(_lib.ptr(self.pose), _lib.ptr(self.slot), _lib.ptr(self.aux), M, n,
                                              1 + n, self._stream()), "pk_init_particles")
             if n and M:
@@ -388,10 +406,9 @@ class FastSLAM(object):
         K = obs.shape[0]
         if K > _lib.PK_MAX_OBS:
             raise ValueError("at most %d blobs per frame (got %d)" % (_lib.PK_MAX_OBS, K))
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             if self._assoc is None or self._assoc.shape[1] != K:
                 self._assoc = torch.zeros((M, max(K, 1)), dtype=torch.int32, device=self._device)
-            self._stats.zero_()
             _lib.check(lib.pk_measurement_update(
                 _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
                 self.capacity, self._dt, M, obs.ctypes.data, K, ctypes.byref(self.params),
@@ -431,7 +448,7 @@ class FastSLAM(object):
             return
         v = float(twist.linear.x)                                     # :176
         w = float(twist.angular.z)                                    # :177
-        with torch.cuda.device(self._device):
+        with self._on_device():
             z = self._draw_noise(M)
             nptr = 0
             if z is not None:
@@ -458,7 +475,7 @@ class FastSLAM(object):
         new_particle = copy.deepcopy(particle)                        # :181
         pos = particle.state.pose.pose.position
         heading = particle.heading if isinstance(particle, FilterParticle) else FilterParticle.heading.fget(particle)
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             rec = torch.tensor([[float(pos.x), float(pos.y), float(heading), 1.0]], dtype=torch.float64,
                                device=self._device)
             z = self._draw_noise(1)
@@ -478,7 +495,7 @@ class FastSLAM(object):
         torch, lib, M = self._torch, self._lib, self.num_particles
         if M == 0:
             return
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             u01 = float(self._uniform())
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
@@ -507,7 +524,7 @@ class FastSLAM(object):
     def summary(self):
         """``:254-276``: unweighted mean x, mean y and circular-mean heading."""
         torch, lib, M = self._torch, self._lib, self.num_particles
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             _lib.check(lib.pk_summary_partial(_lib.ptr(self.pose), M, _lib.ptr(self._out5), _lib.ptr(self._red_ws),
                                               self._stream()), "pk_summary_partial")
             s = self._out5.cpu().numpy()
@@ -518,7 +535,7 @@ class FastSLAM(object):
         """Additive API: (index, weight) of the first particle with the largest weight (weights
         are those of the last measurement update; after resampling they are the ancestors')."""
         torch, lib, M = self._torch, self._lib, self.num_particles
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             _lib.check(lib.pk_best_particle(_lib.ptr(self.pose), M, _lib.ptr(self._best2), _lib.ptr(self._red_ws),
                                             self._stream()), "pk_best_particle")
             b = self._best2.cpu().numpy()
@@ -540,7 +557,7 @@ class FastSLAM(object):
         count = self.num_particles - lo if count is None else count
         N = max(self.capacity, 1)
         dev = self._device
-        with self._lock, torch.cuda.device(dev):
+        with self._lock, self._on_device():
             mean5 = torch.zeros((count, N, 5), dtype=torch.float64, device=dev)
             covp = torch.zeros((count, N, 4), dtype=torch.float64, device=dev)
             covc = torch.zeros((count, N, 9), dtype=torch.float64, device=dev)

@@ -9,6 +9,41 @@
 namespace pk {
 
 // ---------------------------------------------------------------------------------------------
+// Branch-free exp (fp64, <= 2 ulp, exact underflow behaviour).  Most arguments here are hundreds
+// below zero (finding F3: the match / no-match decision IS the fp64 underflow of the likelihood), which
+// is libm's slow path, and lanes diverge between fast and slow path.  n = rint(x/ln2), r = x - n ln2
+// (two-constant Cody-Waite), degree-13 Taylor polynomial of e^r by Estrin's scheme, and the scaling by
+// 2^n split in two exact powers so that the last multiply performs the single, correctly rounded
+// step into the subnormal range (or to 0 / inf).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pk_exp(double x) {
+    const double xc = fmin(fmax(x, -1100.0), 1100.0);
+    const double shift = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer
+    const double t = fma(xc, 1.4426950408889634074, shift);
+    const int n = __double2loint(t);
+    const double fn = t - shift;
+    double r = fma(fn, -6.93147180369123816490e-01, xc);
+    r = fma(fn, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = 1.0 + r;
+    const double a1 = fma(r, 1.0 / 6.0, 0.5);
+    const double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+    const double a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+    const double a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+    const double a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    const double lo = fma(r2, a1, a0);                       // 1 + r + r^2 (1/2 + r/6)
+    const double mid = fma(r2, a3, a2);                      // r^4 ( ... )
+    const double hi = fma(r4, a6, fma(r2, a5, a4));          // r^8 ( ... )
+    const double p = fma(r8, hi, fma(r4, mid, lo));
+    const int n1 = n >> 1, n2 = n - n1;
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
+    const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
+    const double y = (p * s1) * s2;
+    return (x != x) ? x : y;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Branch-free atan2 (fp64, <= 1.5 ulp).  libm's atan2 costs ~250 warp-instructions here because
 // its quadrant / magnitude cases diverge across the lanes of a warp.  One division: with
 // mn = min(|x|,|y|), mx = max(|x|,|y|), either t = mn/mx (t <= tan(pi/8)) or
@@ -70,14 +105,14 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
     double a = L.sp[0], b10 = L.sp[2], d = L.sp[3];
     double det2 = a * d - b10 * b10;
     double maha2 = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det2;
-    double bp = exp(-0.5 * (2.0 * kLog2Pi + log(det2) + maha2));
+    double bp = pk_exp(-0.5 * (2.0 * kLog2Pi + log(det2) + maha2));
     // 3-D colour pdf :530-544, lower triangle
     double A = L.sc[0], B = L.sc[3], C = L.sc[6], D = L.sc[4], E = L.sc[7], F = L.sc[8];
     double c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
     double c11 = A * F - C * C, c12 = B * C - A * E, c22 = A * D - B * B;
     double det3 = A * c00 + B * c01 + C * c02;
     double maha3 = (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0 * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
-    double cp = exp(-0.5 * (3.0 * kLog2Pi + log(det3) + maha3));
+    double cp = pk_exp(-0.5 * (3.0 * kLog2Pi + log(det3) + maha3));
     if (!(det2 > 0.0) || !(det3 > 0.0)) flags |= PK_FLAG_SINGULAR_COV;
     // :439, :446, :455
     return (500.0 * bp) * (500.0 * cp) / 250000.0;
@@ -126,7 +161,7 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     double y2 = d1 * I01 + d2 * I11 + d3 * I21;
     double y3 = d1 * I02 + d2 * I12 + d3 * I22;
     double maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
-    double factor = (1.0 / sqrt(2.0 * 3.141592653589793 * fro)) * exp(-0.5 * maha);
+    double factor = (1.0 / sqrt(2.0 * 3.141592653589793 * fro)) * pk_exp(-0.5 * maha);
 
     bool changed = false;
     if (!(L.meta & PK_META_IMMUTABLE)) {

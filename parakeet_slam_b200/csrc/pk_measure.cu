@@ -89,6 +89,12 @@ struct alignas(128) WarpSmem {
     uint64_t key_bar[kStages];
 };
 
+// how many candidates per item get a shared-memory staging slot: two for the 64-byte f32 record, one for f64
+template <typename T>
+__host__ __device__ constexpr int staged_candidates() {
+    return sizeof(typename Rec<T>::Cold) <= 64 ? 2 : 1;
+}
+
 // per-item screen result, kept in registers between screen(g) and evaluate(g)
 struct Hits {
     int cnt, c0, c1;
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, PK_MEASURE_MINB)
 measure_kernel(const __grid_constant__ MeasureArgs A) {
     using Cold = typename Rec<T>::Cold;
     constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
+    constexpr int kStaged = staged_candidates<T>();  // candidates per item prefetched into shared memory
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + (size_t)warp * A.warp_smem;
@@ -128,6 +135,19 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         it_pl[r] = w / K;
         it_k[r] = w - it_pl[r] * K;
         it_key[r] = (it_pl[r] < GP) ? A.okey[it_k[r]] : 0u;
+    }
+
+    // the blob of this lane's item(s) never changes: keep its values in registers
+    double ob_beta[R], ob_r[R], ob_g[R], ob_b[R], ob_dx[R], ob_dy[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int k = (it_pl[r] < GP) ? it_k[r] : 0;
+        ob_beta[r] = A.beta[k];
+        ob_r[r] = A.cr[k];
+        ob_g[r] = A.cg[k];
+        ob_b[r] = A.cb[k];
+        ob_dx[r] = A.dirx[k];
+        ob_dy[r] = A.diry[k];
     }
 
     if (lane == 0) {
@@ -254,12 +274,16 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         // per-lane addresses -> cp.async (LDGSTS), one commit group per screened group
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (H[r].cnt > 0) {
-                const unsigned char* src =
-                    cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap, H[r].c0);
-                const uint32_t dst = s_rec + ((unsigned)par * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
 #pragma unroll
-                for (unsigned q = 0; q < kRecBytes / 16u; ++q) cp_async16_a(dst + 16u * q, src + 16u * q);
+            for (int c = 0; c < kStaged; ++c) {
+                if (H[r].cnt > c) {
+                    const unsigned char* src = cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap,
+                                                           c == 0 ? H[r].c0 : H[r].c1);
+                    const uint32_t dst =
+                        s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
+#pragma unroll
+                    for (unsigned q = 0; q < kRecBytes / 16u; ++q) cp_async16_a(dst + 16u * q, src + 16u * q);
+                }
             }
         }
         cp_async_commit();
@@ -292,10 +316,10 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             bestj = -1;
             lastj = -1;
             if (cnt > 0) {
-                load_staged<T>(s_rec + ((unsigned)par * 32u * R + (unsigned)w) * kRecBytes, L);
+                load_staged<T>(s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)w) * kRecBytes, L);
                 lastj = H[r].c0;
-                const double Lk = match_likelihood(L, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
-                                                   A.diry[k], A.prm, st_flags, pse);
+                const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r],
+                                                   ob_dy[r], A.prm, st_flags, pse);
                 st_eval += 1;
                 if (Lk > 0.0) {
                     best = Lk;
@@ -304,11 +328,12 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 }
             }
             if (__any_sync(kFull, cnt > 1)) {
-                if (cnt == 2) {  // a second colour-compatible landmark: fetched directly
-                    load_landmark<T>(block, cap, H[r].c1, L);
+                if (cnt == 2) {  // a second colour-compatible landmark
+                    if (kStaged > 1) load_staged<T>(s_rec + (((unsigned)par * kStaged + 1u) * 32u * R + (unsigned)w) * kRecBytes, L);
+                    else load_landmark<T>(block, cap, H[r].c1, L);
                     lastj = H[r].c1;
-                    const double Lk = match_likelihood(L, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.dirx[k],
-                                                       A.diry[k], A.prm, st_flags, pse);
+                    const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r],
+                                                       ob_dy[r], A.prm, st_flags, pse);
                     st_eval += 1;
                     if (Lk > best) {
                         best = Lk;
@@ -323,8 +348,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     for (int j = 0; j < nlive; ++j) {
                         Landmark Lj;
                         load_landmark<T>(block, cap, j, Lj);
-                        const double Lk = match_likelihood(Lj, px, py, pth, A.beta[k], A.cr[k], A.cg[k], A.cb[k],
-                                                           A.dirx[k], A.diry[k], A.prm, st_flags, pse);
+                        const double Lk = match_likelihood(Lj, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                           ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
                         st_eval += 1;
                         if (Lk > best) {
                             best = Lk;
@@ -368,7 +393,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     if (q > 0 || lastj != bestj) load_landmark<T>(block, cap, bestj, L);
                     int promoted = 0;
                     bool changed = false;
-                    factor = ekf_update_lm(L, px, py, A.beta[k], A.cr[k], A.cg[k], A.cb[k], A.prm, id_out, st_flags,
+                    factor = ekf_update_lm(L, px, py, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], A.prm, id_out, st_flags,
                                            promoted, changed, true, best_pse);
                     if (changed) store_landmark<T>(block, cap, bestj, L);
                     st_promoted += promoted;
@@ -441,7 +466,7 @@ static int launch_measure(MeasureArgs& args, cudaStream_t st) {
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     args.keys_off = (int)align128(sizeof(WarpSmem));
     args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
-    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * 32 * R * sizeof(typename Rec<T>::Cold));
+    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * staged_candidates<T>() * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
     if ((int)smem > configured_smem) {
         PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -488,6 +513,7 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
         return PK_OK;
     }
     PK_CHECK_ARG(obs_host != nullptr && assoc != nullptr, "obs_host / assoc is NULL");
+    if (stats != nullptr) PK_CUDA(cudaMemsetAsync(stats, 0, PK_NUM_STATS * sizeof(unsigned long long), st));
 
     static thread_local MeasureArgs args;
     args.pose4 = pose4;

@@ -115,28 +115,43 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
         g_lo[t] = acc.lo;
     }
     __syncthreads();
-    // phase B: one thread folds the group totals in order
-    if (t == 0) {
+    // phase B: exclusive double-double scan of the group totals.  One warp; each lane folds a
+    // contiguous run of groups left to right, lane bases by a left fold over the lane totals (a fixed
+    // tree: every rank runs this kernel on the same array, so the result does not depend on the
+    // number of shards).
+    if (t < 32) {
+        const int per = (int)((ngroups + 31) / 32);
+        const long long q0 = (long long)t * per, q1 = min(ngroups, q0 + per);
         dd run{0.0, 0.0};
-        for (long long g = 0; g < ngroups; ++g) {
-            const dd cur{g_hi[g], g_lo[g]};
-            g_hi[g] = run.hi;
-            g_lo[g] = run.lo;
-            run = dd_add(run, cur);
+        for (long long g = q0; g < q1; ++g) run = dd_add(run, dd{g_hi[g], g_lo[g]});
+        dd base{0.0, 0.0};
+        for (int l = 0; l < 32; ++l) {
+            const double h = __shfl_sync(0xffffffffu, run.hi, l), lo2 = __shfl_sync(0xffffffffu, run.lo, l);
+            if (l < t) base = dd_add(base, dd{h, lo2});
+            if (l == 31 && t == 31) run = dd_add(base, run);  // grand total, held by lane 31
         }
-        const double total = run.hi + run.lo;
-        const double r = total / (double)M_total;  // range_ = sum_/float(len(particles)) :225
-        const double u0 = u01 * r;                 // step = random()*range_             :226
-        s_r = r;
-        s_u0 = u0;
-        plan[0] = total;
-        plan[1] = r;
-        plan[2] = u0;
-        plan[3] = run.hi;
-        plan[4] = run.lo;
-        plan[5] = (double)M_total;
-        plan[6] = u01;
-        plan[7] = 0.0;
+        dd acc2 = base;
+        for (long long g = q0; g < q1; ++g) {
+            const dd cur{g_hi[g], g_lo[g]};
+            g_hi[g] = acc2.hi;
+            g_lo[g] = acc2.lo;
+            acc2 = dd_add(acc2, cur);
+        }
+        if (t == 31) {
+            const double total = run.hi + run.lo;
+            const double r = total / (double)M_total;  // range_ = sum_/float(len(particles)) :225
+            const double u0 = u01 * r;                 // step = random()*range_             :226
+            s_r = r;
+            s_u0 = u0;
+            plan[0] = total;
+            plan[1] = r;
+            plan[2] = u0;
+            plan[3] = run.hi;
+            plan[4] = run.lo;
+            plan[5] = (double)M_total;
+            plan[6] = u01;
+            plan[7] = 0.0;
+        }
     }
     __syncthreads();
     // phase C: global block prefixes, and the emitted-output count at the end of every block
@@ -155,14 +170,23 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
         g_cnt[t] = runmax;
     }
     __syncthreads();
-    if (t == 0) {
-        long long run = 0;
-        for (long long g = 0; g < ngroups; ++g) {
+    if (t < 32) {
+        const int per = (int)((ngroups + 31) / 32);
+        const long long q0 = (long long)t * per, q1 = min(ngroups, q0 + per);
+        long long mx = 0;
+        for (long long g = q0; g < q1; ++g) mx = max(mx, g_cnt[g]);
+        long long base = 0;
+        for (int l = 0; l < 32; ++l) {
+            const long long v = __shfl_sync(0xffffffffu, mx, l);
+            if (l < t) base = max(base, v);
+        }
+        long long run = base;
+        for (long long g = q0; g < q1; ++g) {
             const long long cur = g_cnt[g];
             g_cnt[g] = run;
             run = max(run, cur);
         }
-        block_count[0] = 0;
+        if (t == 0) block_count[0] = 0;
     }
     __syncthreads();
     if (t < ngroups) {

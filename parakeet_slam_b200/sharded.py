@@ -106,7 +106,7 @@ class ShardedFastSLAM(FastSLAM):
         torch, lib, dist = self._torch, self._lib, self._dist
         Ml, Mt, G, me, nb = self.num_particles, self.num_particles_total, self.world_size, self.rank, self._nb
         dev = self._device
-        with self._lock, torch.cuda.device(dev):
+        with self._lock, self._on_device():
             u01 = float(self._uniform())  # every rank must draw the same value (same seed / same source)
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
@@ -138,17 +138,17 @@ class ShardedFastSLAM(FastSLAM):
             n_send, n_in = sum(send_counts), sum(recv_counts)
             rec = self._record_bytes
             self._ensure_exchange_buffers(n_send, n_in)
-            # runs for ranks below / above me are contiguous in the emit list, on either side of the local run
-            off = 0
-            for h in range(G):
-                if send_counts[h]:
-                    run = emit[plan["send_start"][h]:]
-                    _lib.check(lib.pk_pack_particles(_lib.ptr(run), send_counts[h], self.particle_offset,
+            # the runs for the ranks below me are contiguous at the head of the emit list and those for the
+            # ranks above me at its tail (ancestors ascend), so two pack calls cover every destination
+            n_below = sum(send_counts[:me])
+            n_above = sum(send_counts[me + 1:])
+            for count, start, off in ((n_below, 0, 0), (n_above, plan["emit_n"] - n_above, n_below)):
+                if count:
+                    _lib.check(lib.pk_pack_particles(_lib.ptr(emit[start:]), count, self.particle_offset,
                                                      _lib.ptr(pose_in), _lib.ptr(aux_in), _lib.ptr(slot_in),
                                                      _lib.ptr(self._pool), self.capacity, self._dt,
                                                      self._send_buf.data_ptr() + off * rec, _lib.ptr(self._pack_ws), st),
                                "pk_pack_particles")
-                    off += send_counts[h]
             if G > 1:
                 # cross-shard resampled particles: one record per particle, rank to rank over NVLink
                 dist.all_to_all_single(self._recv_buf[:n_in], self._send_buf[:n_send], recv_counts, send_counts,
@@ -182,7 +182,7 @@ class ShardedFastSLAM(FastSLAM):
 
     def summary(self):
         torch, lib, dist = self._torch, self._lib, self._dist
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             _lib.check(lib.pk_summary_partial(_lib.ptr(self.pose), self.num_particles, _lib.ptr(self._out5),
                                               _lib.ptr(self._red_ws), self._stream()), "pk_summary_partial")
             dist.all_reduce(self._out5, group=self._group)
@@ -192,7 +192,7 @@ class ShardedFastSLAM(FastSLAM):
 
     def best_particle(self):
         torch, lib, dist = self._torch, self._lib, self._dist
-        with self._lock, torch.cuda.device(self._device):
+        with self._lock, self._on_device():
             _lib.check(lib.pk_best_particle(_lib.ptr(self.pose), self.num_particles, _lib.ptr(self._best2),
                                             _lib.ptr(self._red_ws), self._stream()), "pk_best_particle")
             mine = self._best2.clone()
