@@ -83,39 +83,42 @@ constexpr double kLog2Pi = 1.8378770664093453;  // math.log(2*pi)
 __device__ __forceinline__ double match_likelihood(const Landmark& L, double px, double py, double pth, double beta,
                                                    double orr, double og, double ob, double dirx, double diry,
                                                    const pk_params& prm, unsigned& flags, double& pse_out) {
-    pse_out = 0.0;
+    // Written without early exits: candidates that reach this point almost always pass the gates, and
+    // one straight-line block lets the independent chains (bearing, position pdf, colour pdf) overlap.
     // colour gate :425-427, :441
-    double dr = orr - L.r, dg = og - L.g, db = ob - L.b;
-    double cdist = dr * dr + dg * dg + db * db;
-    if (fabs(cdist) > prm.color_gate) return 0.0;
+    const double dr = orr - L.r, dg = og - L.g, db = ob - L.b;
+    const double cdist = dr * dr + dg * dg + db * db;
+    bool gated = fabs(cdist) > prm.color_gate;
     // bearing gate :408-415, :433
-    double dx = L.x - px, dy = L.y - py;
-    double pse = pk_atan2(dy, dx);
+    const double dx = L.x - px, dy = L.y - py;
+    const double pse = pk_atan2(dy, dx);
     pse_out = pse;
-    double del = beta - (pse - pth);
-    if (fabs(del) > prm.bearing_gate) return 0.0;
+    const double del = beta - (pse - pth);
+    gated = gated || (fabs(del) > prm.bearing_gate);
     // prob_position_match :473-475 (robot-frame bearing used as if world frame, finding F4c)
-    if (fabs(pse - beta) > prm.position_gate) return 0.0;
+    gated = gated || (fabs(pse - beta) > prm.position_gate);
     // closest_point :509-522
-    double t = dx * dirx + dy * diry;
-    double nx = (t < 0.0) ? px : px + dirx * t;
-    double ny = (t < 0.0) ? py : py + diry * t;
-    double ex = nx - L.x, ey = ny - L.y;
+    const double t = dx * dirx + dy * diry;
+    const double nx = (t < 0.0) ? px : px + dirx * t;
+    const double ny = (t < 0.0) ? py : py + diry * t;
+    const double ex = nx - L.x, ey = ny - L.y;
     // 2-D pdf, covariance symmetrised from the LOWER triangle (scipy eigh(lower=True)) :482-490
-    double a = L.sp[0], b10 = L.sp[2], d = L.sp[3];
-    double det2 = a * d - b10 * b10;
-    double maha2 = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det2;
-    double bp = pk_exp(-0.5 * (2.0 * kLog2Pi + log(det2) + maha2));
+    const double a = L.sp[0], b10 = L.sp[2], d = L.sp[3];
+    const double det2 = a * d - b10 * b10;
+    const double maha2 = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det2;
+    const double bp = pk_exp(-0.5 * (2.0 * kLog2Pi + log(det2) + maha2));
     // 3-D colour pdf :530-544, lower triangle
-    double A = L.sc[0], B = L.sc[3], C = L.sc[6], D = L.sc[4], E = L.sc[7], F = L.sc[8];
-    double c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
-    double c11 = A * F - C * C, c12 = B * C - A * E, c22 = A * D - B * B;
-    double det3 = A * c00 + B * c01 + C * c02;
-    double maha3 = (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0 * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
-    double cp = pk_exp(-0.5 * (3.0 * kLog2Pi + log(det3) + maha3));
-    if (!(det2 > 0.0) || !(det3 > 0.0)) flags |= PK_FLAG_SINGULAR_COV;
+    const double A = L.sc[0], B = L.sc[3], C = L.sc[6], D = L.sc[4], E = L.sc[7], F = L.sc[8];
+    const double c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
+    const double c11 = A * F - C * C, c12 = B * C - A * E, c22 = A * D - B * B;
+    const double det3 = A * c00 + B * c01 + C * c02;
+    const double maha3 =
+        (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0 * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
+    const double cp = pk_exp(-0.5 * (3.0 * kLog2Pi + log(det3) + maha3));
+    if (!gated && (!(det2 > 0.0) || !(det3 > 0.0))) flags |= PK_FLAG_SINGULAR_COV;
     // :439, :446, :455
-    return (500.0 * bp) * (500.0 * cp) / 250000.0;
+    const double Lk = (500.0 * bp) * (500.0 * cp) / 250000.0;
+    return gated ? 0.0 : Lk;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -96,8 +96,10 @@ __host__ __device__ constexpr int staged_candidates() {
 }
 
 // per-item screen result, kept in registers between screen(g) and evaluate(g)
+constexpr int kMaxHits = 4;
 struct Hits {
-    int cnt, c0, c1;
+    int cnt;
+    int c[kMaxHits];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -229,7 +231,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         const int nitems = gpn * K;
         produce();  // opens this group if it is not open yet
 #pragma unroll
-        for (int r = 0; r < R; ++r) H[r] = Hits{0, -1, -1};
+        for (int r = 0; r < R; ++r) H[r] = Hits{0, {-1, -1, -1, -1}};
         const int nsteps = S.nsteps_s[gi];
         for (int step = 0; step < nsteps; ++step) {
             produce();
@@ -262,8 +264,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 while (m) {  // about one hit per item
                     const int j = step * kChunk + __ffsll((long long)m) - 1;
                     m &= m - 1ull;
-                    if (H[r].cnt == 0) H[r].c0 = j;
-                    else if (H[r].cnt == 1) H[r].c1 = j;
+#pragma unroll
+                    for (int c = 0; c < kMaxHits; ++c)
+                        if (H[r].cnt == c) H[r].c[c] = j;
                     H[r].cnt += 1;
                 }
             }
@@ -278,7 +281,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             for (int c = 0; c < kStaged; ++c) {
                 if (H[r].cnt > c) {
                     const unsigned char* src = cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap,
-                                                           c == 0 ? H[r].c0 : H[r].c1);
+                                                           H[r].c[c]);
                     const uint32_t dst =
                         s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
 #pragma unroll
@@ -317,7 +320,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             lastj = -1;
             if (cnt > 0) {
                 load_staged<T>(s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)w) * kRecBytes, L);
-                lastj = H[r].c0;
+                lastj = H[r].c[0];
                 const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r],
                                                    ob_dy[r], A.prm, st_flags, pse);
                 st_eval += 1;
@@ -328,19 +331,34 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 }
             }
             if (__any_sync(kFull, cnt > 1)) {
-                if (cnt == 2) {  // a second colour-compatible landmark
-                    if (kStaged > 1) load_staged<T>(s_rec + (((unsigned)par * kStaged + 1u) * 32u * R + (unsigned)w) * kRecBytes, L);
-                    else load_landmark<T>(block, cap, H[r].c1, L);
-                    lastj = H[r].c1;
-                    const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r],
-                                                       ob_dy[r], A.prm, st_flags, pse);
-                    st_eval += 1;
-                    if (Lk > best) {
-                        best = Lk;
-                        bestj = lastj;
-                        best_pse = pse;
+                if (cnt <= kMaxHits) {  // further colour-compatible landmarks, in slot order
+#pragma unroll
+                    for (int c = 1; c < kMaxHits; ++c) {
+                        // Most extra hits are false positives of the byte-key screen: apply the exact colour
+                        // gate (:441) first and run the full likelihood only if some lane still needs it.
+                        bool need = false;
+                        if (c < cnt) {
+                            if (c < kStaged)
+                                load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)w) * kRecBytes, L);
+                            else
+                                load_landmark<T>(block, cap, H[r].c[c], L);
+                            lastj = H[r].c[c];
+                            const double dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
+                            need = !(fabs(dr * dr + dg * dg + db * db) > A.prm.color_gate);
+                        }
+                        if (!__any_sync(kFull, need)) continue;
+                        if (need) {
+                            const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                               ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
+                            st_eval += 1;
+                            if (Lk > best) {
+                                best = Lk;
+                                bestj = lastj;
+                                best_pse = pse;
+                            }
+                        }
                     }
-                } else if (cnt > 2) {  // many colour-compatible landmarks: scan the whole map in slot order
+                } else if (cnt > kMaxHits) {  // many colour-compatible landmarks: scan the whole map in slot order
                     best = 0.0;
                     bestj = -1;
                     lastj = -1;
@@ -428,7 +446,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     // ---- software pipeline over this warp's groups -----------------------------------------------
     Hits Hcur[R], Hnext[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
+    for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, {-1, -1, -1, -1}};
     for (long long git = -1; git < my_groups; ++git) {
         if (git + 1 < my_groups) screen(git + 1, Hnext);
         if (git >= 0) evaluate(git, Hcur, git + 1 < my_groups);

@@ -174,3 +174,49 @@ def _export_subset(fs, sub):
         rows = sub[sel] - lo
         mean5[sel], covp[sel], covc[sel], meta[sel], ids[sel], nlive[sel] = m5[rows], cp[rows], cc[rows], me[rows], idd[rows], nl[rows]
     return mean5, covp, covc, meta, ids, nlive
+
+
+@pytest.mark.parametrize("n_colours", [24, 6])
+def test_colour_ambiguous_maps_against_oracle(n_colours):
+    """Landmarks that share colours: every blob has several colour-compatible landmarks, so the
+    bearing / position terms decide.  Exercises the 2..4-candidate path (24 colours for 48 landmarks)
+    and the whole-map scan (6 colours, 8 landmarks each)."""
+    import torch
+    from oracle import fastslam_np as onp
+    from parakeet_slam_b200.scenario import DT_NSEC
+    M, N, T = 2048, 48, 5
+    noise_rs = np.random.RandomState(5)
+    blocks = [noise_rs.standard_normal((M, 3)) for _ in range(T)]
+    it = iter(blocks)
+    scn, fs, clk, tw = _make(M, N, "f64", T, noise=lambda m: next(it))
+    # recolour the world: n_colours distinct colours, jittered by < 2 units
+    rs = np.random.RandomState(8)
+    palette = rs.uniform(20, 235, (n_colours, 3))
+    scn.landmarks[:, 2:5] = palette[np.arange(N) % n_colours] + rs.uniform(-1.5, 1.5, (N, 3))
+    for t in range(T):
+        scn.observations[t, :, 1:4] = scn.landmarks[scn.obs_landmark[t], 2:5] + rs.normal(0, 0.3, (8, 3))
+    from device_harness import make_features
+    from parakeet_slam_b200.core import FastSLAM
+    fs2 = FastSLAM(make_features(scn), num_particles=M, dtype="f64", noise=lambda m: next(it), uniform=random.Random(4).random,
+                   clock=clk)
+    fs2.last_control = tw
+    fs2.keep_trace = True
+    st = onp.OracleState(M, scn.landmarks, preset_covar=scn.preset_covar)
+    urng = random.Random(4)
+    evals = 0
+    for t in range(T):
+        clk.ns += DT_NSEC
+        fs2.motion_update(tw)
+        fs2.measurement_update(scn.observations[t])
+        evals = max(evals, fs2.stats()["evaluated"] / M)
+        fs2.low_variance_resample()
+        ids, wgt, anc, _ = onp.frame(st, scn.observations[t], blocks[t], scn.v, scn.w, scn.dt, urng.random(),
+                                     sequential_resample=False)
+        assert np.array_equal(fs2.last_assoc.cpu().numpy(), ids), "frame %d" % t
+        assert np.array_equal(fs2.last_ancestors.cpu().numpy(), anc), "frame %d" % t
+        w = fs2.last_weight.cpu().numpy()
+        big = wgt > 1e-300
+        assert np.max(np.abs(w[big] - wgt[big]) / wgt[big]) < 1e-8
+    assert evals > (12 if n_colours == 24 else 40)   # the ambiguous paths really ran
+    mean5 = fs2.export_maps()[0]
+    assert np.max(np.abs(mean5 - st.mean) / np.maximum(np.abs(st.mean), 1e-3)) < 1e-8
