@@ -52,6 +52,7 @@ constexpr int kKeyStride = kChunk + 4;  // words; +4 keeps the particles' key ro
 constexpr int kStages = 2;           // key stages in flight per warp
 constexpr int kMaxGroup = 8;         // particles per group
 constexpr int kMaxItems = 64;        // group * K
+constexpr int kMaxHits = 8;          // hits per item kept (two in registers, the rest in shared memory)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct MeasureArgs {
@@ -86,6 +87,7 @@ struct alignas(128) WarpSmem {
     int slot_s[4][kMaxGroup];
     int nlive_s[4][kMaxGroup];
     int nsteps_s[4];
+    int more_hits[2][kMaxItems][kMaxHits - 2];  // third and later hits of an item (rare)
     uint64_t key_bar[kStages];
 };
 
@@ -96,10 +98,8 @@ __host__ __device__ constexpr int staged_candidates() {
 }
 
 // per-item screen result, kept in registers between screen(g) and evaluate(g)
-constexpr int kMaxHits = 4;
 struct Hits {
-    int cnt;
-    int c[kMaxHits];
+    int cnt, c0, c1;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -231,7 +231,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         const int nitems = gpn * K;
         produce();  // opens this group if it is not open yet
 #pragma unroll
-        for (int r = 0; r < R; ++r) H[r] = Hits{0, {-1, -1, -1, -1}};
+        for (int r = 0; r < R; ++r) H[r] = Hits{0, -1, -1};
         const int nsteps = S.nsteps_s[gi];
         for (int step = 0; step < nsteps; ++step) {
             produce();
@@ -264,9 +264,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 while (m) {  // about one hit per item
                     const int j = step * kChunk + __ffsll((long long)m) - 1;
                     m &= m - 1ull;
-#pragma unroll
-                    for (int c = 0; c < kMaxHits; ++c)
-                        if (H[r].cnt == c) H[r].c[c] = j;
+                    if (H[r].cnt == 0) H[r].c0 = j;
+                    else if (H[r].cnt == 1) H[r].c1 = j;
+                    else if (H[r].cnt < kMaxHits) S.more_hits[par][r * 32 + lane][H[r].cnt - 2] = j;
                     H[r].cnt += 1;
                 }
             }
@@ -281,7 +281,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             for (int c = 0; c < kStaged; ++c) {
                 if (H[r].cnt > c) {
                     const unsigned char* src = cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap,
-                                                           H[r].c[c]);
+                                                           c == 0 ? H[r].c0 : H[r].c1);
                     const uint32_t dst =
                         s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
 #pragma unroll
@@ -320,7 +320,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             lastj = -1;
             if (cnt > 0) {
                 load_staged<T>(s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)w) * kRecBytes, L);
-                lastj = H[r].c[0];
+                lastj = H[r].c0;
                 const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r],
                                                    ob_dy[r], A.prm, st_flags, pse);
                 st_eval += 1;
@@ -332,17 +332,18 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             }
             if (__any_sync(kFull, cnt > 1)) {
                 if (cnt <= kMaxHits) {  // further colour-compatible landmarks, in slot order
-#pragma unroll
-                    for (int c = 1; c < kMaxHits; ++c) {
+                    const int maxcnt = __reduce_max_sync(kFull, cnt <= kMaxHits ? cnt : 0);
+                    for (int c = 1; c < maxcnt; ++c) {
                         // Most extra hits are false positives of the byte-key screen: apply the exact colour
                         // gate (:441) first and run the full likelihood only if some lane still needs it.
                         bool need = false;
                         if (c < cnt) {
+                            const int j = (c == 1) ? H[r].c1 : S.more_hits[par][w][c - 2];
                             if (c < kStaged)
                                 load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)w) * kRecBytes, L);
                             else
-                                load_landmark<T>(block, cap, H[r].c[c], L);
-                            lastj = H[r].c[c];
+                                load_landmark<T>(block, cap, j, L);
+                            lastj = j;
                             const double dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
                             need = !(fabs(dr * dr + dg * dg + db * db) > A.prm.color_gate);
                         }
@@ -358,21 +359,38 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                             }
                         }
                     }
-                } else if (cnt > kMaxHits) {  // many colour-compatible landmarks: scan the whole map in slot order
+                } else if (cnt > kMaxHits) {
+                    // More colour-compatible landmarks than hit registers: walk the particle's keys again
+                    // (from global memory this time) and evaluate every landmark that passes the key screen
+                    // and the exact colour gate, in slot order.
                     best = 0.0;
                     bestj = -1;
                     lastj = -1;
                     const int nlive = S.nlive_s[gi][pl];
-                    for (int j = 0; j < nlive; ++j) {
-                        Landmark Lj;
-                        load_landmark<T>(block, cap, j, Lj);
-                        const double Lk = match_likelihood(Lj, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
-                                                           ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
-                        st_eval += 1;
-                        if (Lk > best) {
-                            best = Lk;
-                            bestj = j;
-                            best_pse = pse;
+                    const unsigned* gkeys = reinterpret_cast<const unsigned*>(block);
+                    const unsigned mykey = it_key[r];
+                    for (int j4 = 0; j4 < nlive; j4 += 4) {
+                        const int4 kv = ldcg16(gkeys + j4);  // the key region is padded to 16 bytes
+                        const unsigned kk[4] = {(unsigned)kv.x, (unsigned)kv.y, (unsigned)kv.z, (unsigned)kv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 + e;
+                            const unsigned dk = __vabsdiffu4(kk[e], mykey);
+                            if (j >= nlive || (int)__dp4a(dk, dk, 0u) > key_thr) continue;
+                            double cr_, cg_, cb_;
+                            load_colour<T>(block, cap, j, cr_, cg_, cb_);
+                            const double dr = ob_r[r] - cr_, dg = ob_g[r] - cg_, db = ob_b[r] - cb_;
+                            if (fabs(dr * dr + dg * dg + db * db) > A.prm.color_gate) continue;
+                            load_landmark<T>(block, cap, j, L);
+                            lastj = j;
+                            const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                               ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
+                            st_eval += 1;
+                            if (Lk > best) {
+                                best = Lk;
+                                bestj = j;
+                                best_pse = pse;
+                            }
                         }
                     }
                 }
@@ -446,7 +464,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     // ---- software pipeline over this warp's groups -----------------------------------------------
     Hits Hcur[R], Hnext[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, {-1, -1, -1, -1}};
+    for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
     for (long long git = -1; git < my_groups; ++git) {
         if (git + 1 < my_groups) screen(git + 1, Hnext);
         if (git >= 0) evaluate(git, Hcur, git + 1 < my_groups);

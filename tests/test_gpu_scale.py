@@ -176,11 +176,11 @@ def _export_subset(fs, sub):
     return mean5, covp, covc, meta, ids, nlive
 
 
-@pytest.mark.parametrize("n_colours", [24, 6])
+@pytest.mark.parametrize("n_colours", [24, 6, 3])
 def test_colour_ambiguous_maps_against_oracle(n_colours):
     """Landmarks that share colours: every blob has several colour-compatible landmarks, so the
     bearing / position terms decide.  Exercises the 2..4-candidate path (24 colours for 48 landmarks)
-    and the whole-map scan (6 colours, 8 landmarks each)."""
+    the shared-memory hit list (6 colours, 8 landmarks each) and the key re-walk (3 colours, 16 each)."""
     import torch
     from oracle import fastslam_np as onp
     from parakeet_slam_b200.scenario import DT_NSEC
