@@ -8,6 +8,23 @@
 
 namespace pk {
 
+// fp64 literals are materialised by two UMOV/IMAD.MOV each; coefficients placed in __constant__ memory are
+// consumed directly as c[bank][offset] operands of DFMA / DADD.
+__constant__ double kExpC[12] = {1.0 / 6.0,        0.5,
+                                 1.0 / 120.0,      1.0 / 24.0,
+                                 1.0 / 5040.0,     1.0 / 720.0,
+                                 1.0 / 362880.0,   1.0 / 40320.0,
+                                 1.0 / 39916800.0, 1.0 / 3628800.0,
+                                 1.0 / 6227020800.0, 1.0 / 479001600.0};
+__constant__ double kExpK[4] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
+                                -1.90821492927058770002e-10};
+__constant__ double kAtanC[11] = {3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                                  -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
+                                  6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                                  -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+__constant__ double kAtanK[6] = {7.85398163397448278999e-01, 3.06161699786838301793e-17, 1.57079632679489655800e+00,
+                                 6.12323399573676603587e-17, 3.14159265358979311600e+00, 1.22464679914735317720e-16};
+
 // ---------------------------------------------------------------------------------------------
 // Branch-free exp (fp64, <= 2 ulp, exact underflow behaviour).  Most arguments here are hundreds
 // below zero (finding F3: the match / no-match decision IS the fp64 underflow of the likelihood), which
@@ -17,21 +34,22 @@ namespace pk {
 // step into the subnormal range (or to 0 / inf).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pk_exp(double x) {
-    const double xc = fmin(fmax(x, -1100.0), 1100.0);
-    const double shift = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer
-    const double t = fma(xc, 1.4426950408889634074, shift);
+    double xc = (x < -1100.0) ? -1100.0 : x;  // (plain selects: fmin/fmax cost ~10 instructions each in fp64)
+    xc = (xc > 1100.0) ? 1100.0 : xc;
+    const double shift = kExpK[1];  // 1.5 * 2^52: adding it rounds to nearest integer
+    const double t = fma(xc, kExpK[0], shift);
     const int n = __double2loint(t);
     const double fn = t - shift;
-    double r = fma(fn, -6.93147180369123816490e-01, xc);
-    r = fma(fn, -1.90821492927058770002e-10, r);
+    double r = fma(fn, kExpK[2], xc);
+    r = fma(fn, kExpK[3], r);
     const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
     const double a0 = 1.0 + r;
-    const double a1 = fma(r, 1.0 / 6.0, 0.5);
-    const double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    const double a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-    const double a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-    const double a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
-    const double a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    const double a1 = fma(r, kExpC[0], kExpC[1]);
+    const double a2 = fma(r, kExpC[2], kExpC[3]);
+    const double a3 = fma(r, kExpC[4], kExpC[5]);
+    const double a4 = fma(r, kExpC[6], kExpC[7]);
+    const double a5 = fma(r, kExpC[8], kExpC[9]);
+    const double a6 = fma(r, kExpC[10], kExpC[11]);
     const double lo = fma(r2, a1, a0);                       // 1 + r + r^2 (1/2 + r/6)
     const double mid = fma(r2, a3, a2);                      // r^4 ( ... )
     const double hi = fma(r4, a6, fma(r2, a5, a4));          // r^8 ( ... )
@@ -52,26 +70,21 @@ __device__ __forceinline__ double pk_exp(double x) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pk_atan2(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
-    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool steep = ay > ax;
+    const double mx = steep ? ay : ax, mn = steep ? ax : ay;
     const bool big = mn > 0.41421356237309503 * mx;
     const double num = big ? mn - mx : mn;
     const double den = big ? mn + mx : mx;
     double t = num / den;
     if (den == 0.0) t = 0.0;  // atan2(+-0, +-0): math.atan2 gives +-0 / +-pi like the selects below
     const double z = t * t, w = z * z;
-    const double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, 1.62858201153657823623e-02, 4.97687799461593236017e-02),
-                                                         6.66107313738753120669e-02),
-                                                  9.09088713343650656196e-02),
-                                           1.42857142725034663711e-01),
-                                    3.33333333333329318027e-01);
-    const double s2 = w * fma(w, fma(w, fma(w, fma(w, -3.65315727442169155270e-02, -5.83357013379057348645e-02),
-                                                  -7.69187620504482999495e-02),
-                                           -1.11111104054623557880e-01),
-                                    -1.99999999998764832476e-01);
+    const double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, kAtanC[10], kAtanC[8]), kAtanC[6]), kAtanC[4]), kAtanC[2]),
+                              kAtanC[0]);
+    const double s2 = w * fma(w, fma(w, fma(w, fma(w, kAtanC[9], kAtanC[7]), kAtanC[5]), kAtanC[3]), kAtanC[1]);
     double r = t - t * (s1 + s2);
-    if (big) r = 7.85398163397448278999e-01 + (r + 3.06161699786838301793e-17);
-    if (ay > ax) r = 1.57079632679489655800e+00 - (r - 6.12323399573676603587e-17);
-    if (signbit(x)) r = 3.14159265358979311600e+00 - (r - 1.22464679914735317720e-16);
+    if (big) r = kAtanK[0] + (r + kAtanK[1]);
+    if (steep) r = kAtanK[2] - (r - kAtanK[3]);
+    if (signbit(x)) r = kAtanK[4] - (r - kAtanK[5]);
     return copysign(r, y);
 }
 

@@ -208,7 +208,10 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 if (p_step == 0) tma_load_1d_a(s_pose + (uint32_t)gi * (kMaxGroup * 32), A.pose4 + 4 * p0, (unsigned)(gpn * 32), bar);
             }
             __syncwarp();
-            if (bytes)  // every lane moves its own particle's keys
+            // every lane moves its own particle's keys.  (cp.async.bulk takes warp-uniform operands, so this
+            // compiles to a short waterfall over the <= 8 issuing lanes; issuing all copies from lane 0 in a
+            // loop was measured slower.)
+            if (bytes)
                 tma_load_1d_a(s_keys + ((stage * (unsigned)GP + (unsigned)lane) * kKeyStride) * 4u,
                               A.pool + (size_t)S.slot_s[gi][lane] * A.block_bytes + (size_t)p_step * kChunk * 4, bytes, bar);
             ++p_cnt;
