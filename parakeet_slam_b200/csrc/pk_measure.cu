@@ -429,11 +429,14 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 if (matched && rank == q) {
                     // the winner's record is in registers unless another candidate was evaluated after
                     // it, or an earlier blob of this frame has just rewritten the landmark
-                    if (q > 0 || lastj != bestj) load_landmark<T>(block, cap, bestj, L);
+                    const bool fresh = (q > 0 || lastj != bestj);
+                    if (fresh) load_landmark<T>(block, cap, bestj, L);
                     int promoted = 0;
                     bool changed = false;
+                    // the bearing computed during association is that of the PRE-update landmark: it can be
+                    // re-used only if no earlier blob of this frame has moved the landmark since
                     factor = ekf_update_lm(L, px, py, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], A.prm, id_out, st_flags,
-                                           promoted, changed, true, best_pse);
+                                           promoted, changed, !fresh, best_pse);
                     if (changed) store_landmark<T>(block, cap, bestj, L);
                     st_promoted += promoted;
                     if (q > 0) st_same += 1;

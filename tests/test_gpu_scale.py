@@ -220,3 +220,82 @@ def test_colour_ambiguous_maps_against_oracle(n_colours):
     assert evals > (12 if n_colours == 24 else 40)   # the ambiguous paths really ran
     mean5 = fs2.export_maps()[0]
     assert np.max(np.abs(mean5 - st.mean) / np.maximum(np.abs(st.mean), 1e-3)) < 1e-8
+
+
+@pytest.mark.parametrize("K", [1, 3, 33, 40, 64])
+def test_blob_counts_against_oracle(K):
+    """Scans with 1, 3 (partial lane groups), 33/40/64 blobs (two items per lane) -- several blobs hit the
+    same landmark, so the sequential same-landmark updates (finding F2) are exercised too."""
+    from oracle import fastslam_np as onp
+    from device_harness import make_features
+    from parakeet_slam_b200.core import FastSLAM
+    from parakeet_slam_b200.rosless import Time, messages
+    from parakeet_slam_b200.scenario import DT_NSEC, make_scenario
+    M, N, T = 1001, 24, 4
+    scn = make_scenario("c2", num_particles=M, num_landmarks=N, obs_per_frame=min(K, N), frames=T)
+    rs = np.random.RandomState(K)
+    obs = np.zeros((T, K, 4))
+    for t in range(T):
+        pick = np.concatenate([np.arange(min(K, N)), rs.randint(0, min(K, N), max(0, K - N))])
+        obs[t] = scn.observations[t][pick]
+        obs[t, :, 0] += rs.normal(0, 0.01, K)        # repeated blobs: same landmark, slightly different reading
+        obs[t, :, 1:] += rs.normal(0, 0.2, (K, 3))
+
+    class Clk(object):
+        ns = 0
+
+        def __call__(self):
+            return Time(0, self.ns)
+    clk = Clk()
+    blocks = [rs.standard_normal((M, 3)) for _ in range(T)]
+    it = iter(blocks)
+    fs = FastSLAM(make_features(scn), num_particles=M, dtype="f64", noise=lambda m: next(it),
+                  uniform=random.Random(2).random, clock=clk)
+    fs.keep_trace = True
+    tw = messages.Twist()
+    tw.linear.x, tw.angular.z = scn.v, scn.w
+    fs.last_control = tw
+    st = onp.OracleState(M, scn.landmarks, preset_covar=scn.preset_covar)
+    urng = random.Random(2)
+    same = 0
+    for t in range(T):
+        clk.ns += DT_NSEC
+        fs.motion_update(tw)
+        fs.measurement_update(obs[t])
+        same += fs.stats()["same_landmark"]
+        fs.low_variance_resample()
+        ids, wgt, anc, _ = onp.frame(st, obs[t], blocks[t], scn.v, scn.w, scn.dt, urng.random(), sequential_resample=False)
+        assert np.array_equal(fs.last_assoc.cpu().numpy(), ids), "frame %d" % t
+        assert np.array_equal(fs.last_ancestors.cpu().numpy(), anc), "frame %d" % t
+        w = fs.last_weight.cpu().numpy()
+        big = wgt > 1e-300
+        assert np.max(np.abs(w[big] - wgt[big]) / wgt[big]) < 1e-8
+    mean5, covp, covc, meta, _, _ = fs.export_maps()
+    assert np.max(np.abs(mean5 - st.mean) / np.maximum(np.abs(st.mean), 1e-3)) < 1e-8
+    assert np.max(np.abs(covc - st.cov[..., 2:, 2:])) < 1e-10
+    assert np.array_equal(meta & 0xFFFFFF, st.count)
+    if K > N:
+        assert same > 0
+
+
+def test_empty_scan_and_too_many_blobs():
+    from device_harness import make_features
+    from parakeet_slam_b200.core import FastSLAM
+    from parakeet_slam_b200.rosless import messages
+    from parakeet_slam_b200.scenario import make_scenario
+    scn = make_scenario("c1", num_particles=64, frames=1)
+    fs = FastSLAM(make_features(scn), num_particles=64, noise="philox")
+    fs.keep_trace = True
+
+    class V(object):
+        last_sensor_reading = messages.VizScan()
+    before = fs.export_maps()[0]
+    fs.cam_cb(V())                               # no blobs: weights stay 1, resampling keeps everyone
+    assert np.array_equal(fs.last_ancestors.cpu().numpy(), np.arange(64))
+    assert np.array_equal(fs.export_maps()[0], before)
+    assert fs.particles[3].weight == 1.0 and fs.particles[3].next_id == 21
+    with pytest.raises(ValueError):
+        fs.measurement_update(np.zeros((65, 4)))
+    V.last_sensor_reading = None
+    with pytest.raises(AttributeError):          # as the reference: scan.observes on None (:344)
+        fs.cam_cb(V())
