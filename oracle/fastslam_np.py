@@ -68,6 +68,7 @@ class OracleState(object):
         self.count = np.zeros((M, N), dtype=np.int64)
         self.immutable = np.zeros((M, N), dtype=bool)
         self.live = np.zeros((M, N), dtype=bool)
+        self.potential = np.zeros((M, N), dtype=bool)     # lives in potential_features, id = -(slot+1)  :287
         self.next_id = np.ones(M, dtype=np.int64)         # :292
         if n:
             self.mean[:, :n] = np.asarray(landmarks, dtype=np.float64)[None]
@@ -225,6 +226,10 @@ def associate(state: OracleState, obs):
     best = np.argmax(L, axis=2)          # first occurrence of the maximum
     best_val = np.take_along_axis(L, best[:, :, None], axis=2)[:, :, 0]
     ids = np.where(best_val > 0.0, best + 1, 0)
+    # potential features carry negative ids (:336, :367); with full features in the lower slots the slot
+    # order is the reference's iteration order (feature_set first, then potential_features)
+    pot = np.take_along_axis(state.potential, best, axis=1)
+    ids = np.where(pot, -ids, ids)
     return ids.astype(np.int32), best_val
 
 
@@ -252,7 +257,7 @@ def measurement_update(state: OracleState, obs, ids=None):
         m = ~un
         if m.any():
             r = rows[m]
-            j = idk[m] - 1
+            j = np.abs(idk[m]) - 1
             mu = state.mean[r, j]                       # [m,5]
             Sg = state.cov[r, j]                        # [m,5,5]
             px = state.pose[r, 0]
@@ -286,7 +291,13 @@ def measurement_update(state: OracleState, obs, ids=None):
             v1 = (2.0 * math.pi * np.sqrt(np.sum(np.abs(Q) ** 2, axis=(1, 2)))) ** -0.5
             expo = -0.5 * np.einsum("mi,mij,mj->m", delz, Qinv, delz)
             with np.errstate(under="ignore"):
-                factor[m] = v1 * np.exp(expo)
+                fm = v1 * np.exp(expo)
+            neg = idk[m] < 0
+            # potential feature :109-118: weight as if unseen; promoted when update_count > 5
+            fm = np.where(neg, NO_MATCH_WEIGHT, fm)
+            factor[m] = fm
+            promote = neg & (state.count[r, j] > PROMOTE_COUNT)
+            state.potential[r[promote], j[promote]] = False
         state.weight = state.weight * factor            # :124 / :95
     return ids
 
@@ -332,7 +343,7 @@ def resample_searchsorted(weight, u01):
 
 def apply_ancestors(state: OracleState, anc):
     """``temp_particles.append(deepcopy(particle))`` (``:243``) for every ancestor."""
-    for name in ("pose", "weight", "mean", "cov", "count", "immutable", "live", "next_id"):
+    for name in ("pose", "weight", "mean", "cov", "count", "immutable", "live", "potential", "next_id"):
         setattr(state, name, getattr(state, name)[anc].copy())
 
 
@@ -368,13 +379,15 @@ def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=Non
     return ids, wgt, anc, pose_pre
 
 
-def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), chunk=None):
+def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), chunk=None, potential_slots=()):
     """Run the restatement over a ``Scenario`` (same trace layout as
     ``oracle.ref_driver.run_reference``)."""
     T = scn.frames if frames is None else frames
     M = scn.num_particles if num_particles is None else num_particles
     K = scn.obs_per_frame
     st = OracleState(M, scn.landmarks, preset_covar=scn.preset_covar, immutable=scn.immutable)
+    for j in potential_slots:
+        st.potential[:, j] = True
     trace = dict(pose_pre=np.zeros((T, M, 3)), pose_post=np.zeros((T, M, 3)),
                  assoc=np.zeros((T, M, K), dtype=np.int32), weight=np.zeros((T, M)),
                  ancestors=np.zeros((T, M), dtype=np.int32), summary=np.zeros((T, 3)),
@@ -395,5 +408,6 @@ def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), c
             trace["lm_mean"][t] = st.mean.copy()
             trace["lm_cov"][t] = st.cov.copy()
             trace["lm_count"][t] = st.count.copy()
+            trace.setdefault("lm_potential", {})[t] = st.potential.copy()
     trace["state"] = st
     return trace

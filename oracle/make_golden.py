@@ -37,9 +37,9 @@ def _blockdiag_parts(cov):
     return cov[..., :2, :2].copy(), cov[..., 2:, 2:].copy(), cross
 
 
-def trace_fixture(name, scn, frames, checkpoints, spawn=False, known_map=True):
+def trace_fixture(name, scn, frames, checkpoints, spawn=False, known_map=True, potential_slots=()):
     tr = ref_driver.run_reference(scn, frames=frames, record_landmarks_at=checkpoints,
-                                  spawn=spawn, known_map=known_map)
+                                  spawn=spawn, known_map=known_map, potential_slots=potential_slots)
     out = dict(
         scenario=np.array([scn.name]), trajectory=np.array([scn.meta["trajectory"]]),
         num_particles=scn.num_particles, num_landmarks=scn.num_landmarks,
@@ -50,6 +50,7 @@ def trace_fixture(name, scn, frames, checkpoints, spawn=False, known_map=True):
         pose_pre=tr["pose_pre"], pose_post=tr["pose_post"], assoc=tr["assoc"].astype(np.int16),
         weight=tr["weight"], ancestors=tr["ancestors"].astype(np.int32), summary=tr["summary"],
         next_id=tr["next_id"].astype(np.int32), checkpoints=np.asarray(checkpoints),
+        potential_slots=np.asarray(potential_slots, dtype=np.int32),
     )
     worst_cross = 0.0
     for t in checkpoints:
@@ -59,6 +60,7 @@ def trace_fixture(name, scn, frames, checkpoints, spawn=False, known_map=True):
         out["lm_covp_%d" % t] = cp
         out["lm_covc_%d" % t] = cc
         out["lm_count_%d" % t] = tr["lm_count"][t].astype(np.int32)
+        out["lm_potential_%d" % t] = tr["lm_potential"][t]
     out["max_cross_block"] = worst_cross
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     np.savez_compressed(path, **out)
@@ -311,6 +313,10 @@ def main(argv=None):
             make_scenario("c1", num_particles=48, frames=40, trajectory="corridor",
                           sigma_color=3.0, sigma_bearing=0.08, num_landmarks=40), 40, (0, 39)),
     }
+    jobs["potential"] = lambda: trace_fixture(
+        "trace_corridor_potential_m24_t12",
+        make_scenario("c1", num_particles=24, frames=12, trajectory="corridor", num_landmarks=16), 12,
+        (0, 2, 3, 11), potential_slots=(1, 5, 8, 9, 12, 13, 14, 15))
     if args.full_c1:
         jobs["c1"] = lambda: trace_fixture(
             "trace_c1_m100_n20_t500", make_scenario("c1"), 500, (0, 99, 249, 499))

@@ -40,7 +40,7 @@ def pose_of(ref, particle):
             heading_of(ref, particle))
 
 
-def build_reference_filter(ref, scn: Scenario, num_particles=None, known_map=True):
+def build_reference_filter(ref, scn: Scenario, num_particles=None, known_map=True, potential_slots=()):
     """``FastSLAM`` with M particles (the reference hard-codes 50, ``:41``) preloaded with the
     scenario's true landmarks, covar ``preset_covar * I5`` (``prkt_ros.py:33-37``)."""
     core = ref.core
@@ -59,6 +59,11 @@ def build_reference_filter(ref, scn: Scenario, num_particles=None, known_map=Tru
         fs.particles = [core.FilterParticle() for _ in range(M)]
         for particle in fs.particles:
             particle.load_feature_list(feats)
+    # some landmarks as POTENTIAL features: potential_features[-id] (:287, :679); a state the API allows
+    # although the reference's own flow never reaches it (finding F5)
+    for particle in fs.particles:
+        for j in potential_slots:
+            particle.potential_features[-(j + 1)] = particle.feature_set.pop(j + 1)
     return fs
 
 
@@ -69,15 +74,23 @@ def landmark_state(fs, n_slots):
     cov = np.zeros((M, n_slots, 5, 5))
     cnt = np.zeros((M, n_slots), dtype=np.int64)
     for i, p in enumerate(fs.particles):
-        for id_, f in p.feature_set.items():
-            mean[i, id_ - 1] = np.asarray(f.mean, dtype=np.float64).reshape(5)
-            cov[i, id_ - 1] = np.asarray(f.covar, dtype=np.float64)
-            cnt[i, id_ - 1] = f.update_count
+        for id_, f in list(p.feature_set.items()) + list(p.potential_features.items()):
+            mean[i, abs(id_) - 1] = np.asarray(f.mean, dtype=np.float64).reshape(5)
+            cov[i, abs(id_) - 1] = np.asarray(f.covar, dtype=np.float64)
+            cnt[i, abs(id_) - 1] = f.update_count
     return mean, cov, cnt
 
 
+def potential_state(fs, n_slots):
+    pot = np.zeros((len(fs.particles), n_slots), dtype=bool)
+    for i, p in enumerate(fs.particles):
+        for id_ in p.potential_features:
+            pot[i, -id_ - 1] = True
+    return pot
+
+
 def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmarks_at=(),
-                  ref=None, spawn=False, known_map=True, timing=None):
+                  ref=None, spawn=False, known_map=True, timing=None, potential_slots=()):
     """Run the reference over ``frames`` frames.  Returns a dict of numpy traces:
 
     ``pose_pre``  [T, M, 3] pose after motion, before resampling (the pose the
@@ -97,7 +110,7 @@ def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmar
     M = scn.num_particles if num_particles is None else num_particles
     K = scn.obs_per_frame
 
-    fs = build_reference_filter(ref, scn, num_particles=M, known_map=known_map)
+    fs = build_reference_filter(ref, scn, num_particles=M, known_map=known_map, potential_slots=potential_slots)
     twist = ref.msgs.Twist()
     twist.linear.x = scn.v
     twist.angular.z = scn.w
@@ -159,6 +172,7 @@ def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmar
                 if t in record_landmarks_at:
                     mean, cov, cnt = landmark_state(fs, scn.num_landmarks)
                     trace["lm_mean"][t], trace["lm_cov"][t], trace["lm_count"][t] = mean, cov, cnt
+                    trace.setdefault("lm_potential", {})[t] = potential_state(fs, scn.num_landmarks)
                 if timing is not None and timing(t, trace["frame_seconds"][: t + 1]):
                     trace["frames_run"] = t + 1
                     break

@@ -571,6 +571,23 @@ class FastSLAM(object):
             return (mean5.cpu().numpy(), covp.cpu().numpy().reshape(count, N, 2, 2),
                     covc.cpu().numpy().reshape(count, N, 3, 3), meta.cpu().numpy(), ids.cpu().numpy(), nlive)
 
+    def import_maps(self, lo, mean5, covp, covc, meta, ids, n_live=None):
+        """Overwrite the landmark state of particles [lo, lo+count) from fp64 arrays shaped like the
+        output of ``export_maps`` (``meta`` = update_count | PK_META_IMMUTABLE | PK_META_POTENTIAL, ``ids`` the
+        reference ids: > 0 full feature, < 0 potential feature)."""
+        torch, lib = self._torch, self._lib
+        count = len(mean5)
+        dev = self._device
+        with self._lock, self._on_device():
+            t = [torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev) for a, dt in
+                 ((mean5, np.float64), (np.reshape(covp, (count, -1, 4)), np.float64),
+                  (np.reshape(covc, (count, -1, 9)), np.float64), (meta, np.int32), (ids, np.int32))]
+            _lib.check(lib.pk_map_import(_lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self.slot), lo, count,
+                                         *[_lib.ptr(x) for x in t], self._stream()), "pk_map_import")
+            if n_live is not None:
+                self.aux[lo:lo + count, 0] = torch.from_numpy(np.asarray(n_live, dtype=np.int32)).to(dev)
+            torch.cuda.current_stream(dev).synchronize()
+
     def get_map(self, i):
         """Additive API: ``{id: Feature}`` of particle ``i`` (full and potential landmarks)."""
         p = self._particle_view(i)

@@ -26,7 +26,8 @@ def unit_vectors():
 
 
 TRACE_FIXTURES = ["trace_circle_m32_t60", "trace_corridor_m32_t60",
-                  "trace_circle_immutable_m32_t40", "trace_corridor_noisy_m48_t40"]
+                  "trace_circle_immutable_m32_t40", "trace_corridor_noisy_m48_t40",
+                  "trace_corridor_potential_m24_t12"]
 if os.path.exists(golden_path("trace_c1_m100_n20_t500.npz")):
     TRACE_FIXTURES.append("trace_c1_m100_n20_t500")
 

@@ -22,7 +22,7 @@ def make_features(scn):
     return feats
 
 
-def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=(), noise="numpy"):
+def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=(), noise="numpy", potential_slots=()):
     from parakeet_slam_b200.core import FastSLAM
     T = scn.frames if frames is None else frames
     M = scn.num_particles if num_particles is None else num_particles
@@ -30,6 +30,13 @@ def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=()
     clock.set(0.0)
     fs = FastSLAM(make_features(scn), num_particles=M, dtype=dtype, noise=noise)
     fs.keep_trace = True
+    if len(potential_slots):
+        # turn some preset landmarks into POTENTIAL features (id < 0), as potential_features[-id] of the reference
+        mean5, covp, covc, meta, ids, nlive = fs.export_maps()
+        sl = list(potential_slots)
+        meta[:, sl] |= 0x20000000
+        ids[:, sl] = -ids[:, sl]
+        fs.import_maps(0, mean5, covp, covc, meta, ids)
     tw = messages.Twist()
     tw.linear.x = scn.v
     tw.angular.z = scn.w
@@ -60,5 +67,6 @@ def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=()
             mean5, covp, covc, meta, ids, nlive = fs.export_maps()
             tr["lm_mean"][t], tr["lm_covp"][t], tr["lm_covc"][t] = mean5, covp, covc
             tr["lm_count"][t] = meta & 0x00FFFFFF
+            tr.setdefault("lm_potential", {})[t] = (meta & 0x20000000) != 0
     tr["filter"] = fs
     return tr

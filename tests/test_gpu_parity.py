@@ -119,8 +119,12 @@ def test_trace_f64(lib, name):
     g = load_trace(name)
     scn = scenario_from_trace(g)
     cps = tuple(int(c) for c in g["checkpoints"])
-    tr = run_device(scn, "f64", checkpoints=cps)
+    pot = tuple(int(j) for j in g["potential_slots"]) if "potential_slots" in g.files else ()
+    tr = run_device(scn, "f64", checkpoints=cps, potential_slots=pot)
     _check_trace(tr, g, cps, exact=True, tol_state=1e-5, tol_weight=1e-5, min_index_match=1.0)
+    for t in cps:
+        if pot:   # potential -> full promotion (:114-118) happened on the same frames as in the reference
+            assert np.array_equal(tr["lm_potential"][t], g["lm_potential_%d" % t])
     # tighter: what the fp64 path actually achieves
     assert np.max(np.abs(tr["pose_pre"] - g["pose_pre"])) < 1e-11
     big = g["weight"] > 1e-300
@@ -135,7 +139,8 @@ def test_trace_f32_storage(lib, name):
     from device_harness import run_device
     g = load_trace(name)
     scn = scenario_from_trace(g)
-    tr = run_device(scn, "f32")
+    pot = tuple(int(j) for j in g["potential_slots"]) if "potential_slots" in g.files else ()
+    tr = run_device(scn, "f32", potential_slots=pot)
     a, r = _check_trace(tr, g, (), exact=False, tol_state=1e-5, tol_weight=1e-3, min_index_match=0.90)
     # first frame sees identical state: landmark presets are exactly representable or rounded once
     assert np.array_equal(tr["assoc"][0], g["assoc"][0])

@@ -99,7 +99,8 @@ def test_trace(name):
     g = load_trace(name)
     scn = scenario_from_trace(g)
     cps = tuple(int(c) for c in g["checkpoints"])
-    tr = onp.run_scenario(scn, record_landmarks_at=cps)
+    pot = tuple(int(j) for j in g["potential_slots"]) if "potential_slots" in g.files else ()
+    tr = onp.run_scenario(scn, record_landmarks_at=cps, potential_slots=pot)
     assert np.array_equal(tr["assoc"], g["assoc"])           # bit-exact indices
     assert np.array_equal(tr["ancestors"], g["ancestors"])
     assert np.array_equal(tr["next_id"], g["next_id"])
@@ -112,4 +113,9 @@ def test_trace(name):
         assert np.max(np.abs(tr["lm_cov"][t][..., :2, :2] - g["lm_covp_%d" % t])) < 1e-10
         assert np.max(np.abs(tr["lm_cov"][t][..., 2:, 2:] - g["lm_covc_%d" % t])) < 1e-10
         assert np.array_equal(tr["lm_count"][t], g["lm_count_%d" % t])
+        if pot:
+            assert np.array_equal(tr["lm_potential"][t], g["lm_potential_%d" % t])
+    if pot:  # the fixture really exercises negative ids and the promotion of :114-118
+        assert (g["assoc"] < 0).any() and (g["assoc"][-1] > 0).all()
+        assert g["lm_potential_%d" % cps[0]].any() and not g["lm_potential_%d" % cps[-1]][:, list(pot)].all()
     assert float(g["max_cross_block"]) == 0.0
