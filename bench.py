@@ -37,6 +37,9 @@ LANDMARKS = 64
 BLOBS = 8
 KERNELS_PER_STEP = 11  # motion, measure, weight_scan, thresholds, ancestors, fill_runs,
 #                        dead_scan, block_offsets, free_list, assign, copy_blocks
+KERNELS_PER_STEP_PEER = 18   # + 2 peer barriers, exchange plan, push headers, push blocks, offspring window,
+#                              unpack blocks (sharded filter, peer exchange; no NCCL kernel in a frame)
+KERNELS_PER_STEP_NCCL = 16   # + 2 x (pack headers, pack blocks), offspring window, unpack (plus 2 NCCL collectives)
 
 
 def measured_peaks():
@@ -220,10 +223,20 @@ def run_ours(args):
     clk = _Clock()
     import random
     urng = random.Random(12345)
+    exchange = None
     if world > 1:
         from parakeet_slam_b200.sharded import ShardedFastSLAM
-        fs = ShardedFastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
-                             uniform=urng.random, clock=clk)
+        exchange = args.exchange
+        try:
+            fs = ShardedFastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
+                                 uniform=urng.random, clock=clk, exchange=exchange)
+        except _lib.ParakeetLibraryError as exc:
+            if exchange != "peer":
+                raise
+            # CUDA IPC unavailable on this box: same filter over NCCL (both are GPU paths); say so in the line
+            exchange = "nccl (peer memory unavailable: %s)" % str(exc)[:120]
+            fs = ShardedFastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
+                                 uniform=urng.random, clock=clk, exchange="nccl")
     else:
         fs = FastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
                       uniform=urng.random, clock=clk)
@@ -350,6 +363,7 @@ def run_ours(args):
                 "matched_fraction": matched_frac, "exact_evaluations_per_particle": eval_per_particle,
                 "f_dup_last_frame": f_dup,
                 "parallelism": "particle-sharded x%d" % world,
+                "exchange": exchange,
             },
             "kernel_ms": {"motion": ms_motion, "measure": ms_measure, "resample_total": ms_resample},
             "roofline": {
@@ -365,7 +379,8 @@ def run_ours(args):
             "e2e": {"value": updates / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": K * 4 * 8 + 3 * 8, "d2h_bytes_per_step": 5 * 8,
                     "ms_per_step": e2e_ms / steps, "api": "FastSLAM.cam_cb(view) + FastSLAM.summary()"},
-            "gpu_launches": KERNELS_PER_STEP * steps,
+            "gpu_launches": (KERNELS_PER_STEP if world == 1 else KERNELS_PER_STEP_PEER if exchange == "peer"
+                             else KERNELS_PER_STEP_NCCL) * steps,
             "clocks": clocks,
             "summary_last": list(est),
         }
@@ -387,6 +402,8 @@ def main(argv=None):
     ap.add_argument("--particles-per-gpu", type=int, default=PARTICLES_PER_GPU)
     ap.add_argument("--landmarks", type=int, default=LANDMARKS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="cross-shard exchange engine of the sharded filter (N > 1)")
     args = ap.parse_args(argv)
     if args.impl == "reference":
         return run_reference_arm(args)

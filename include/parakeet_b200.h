@@ -10,8 +10,10 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends
  *     in _host; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
- *   - the library never allocates or frees persistent device memory: the caller owns all
- *     state (PyTorch tensors on the Python side) and passes a workspace where one is needed
+ *   - the library never allocates or frees persistent device memory behind the caller's back: the
+ *     caller owns all state (PyTorch tensors on the Python side) and passes a workspace where one
+ *     is needed.  The one exception is explicit: pk_peer_alloc / pk_peer_free, because memory that
+ *     is shared with other ranks through CUDA IPC must be a plain cudaMalloc allocation
  *   - every function returns 0 on success or a negative PK_E* code; pk_last_error() gives a
  *     thread-local message.  No C++ exception crosses the boundary.
  *   - all work is asynchronous on `stream`; nothing here synchronises the device
@@ -67,6 +69,27 @@ extern "C" {
 #define PK_STAT_SAME_LANDMARK 4  /* updates that had to wait for an earlier blob on the same landmark */
 #define PK_STAT_PROMOTED 5       /* potential -> full promotions (prkt_core_v2.py:114-118) */
 #define PK_NUM_STATS 8
+
+/* peer (NVLink) exchange of the sharded filter */
+#define PK_MAX_RANKS 32          /* ranks of one node sharing a filter (lane g of a warp serves rank g) */
+#define PK_XPLAN_LONGS 80        /* int64 words of the device-resident exchange plan */
+#define PK_PEER_HANDLE_BYTES 64  /* size of an exported peer-memory handle (cudaIpcMemHandle_t) */
+#define PK_PEER_OVERFLOW 1ull    /* status bit: a rank would receive more than the exchange capacity */
+#define PK_PEER_TIMEOUT 2ull     /* status bit: a peer did not reach a barrier within the time-out */
+/* words of the exchange plan a caller may read back (the rest is internal) */
+#define PK_XP_EMIT_LO 0
+#define PK_XP_EMIT_N 1
+#define PK_XP_N_LO 2
+#define PK_XP_N_LOC 3
+#define PK_XP_N_HI 4
+#define PK_XP_N_BELOW 5
+#define PK_XP_N_ABOVE 6
+#define PK_XP_ABOVE_START 7
+#define PK_XP_N_SEND 8
+#define PK_XP_N_IN 9
+#define PK_XP_OVERFLOW 10
+#define PK_XP_RANK_LO 16
+#define PK_XP_RANK_LOC (16 + PK_MAX_RANKS)
 
 #define PK_FLAG_SINGULAR_COV 1u      /* a landmark covariance block had det <= 0 (SciPy would raise) */
 #define PK_FLAG_NONFINITE_WEIGHT 2u  /* a particle weight became NaN/Inf */
@@ -202,6 +225,53 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
 int pk_copy_blocks(const void* src_base, void* dst_base, int capacity, int dtype, const int* src_slot,
                    const int* dst_slot, const int* n_live, long long n_max, const long long* n_dev,
                    void* stream);
+
+/* ---- peer path of the sharded filter: same arithmetic, but every count stays on the device and the
+ *      two exchanges of low_variance_resample (prkt_core_v2.py:218-226 needs the global weight sum,
+ *      :243 moves whole particles) are done by this library's kernels over NVLink peer memory.  Each
+ *      rank owns ONE peer allocation [flags | all block totals | receive buffer] and holds device
+ *      tables (uint64[n_ranks]) with the address of each region on every rank. ---------------------- */
+int pk_peer_alloc(long long bytes, void** ptr_out);                   /* cudaMalloc + zero fill */
+int pk_peer_free(void* ptr);
+int pk_peer_export(void* ptr, unsigned char* handle_out_host);        /* PK_PEER_HANDLE_BYTES */
+int pk_peer_open(const unsigned char* handle_host, void** ptr_out);   /* map a peer's allocation */
+int pk_peer_close(void* ptr);
+/* K3a fused with the all-gather of the block totals: block b of rank `rank` is also stored to
+ * peer_sums_tab[g][rank * nb + b] for every rank g (g == rank included). */
+int pk_weight_scan_publish(const double* pose4, long long M, double* cumsum, double* block_sums,
+                           const unsigned long long* peer_sums_tab, int rank, int n_ranks,
+                           void* stream);
+/* Device-side barrier over flags in peer memory (peer_flags_tab[g] = uint64[n_ranks] on rank g).
+ * `epoch` must increase by one per call, starting at 1, identically on all ranks.  A peer that does
+ * not arrive within timeout_s sets PK_PEER_TIMEOUT in *status (device uint64) instead of hanging. */
+int pk_peer_barrier(const unsigned long long* peer_flags_tab, int rank, int n_ranks,
+                    unsigned long long epoch, double timeout_s, unsigned long long* status,
+                    void* stream);
+/* Exchange plan of this rank from block_count (K3b output over all ranks' blocks, nb_per_rank each):
+ * xplan[PK_XPLAN_LONGS] device int64.  `capacity` = records a rank may RECEIVE per frame (the size
+ * of its receive buffer); a rank then sends at most (n_ranks - 1) * capacity.  Exceeding it sets
+ * PK_PEER_OVERFLOW in *status and voids the frame (no out-of-bounds access). */
+int pk_exchange_plan(const long long* block_count, long long nb_per_rank, int n_ranks, int rank,
+                     long long Ml, long long capacity, long long* xplan, unsigned long long* status,
+                     void* stream);
+/* Same arithmetic on the host from emitted_before[n_ranks+1] (CPU tests, debugging). */
+int pk_exchange_plan_host(const long long* emitted_before_host, int n_ranks, int rank, long long Ml,
+                          long long capacity, long long* xplan_host);
+/* Push every offspring of a local particle whose output slot lives on another rank straight into
+ * that rank's receive buffer (peer_recv_tab[g]).  send_capacity >= (n_ranks - 1) * capacity;
+ * workspace: 4 * send_capacity ints. */
+int pk_push_particles(const long long* xplan, const long long* out_lo, long long Ml, int rank,
+                      const double* pose4, const int* aux2, const int* slot, const void* pool,
+                      int capacity, int dtype, const unsigned long long* peer_recv_tab,
+                      long long send_capacity, int* workspace, void* stream);
+/* pk_resample_gather_sharded with the window split read from xplan; anc_window[Ml] = global ancestor
+ * of each local output slot (as written by pk_resample_ancestors with out_offset = rank * Ml). */
+int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
+                            const long long* out_lo, const int* offspring, long long Ml,
+                            long long particle_offset, const double* pose4_in, double* pose4_out,
+                            const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
+                            const void* recv, long long recv_capacity, void* pool, int capacity,
+                            int dtype, void* workspace, long long* total_dead_out, void* stream);
 
 /* ---- K6 queries: FastSLAM.summary (prkt_core_v2.py:254-276); best particle is additive ------- */
 /* out5[0..3] = sum x, sum y, sum sin(theta), sum cos(theta); out5[4] = M.  The caller finishes

@@ -39,6 +39,14 @@ PK_META_POTENTIAL = 0x20000000
 PK_STAT_MATCHED, PK_STAT_UNMATCHED, PK_STAT_EVALUATED, PK_STAT_FLAGS = 0, 1, 2, 3
 PK_STAT_SAME_LANDMARK, PK_STAT_PROMOTED = 4, 5
 PK_FLAG_SINGULAR_COV, PK_FLAG_NONFINITE_WEIGHT, PK_FLAG_REPROMOTED = 1, 2, 4
+PK_MAX_RANKS = 32
+PK_XPLAN_LONGS = 80
+PK_PEER_HANDLE_BYTES = 64
+PK_PEER_OVERFLOW, PK_PEER_TIMEOUT = 1, 2
+(PK_XP_EMIT_LO, PK_XP_EMIT_N, PK_XP_N_LO, PK_XP_N_LOC, PK_XP_N_HI, PK_XP_N_BELOW, PK_XP_N_ABOVE,
+ PK_XP_ABOVE_START, PK_XP_N_SEND, PK_XP_N_IN, PK_XP_OVERFLOW) = range(11)
+PK_XP_RANK_LO = 16
+PK_XP_RANK_LOC = 16 + PK_MAX_RANKS
 
 
 class PkParams(ctypes.Structure):
@@ -123,6 +131,18 @@ SIGNATURES = {
     "pk_resample_gather_sharded": (_I, [_P, _P, _P, _LL, _LL, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I,
                                         _P, _P, _P]),
     "pk_copy_blocks": (_I, [_P, _P, _I, _I, _P, _P, _P, _LL, _P, _P]),
+    "pk_peer_alloc": (_I, [_LL, ctypes.POINTER(_P)]),
+    "pk_peer_free": (_I, [_P]),
+    "pk_peer_export": (_I, [_P, _P]),
+    "pk_peer_open": (_I, [_P, ctypes.POINTER(_P)]),
+    "pk_peer_close": (_I, [_P]),
+    "pk_weight_scan_publish": (_I, [_P, _LL, _P, _P, _P, _I, _I, _P]),
+    "pk_peer_barrier": (_I, [_P, _I, _I, _ULL, _D, _P, _P]),
+    "pk_exchange_plan": (_I, [_P, _LL, _I, _I, _LL, _LL, _P, _P, _P]),
+    "pk_exchange_plan_host": (_I, [_P, _I, _I, _LL, _LL, _P]),
+    "pk_push_particles": (_I, [_P, _P, _LL, _I, _P, _P, _P, _P, _I, _I, _P, _LL, _P, _P]),
+    "pk_resample_gather_peer": (_I, [_P, _P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _P, _I, _I,
+                                     _P, _P, _P]),
     "pk_summary_partial": (_I, [_P, _LL, _P, _P, _P]),
     "pk_best_particle": (_I, [_P, _LL, _P, _P, _P]),
     "pk_probe_likelihood": (_I, [_P, _P, _P, _P, _P, _P, _LL, ctypes.POINTER(PkParams), _P, _P]),

@@ -34,7 +34,8 @@ __device__ __forceinline__ int padded(int e) { return e + (e >> 5); }
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanWarps * 32)
 weight_scan_kernel(const double* __restrict__ pose4, long long M, double* __restrict__ cumsum,
-                   double* __restrict__ block_sums, long long nb) {
+                   double* __restrict__ block_sums, long long nb, double* const* __restrict__ peer_sums, int me,
+                   int n_ranks) {
     __shared__ double sm[kScanWarps][PK_SCAN_BLOCK + 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long blk = (long long)blockIdx.x * kScanWarps + warp;
@@ -72,7 +73,14 @@ weight_scan_kernel(const double* __restrict__ pose4, long long M, double* __rest
         const int e = it * 32 + lane;
         if (e < n) cumsum[base + e] = s[padded(e)];
     }
-    if (lane == 31) block_sums[blk] = __dadd_rn(b, total);
+    const double block_total = __dadd_rn(b, total);
+    if (lane == 31) block_sums[blk] = block_total;
+    if (peer_sums != nullptr) {
+        // fused all-gather: lane g stores this block's total straight into rank g's copy of the global
+        // block-total array (peer memory over NVLink; rank g == me is the local copy)
+        const double t31 = __shfl_sync(kFullMask, block_total, 31);
+        if (lane < n_ranks) peer_sums[lane][(long long)me * nb + blk] = t31;
+    }
 }
 
 // number of outputs k in [0, M) with u0 + k*r <= P + c   (P double-double block prefix)
@@ -342,6 +350,154 @@ assign_kernel(const long long* __restrict__ ancestors, long long M, const double
 // by its landmark block.  kHeaderBytes keeps the block 64-byte aligned inside the exchange buffer.
 constexpr int kHeaderBytes = 64;
 
+// ---- device-resident exchange plan (peer path) ------------------------------------------------------
+// Everything the exchange needs follows from E[g] = number of output slots whose ancestor lives on a
+// rank < g (E[g] = block_count[g * nb], which every rank computes identically in K3b): rank g's
+// offspring occupy the global output slots [E[g], E[g+1]) and output slot k belongs to rank k / Ml.
+// The same function runs on the host (pk_exchange_plan_host; CPU tests compare it with the Python
+// plan_exchange) and in a one-thread kernel, so no count ever crosses PCIe.
+enum {
+    XP_EMIT_LO = 0,    // E[me]
+    XP_EMIT_N = 1,     // E[me+1] - E[me]: outputs descending from my particles
+    XP_N_LO = 2,       // my output slots filled from lower ranks
+    XP_N_LOC = 3,      // ... from my own particles
+    XP_N_HI = 4,       // ... from higher ranks
+    XP_N_BELOW = 5,    // my offspring that live on lower ranks
+    XP_N_ABOVE = 6,    // ... on higher ranks
+    XP_ABOVE_START = 7,  // first global output slot of the N_ABOVE run
+    XP_N_SEND = 8,     // N_BELOW + N_ABOVE (0 when XP_OVERFLOW)
+    XP_N_IN = 9,       // N_LO + N_HI        (0 when XP_OVERFLOW)
+    XP_OVERFLOW = 10,  // some rank would receive more than the exchange capacity
+    XP_N_RANKS = 11,
+    XP_ML = 12,
+    XP_RANK_LO = 16,   // [PK_MAX_RANKS] n_lo of every rank
+    XP_RANK_LOC = 16 + PK_MAX_RANKS,  // [PK_MAX_RANKS] n_loc of every rank
+};
+static_assert(PK_XPLAN_LONGS >= 16 + 2 * PK_MAX_RANKS, "exchange plan size");
+
+__host__ __device__ inline long long xp_clamp(long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__host__ __device__ inline void make_exchange_plan(const long long* E, int G, long long Ml, int me, long long cap,
+                                                   long long* xp) {
+    for (int i = 0; i < PK_XPLAN_LONGS; ++i) xp[i] = 0;
+    bool overflow = false;
+    for (int g = 0; g < G; ++g) {
+        const long long w0 = (long long)g * Ml, w1 = w0 + Ml;
+        const long long n_lo = xp_clamp(E[g] - w0, 0, Ml);             // window slots below E[g]
+        const long long loc_hi = xp_clamp(E[g + 1], w0, w1), loc_lo = xp_clamp(E[g], w0, w1);
+        const long long n_loc = loc_hi - loc_lo;
+        xp[XP_RANK_LO + g] = n_lo;
+        xp[XP_RANK_LOC + g] = n_loc;
+        // capacity bounds what a rank RECEIVES; what it sends is then at most (G-1) * cap (the send
+        // lists are sized for that: one particle may own every output slot of the filter)
+        if (Ml - n_loc > cap) overflow = true;
+        if (g == me) {
+            xp[XP_EMIT_LO] = E[g];
+            xp[XP_EMIT_N] = E[g + 1] - E[g];
+            xp[XP_N_LO] = n_lo;
+            xp[XP_N_LOC] = n_loc;
+            xp[XP_N_HI] = Ml - n_lo - n_loc;
+            const long long below_end = xp_clamp(w0, E[g], E[g + 1]);    // offspring slots < my window
+            const long long above_start = xp_clamp(w1, E[g], E[g + 1]);  // offspring slots >= window end
+            xp[XP_N_BELOW] = below_end - E[g];
+            xp[XP_N_ABOVE] = E[g + 1] - above_start;
+            xp[XP_ABOVE_START] = above_start;
+        }
+    }
+    xp[XP_OVERFLOW] = overflow ? 1 : 0;
+    xp[XP_N_SEND] = overflow ? 0 : xp[XP_N_BELOW] + xp[XP_N_ABOVE];
+    xp[XP_N_IN] = overflow ? 0 : xp[XP_N_LO] + xp[XP_N_HI];
+    xp[XP_N_RANKS] = G;
+    xp[XP_ML] = Ml;
+}
+
+__global__ void exchange_plan_kernel(const long long* __restrict__ block_count, long long nb, int G, int me, long long Ml,
+                                     long long cap, long long* __restrict__ xplan, unsigned long long* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long E[PK_MAX_RANKS + 1];
+    for (int g = 0; g <= G; ++g) E[g] = block_count[(long long)g * nb];
+    long long xp[PK_XPLAN_LONGS];
+    make_exchange_plan(E, G, Ml, me, cap, xp);
+    for (int i = 0; i < PK_XPLAN_LONGS; ++i) xplan[i] = xp[i];
+    if (xp[XP_OVERFLOW]) atomicOr(status, (unsigned long long)PK_PEER_OVERFLOW);
+}
+
+// Cross-rank barrier on flags in peer memory: thread g tells rank g "I am at `epoch`" and waits until
+// rank g said the same.  Everything this rank wrote to peer memory earlier on the stream is ordered
+// before the flag (fence + release); everything the peers wrote before their flag is visible after
+// the acquire.  A rank that never shows up trips the time-out instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(PK_MAX_RANKS)
+peer_barrier_kernel(unsigned long long* const* __restrict__ peer_flags, int me, int G, unsigned long long epoch,
+                    unsigned long long timeout_ns, unsigned long long* __restrict__ status) {
+    const int g = threadIdx.x;
+    if (g >= G) return;
+    __threadfence_system();
+    st_release_sys(peer_flags[g] + me, epoch);
+    const unsigned long long* mine = peer_flags[me] + g;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(mine) < epoch) {
+        if (global_timer_ns() - t0 > timeout_ns) {
+            atomicOr(status, (unsigned long long)PK_PEER_TIMEOUT);
+            break;
+        }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+
+// One thread per migrating particle.  Send item j is global output slot k (the N_BELOW run starts at
+// E[me], the N_ABOVE run at ABOVE_START); its ancestor is the last local particle whose run starts at
+// or before k (runs tile [E[me], E[me+1]) in index order).  The header goes straight into the
+// destination rank's receive buffer; the landmark block follows through copy_blocks_kernel.
+__global__ void __launch_bounds__(256)
+push_headers_kernel(const long long* __restrict__ xplan, const long long* __restrict__ out_lo, long long Ml, int me,
+                    const double* __restrict__ pose4, const int* __restrict__ aux2, const int* __restrict__ slot,
+                    const unsigned long long* __restrict__ peer_recv, long long stride, long long cap,
+                    int* __restrict__ src_slot, int* __restrict__ dst_idx, int* __restrict__ dst_rank,
+                    int* __restrict__ nlive) {
+    const long long n_send = min(xplan[XP_N_SEND], cap);
+    const long long n_below = xplan[XP_N_BELOW];
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_send; j += (long long)gridDim.x * blockDim.x) {
+        const long long k = (j < n_below) ? xplan[XP_EMIT_LO] + j : xplan[XP_ABOVE_START] + (j - n_below);
+        // upper_bound(out_lo, k) - 1
+        long long lo = 0, hi = Ml;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (out_lo[mid] <= k) lo = mid + 1; else hi = mid;
+        }
+        const long long a = lo - 1;
+        const int h = (int)(k / Ml);
+        const long long k_local = k - (long long)h * Ml;
+        // receive buffer of rank h is ordered like its output window with the local run removed
+        const long long r = (h > me) ? k_local : k_local - xplan[XP_RANK_LOC + h];
+        unsigned char* out = reinterpret_cast<unsigned char*>(peer_recv[h]) + (size_t)r * stride;
+        const double2* src = reinterpret_cast<const double2*>(pose4 + 4 * a);
+        double2* dst = reinterpret_cast<double2*>(out);
+        dst[0] = src[0];
+        dst[1] = src[1];
+        const int2 ax = reinterpret_cast<const int2*>(aux2)[a];
+        *reinterpret_cast<int2*>(out + 32) = ax;
+        src_slot[j] = slot[a];
+        dst_idx[j] = (int)r;
+        dst_rank[j] = h;
+        nlive[j] = ax.x;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pack_headers_kernel(const long long* __restrict__ emit_run, long long n, long long particle_offset,
                     const double* __restrict__ pose4, const int* __restrict__ aux2, const int* __restrict__ slot,
@@ -375,9 +531,14 @@ offspring_window_kernel(const long long* __restrict__ out_lo, const int* __restr
 // offspring of local ancestors (n_loc) | incoming from higher ranks (Ml - n_lo - n_loc)] because
 // ancestors are globally ascending.  Incoming particles and local duplicates both take blocks
 // freed by local particles with no local offspring.
+//
+// xplan == NULL: n_lo / n_loc are the host's values and local_run[j] is the ancestor of local output
+// n_lo + j (NCCL path).  xplan != NULL: the split is read from the device-resident exchange plan and
+// local_run is indexed by the output slot itself (peer path; nothing on this path visits the host).
 __global__ void __launch_bounds__(256)
 assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, long long particle_offset, long long n_lo,
-                      long long n_loc, const double* __restrict__ pose_in, double* __restrict__ pose_out,
+                      long long n_loc, const long long* __restrict__ xplan, const double* __restrict__ pose_in,
+                      double* __restrict__ pose_out,
                       const int* __restrict__ aux_in, int* __restrict__ aux_out, const int* __restrict__ slot_in,
                       int* __restrict__ slot_out, const unsigned char* __restrict__ recv, long long stride,
                       const int* __restrict__ dead_excl, const int* __restrict__ free_list,
@@ -386,6 +547,13 @@ assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, lon
                       int* __restrict__ unpack_nlive) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Ml) return;
+    long long run_shift = n_lo;
+    if (xplan != nullptr) {
+        if (xplan[XP_OVERFLOW] != 0) return;  // exchange capacity exceeded: flagged, nothing is touched
+        n_lo = xplan[XP_N_LO];
+        n_loc = xplan[XP_N_LOC];
+        run_shift = 0;
+    }
     const long long n_in = Ml - n_loc;
     const long long n_dups = *total_dead - n_in;  // local outputs that are not the first of their ancestor
     double2* dst = reinterpret_cast<double2*>(pose_out + 4 * k);
@@ -407,13 +575,13 @@ assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, lon
         copy_nlive[nidx] = 0;
         return;
     }
-    const long long a = local_run[k - n_lo] - particle_offset;  // local ancestor
+    const long long a = local_run[k - run_shift] - particle_offset;  // local ancestor
     const double2* src = reinterpret_cast<const double2*>(pose_in + 4 * a);
     dst[0] = src[0];
     dst[1] = src[1];
     const int2 ax = reinterpret_cast<const int2*>(aux_in)[a];
     reinterpret_cast<int2*>(aux_out)[k] = ax;
-    const bool first = (k == n_lo) || (local_run[k - n_lo - 1] != local_run[k - n_lo]);
+    const bool first = (k == n_lo) || (local_run[k - run_shift - 1] != local_run[k - run_shift]);
     if (first) {
         slot_out[k] = slot_in[a];
     } else {
@@ -439,10 +607,13 @@ constexpr int kCopyChunk = 4096;
 __global__ void __launch_bounds__(32)
 copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __restrict__ dst_base, long long src_stride,
                    long long dst_stride, int hot_b, int cold_b, int capacity, const int* __restrict__ src_slot, const int* __restrict__ dst_slot,
-                   const int* __restrict__ nlive, long long n_max, const long long* __restrict__ n_dev) {
+                   const int* __restrict__ nlive, long long n_max, const long long* __restrict__ n_dev,
+                   const unsigned long long* __restrict__ dst_tab, const int* __restrict__ dst_rank,
+                   const long long* __restrict__ skip_flag) {
     __shared__ __align__(128) unsigned char buf[kCopyBufs][kCopyChunk];
     __shared__ uint64_t bar[kCopyBufs];
     if (threadIdx.x != 0) return;
+    if (skip_flag != nullptr && *skip_flag != 0) return;  // exchange overflow: the frame's copies are void
     long long n = n_dev ? *n_dev : n_max;
     if (n > n_max) n = n_max;
     for (int b = 0; b < kCopyBufs; ++b) mbar_init(&bar[b], 1);
@@ -494,7 +665,12 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
         mbar_wait(&bar[b], (unsigned)((drained / kCopyBufs) & 1));
         const long long len = seg_len(cd.item, cd.seg);
         const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - cd.off);
-        unsigned char* d = dst_base + (size_t)dst_slot[cd.item] * dst_stride + seg_base(cd.seg) + cd.off;
+        // dst_tab != NULL: the item goes to the receive buffer of rank dst_rank[item] (peer memory) and
+        // dst_base only carries the byte offset inside a record (the header size)
+        unsigned char* db = dst_tab ? reinterpret_cast<unsigned char*>(dst_tab[dst_rank[cd.item]]) +
+                                          reinterpret_cast<size_t>(dst_base)
+                                    : dst_base;
+        unsigned char* d = db + (size_t)dst_slot[cd.item] * dst_stride + seg_base(cd.seg) + cd.off;
         tma_store_1d(d, buf[b], bytes);
         tma_store_commit();
         ++drained;
@@ -652,7 +828,8 @@ int pk_weight_scan(const double* pose4, long long M, double* cumsum, double* blo
     PK_CHECK_ARG(M > 0, "M <= 0");
     const long long nb = num_blocks(M);
     const long long grid = (nb + kScanWarps - 1) / kScanWarps;
-    weight_scan_kernel<<<(unsigned)grid, kScanWarps * 32, 0, (cudaStream_t)stream>>>(pose4, M, cumsum, block_sums, nb);
+    weight_scan_kernel<<<(unsigned)grid, kScanWarps * 32, 0, (cudaStream_t)stream>>>(pose4, M, cumsum, block_sums, nb,
+                                                                                     nullptr, 0, 0);
     PK_LAUNCH_CHECK("weight_scan_kernel");
     return PK_OK;
 }
@@ -695,7 +872,9 @@ long long pk_gather_workspace_bytes(long long M) {
 
 static int copy_blocks_launch(const void* src, void* dst, int capacity, int dtype, const int* src_slot,
                               const int* dst_slot, const int* nlive, long long n_max, const long long* n_dev,
-                              cudaStream_t st, long long src_stride = 0, long long dst_stride = 0) {
+                              cudaStream_t st, long long src_stride = 0, long long dst_stride = 0,
+                              const unsigned long long* dst_tab = nullptr, const int* dst_rank = nullptr,
+                              const long long* skip_flag = nullptr) {
     if (src_stride == 0) src_stride = (long long)block_bytes(capacity, dtype);
     if (dst_stride == 0) dst_stride = (long long)block_bytes(capacity, dtype);
     long long grid = (long long)num_sms() * 12;
@@ -704,7 +883,7 @@ static int copy_blocks_launch(const void* src, void* dst, int capacity, int dtyp
     copy_blocks_kernel<<<(unsigned)grid, 32, 0, st>>>((const unsigned char*)src, (unsigned char*)dst, src_stride,
                                                      dst_stride, (int)hot_bytes(dtype),
                                                      (int)cold_bytes(dtype), capacity, src_slot, dst_slot, nlive, n_max,
-                                                     n_dev);
+                                                     n_dev, dst_tab, dst_rank, skip_flag);
     PK_LAUNCH_CHECK("copy_blocks_kernel");
     return PK_OK;
 }
@@ -763,20 +942,12 @@ int pk_pack_particles(const long long* emit_run, long long n, long long particle
     return PK_OK;
 }
 
-int pk_resample_gather_sharded(const long long* local_run, const long long* out_lo, const int* offspring, long long Ml,
-                               long long particle_offset, long long n_lo, long long n_loc, const double* pose4_in,
-                               double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
-                               const void* recv, void* pool, int capacity, int dtype, void* workspace,
-                               long long* total_dead_out, void* stream) {
-    PK_CHECK_ARG(out_lo && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out && pool &&
-                     workspace && total_dead_out,
-                 "null pointer");
-    PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31), "Ml");
-    PK_CHECK_ARG(n_lo >= 0 && n_loc >= 0 && n_lo + n_loc <= Ml, "window split");
-    PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
-    PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
-    cudaStream_t st = (cudaStream_t)stream;
+static int gather_sharded_impl(const long long* local_run, const long long* xplan, long long recv_capacity,
+                               const long long* out_lo, const int* offspring, long long Ml, long long particle_offset,
+                               long long n_lo, long long n_loc, const double* pose4_in, double* pose4_out,
+                               const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out, const void* recv,
+                               void* pool, int capacity, int dtype, void* workspace, long long* total_dead_out,
+                               cudaStream_t st) {
     GatherWs g = carve(workspace, Ml);
     const long long nb = num_blocks(Ml);
     const long long stride = pk_particle_record_bytes(capacity, dtype);
@@ -791,22 +962,50 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
     PK_LAUNCH_CHECK("block_offsets_kernel");
     free_list_kernel<<<grid, threads, 0, st>>>(g.offspring_local, slot_in, Ml, g.dead_excl, g.block_off, g.free_list);
     PK_LAUNCH_CHECK("free_list_kernel");
-    assign_sharded_kernel<<<grid, threads, 0, st>>>(local_run, Ml, particle_offset, n_lo, n_loc, pose4_in, pose4_out,
+    assign_sharded_kernel<<<grid, threads, 0, st>>>(local_run, Ml, particle_offset, n_lo, n_loc, xplan, pose4_in, pose4_out,
                                                     aux2_in, aux2_out, slot_in, slot_out, (const unsigned char*)recv, stride,
                                                     g.dead_excl, g.free_list, total_dead_out, g.copy_src, g.copy_dst,
                                                     g.copy_nlive, g.unpack_src, g.unpack_dst, g.unpack_nlive);
     PK_LAUNCH_CHECK("assign_sharded_kernel");
     if (capacity > 0) {
+        const long long* skip = xplan ? xplan + XP_OVERFLOW : nullptr;
         // local duplicates: pool -> pool (entries that belong to incoming particles carry src = -1 and are skipped)
-        int rc = copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, Ml, total_dead_out, st);
+        int rc = copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, Ml, total_dead_out, st,
+                                    0, 0, nullptr, nullptr, skip);
         if (rc != PK_OK) return rc;
         // arrivals: exchange buffer -> pool
+        if (xplan != nullptr) {
+            const long long n_max = recv_capacity < Ml ? recv_capacity : Ml;
+            if (n_max > 0)
+                return copy_blocks_launch((const unsigned char*)recv + kHeaderBytes, pool, capacity, dtype, g.unpack_src,
+                                          g.unpack_dst, g.unpack_nlive, n_max, xplan + XP_N_IN, st, stride, 0, nullptr,
+                                          nullptr, skip);
+            return PK_OK;
+        }
         const long long n_in = Ml - n_loc;
         if (n_in > 0)
             return copy_blocks_launch((const unsigned char*)recv + kHeaderBytes, pool, capacity, dtype, g.unpack_src,
                                       g.unpack_dst, g.unpack_nlive, n_in, nullptr, st, stride, 0);
     }
     return PK_OK;
+}
+
+int pk_resample_gather_sharded(const long long* local_run, const long long* out_lo, const int* offspring, long long Ml,
+                               long long particle_offset, long long n_lo, long long n_loc, const double* pose4_in,
+                               double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
+                               const void* recv, void* pool, int capacity, int dtype, void* workspace,
+                               long long* total_dead_out, void* stream) {
+    PK_CHECK_ARG(out_lo && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out && pool &&
+                     workspace && total_dead_out,
+                 "null pointer");
+    PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31), "Ml");
+    PK_CHECK_ARG(n_lo >= 0 && n_loc >= 0 && n_lo + n_loc <= Ml, "window split");
+    PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
+    PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    return gather_sharded_impl(local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
+                               pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
+                               total_dead_out, (cudaStream_t)stream);
 }
 
 int pk_copy_blocks(const void* pool_src, void* pool_dst, int capacity, int dtype, const int* src_slot,
@@ -842,6 +1041,137 @@ int pk_best_particle(const double* pose4, long long M, double* best2, double* wo
     PK_LAUNCH_CHECK("best_partial_kernel");
     best_final_kernel<<<1, 32, 0, st>>>(workspace, (int)blocks, best2);
     PK_LAUNCH_CHECK("best_final_kernel");
+    return PK_OK;
+}
+
+/* ---- peer path: the same resampling with every count resident on the device and the exchange done by
+ *      this library's own kernels over NVLink peer memory (no NCCL call, no host round trip) -------- */
+int pk_weight_scan_publish(const double* pose4, long long M, double* cumsum, double* block_sums,
+                           const unsigned long long* peer_sums_tab, int rank, int n_ranks, void* stream) {
+    PK_CHECK_ARG(pose4 && cumsum && block_sums && peer_sums_tab, "null pointer");
+    PK_CHECK_ARG(M > 0, "M <= 0");
+    PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    const long long nb = num_blocks(M);
+    const long long grid = (nb + kScanWarps - 1) / kScanWarps;
+    weight_scan_kernel<<<(unsigned)grid, kScanWarps * 32, 0, (cudaStream_t)stream>>>(
+        pose4, M, cumsum, block_sums, nb, reinterpret_cast<double* const*>(peer_sums_tab), rank, n_ranks);
+    PK_LAUNCH_CHECK("weight_scan_kernel");
+    return PK_OK;
+}
+
+int pk_peer_barrier(const unsigned long long* peer_flags_tab, int rank, int n_ranks, unsigned long long epoch,
+                    double timeout_s, unsigned long long* status, void* stream) {
+    PK_CHECK_ARG(peer_flags_tab && status, "null pointer");
+    PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    PK_CHECK_ARG(epoch > 0, "epoch must start at 1");
+    PK_CHECK_ARG(timeout_s > 0.0, "timeout");
+    peer_barrier_kernel<<<1, PK_MAX_RANKS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
+        (unsigned long long)(timeout_s * 1e9), status);
+    PK_LAUNCH_CHECK("peer_barrier_kernel");
+    return PK_OK;
+}
+
+int pk_exchange_plan(const long long* block_count, long long nb_per_rank, int n_ranks, int rank, long long Ml,
+                     long long capacity, long long* xplan, unsigned long long* status, void* stream) {
+    PK_CHECK_ARG(block_count && xplan && status, "null pointer");
+    PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    PK_CHECK_ARG(nb_per_rank > 0 && Ml > 0 && capacity >= 0, "sizes");
+    exchange_plan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(block_count, nb_per_rank, n_ranks, rank, Ml, capacity, xplan,
+                                                             status);
+    PK_LAUNCH_CHECK("exchange_plan_kernel");
+    return PK_OK;
+}
+
+int pk_exchange_plan_host(const long long* emitted_before_host, int n_ranks, int rank, long long Ml, long long capacity,
+                          long long* xplan_host) {
+    PK_CHECK_ARG(emitted_before_host && xplan_host, "null pointer");
+    PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    PK_CHECK_ARG(Ml > 0 && capacity >= 0, "sizes");
+    make_exchange_plan(emitted_before_host, n_ranks, Ml, rank, capacity, xplan_host);
+    return PK_OK;
+}
+
+int pk_push_particles(const long long* xplan, const long long* out_lo, long long Ml, int rank, const double* pose4,
+                      const int* aux2, const int* slot, const void* pool, int capacity, int dtype,
+                      const unsigned long long* peer_recv_tab, long long send_capacity, int* workspace, void* stream) {
+    PK_CHECK_ARG(xplan && out_lo && pose4 && aux2 && slot && pool && peer_recv_tab && workspace, "null pointer");
+    PK_CHECK_ARG(Ml > 0 && send_capacity >= 0 && send_capacity < (1ll << 31), "sizes");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    if (send_capacity == 0) return PK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long stride = pk_particle_record_bytes(capacity, dtype);
+    int* src_slot = workspace;
+    int* dst_idx = workspace + send_capacity;
+    int* dst_rank = workspace + 2 * send_capacity;
+    int* nlive = workspace + 3 * send_capacity;
+    long long grid = (send_capacity + 255) / 256;
+    if (grid > 4ll * num_sms()) grid = 4ll * num_sms();
+    push_headers_kernel<<<(unsigned)grid, 256, 0, st>>>(xplan, out_lo, Ml, rank, pose4, aux2, slot, peer_recv_tab, stride,
+                                                        send_capacity, src_slot, dst_idx, dst_rank, nlive);
+    PK_LAUNCH_CHECK("push_headers_kernel");
+    if (capacity > 0)
+        return copy_blocks_launch(pool, reinterpret_cast<void*>((size_t)kHeaderBytes), capacity, dtype, src_slot, dst_idx,
+                                  nlive, send_capacity, xplan + XP_N_SEND, st, 0, stride, peer_recv_tab, dst_rank);
+    return PK_OK;
+}
+
+int pk_resample_gather_peer(const long long* xplan, const long long* anc_window, const long long* out_lo,
+                            const int* offspring, long long Ml, long long particle_offset, const double* pose4_in,
+                            double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
+                            const void* recv, long long recv_capacity, void* pool, int capacity, int dtype,
+                            void* workspace, long long* total_dead_out, void* stream) {
+    PK_CHECK_ARG(xplan && anc_window && out_lo && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in &&
+                     slot_out && pool && workspace && total_dead_out && recv,
+                 "null pointer");
+    PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31) && recv_capacity >= 0, "sizes");
+    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    return gather_sharded_impl(anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
+                               pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
+                               total_dead_out, (cudaStream_t)stream);
+}
+
+/* peer memory: plain cudaMalloc allocations shared between the ranks of one node by CUDA IPC */
+int pk_peer_alloc(long long bytes, void** ptr_out) {
+    PK_CHECK_ARG(ptr_out && bytes > 0, "arguments");
+    void* p = nullptr;
+    PK_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(e, "cudaMemset(peer buffer)");
+    }
+    *ptr_out = p;
+    return PK_OK;
+}
+
+int pk_peer_free(void* ptr) {
+    if (ptr) PK_CUDA(cudaFree(ptr));
+    return PK_OK;
+}
+
+int pk_peer_export(void* ptr, unsigned char* handle_out_host) {
+    PK_CHECK_ARG(ptr && handle_out_host, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PK_PEER_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PK_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out_host, &h, sizeof(h));
+    return PK_OK;
+}
+
+int pk_peer_open(const unsigned char* handle_host, void** ptr_out) {
+    PK_CHECK_ARG(handle_host && ptr_out, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    void* p = nullptr;
+    PK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = p;
+    return PK_OK;
+}
+
+int pk_peer_close(void* ptr) {
+    if (ptr) PK_CUDA(cudaIpcCloseMemHandle(ptr));
     return PK_OK;
 }
 

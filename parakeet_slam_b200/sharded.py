@@ -13,8 +13,22 @@ unchanged on every shard.  Two steps couple particles:
   no extra count exchange;
 * ``summary()`` / ``best_particle()`` -- an all-reduce of five doubles / an all-gather of two.
 
+Two exchange engines implement that step with identical results:
+
+``exchange="peer"`` (default)  every count stays on the device.  Each rank owns one CUDA-IPC shared
+  allocation ``[flags | all block totals | receive buffer]``; the weight-scan kernel stores its block
+  totals straight into every peer's copy (a fused all-gather), a flag barrier in peer memory replaces
+  the collective's synchronisation, a one-thread kernel derives the exchange plan from the K3b
+  output, and migrating particles are pushed by this library's TMA block mover directly into the
+  destination rank's receive buffer over NVLink.  No NCCL call and no host round trip per frame, so
+  the host keeps running ahead of the GPU exactly as in the single-GPU filter.
+``exchange="nccl"``  ``all_gather`` of the block totals, one small D2H copy of the emitted-output
+  counts, ``all_to_all_single`` of the packed records.  Unbounded exchange size; the host waits for
+  the GPU once per frame.
+
 ``plan_exchange`` is the pure host-side arithmetic of the exchange; it is tested on CPU with a
-world-size-2 ``gloo`` group (``tests/test_sharding_cpu.py``).
+world-size-2 ``gloo`` group and against the device plan (``pk_exchange_plan_host``) in
+``tests/test_sharding_cpu.py``.
 """
 from __future__ import annotations
 
@@ -64,8 +78,13 @@ class ShardedFastSLAM(FastSLAM):
     """``FastSLAM`` over ``torch.distributed`` (NCCL): ``num_particles`` is the GLOBAL particle count,
     each rank holds ``num_particles / world_size`` of them (a multiple of 1024)."""
 
-    def __init__(self, preset_features=[], *, num_particles, group=None, **kw):
+    def __init__(self, preset_features=[], *, num_particles, group=None, exchange="peer", exchange_capacity=None,
+                 barrier_timeout_s=20.0, **kw):
         import torch.distributed as dist
+
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
 
         self._dist = dist
         self._group = group
@@ -88,7 +107,174 @@ class ShardedFastSLAM(FastSLAM):
         self._exchange_cap = 0
         self._send_buf = self._recv_buf = self._pack_ws = None
         self._rank_idx = torch.arange(0, G * nb + 1, nb, device=dev)
-        self.last_plan = None
+        self._last_plan = None
+        self._barrier_timeout_s = float(barrier_timeout_s)
+        self._peer = None
+        if exchange == "peer":
+            if G > _lib.PK_MAX_RANKS:
+                raise ValueError("the peer exchange serves at most %d ranks" % _lib.PK_MAX_RANKS)
+            self._setup_peer(exchange_capacity)
+
+    # -- peer memory -------------------------------------------------------------------------------
+    def _setup_peer(self, exchange_capacity):
+        """One CUDA-IPC allocation per rank: [flags 4 KiB | all block totals | receive buffer], mapped by
+        every other rank; device tables hold each region's address on every rank."""
+        torch, lib, dist = self._torch, self._lib, self._dist
+        G, me, nb, Ml, dev = self.world_size, self.rank, self._nb, self.num_particles, self._device
+        rec = self._record_bytes
+        if exchange_capacity is None:
+            # records a rank may receive per frame: the whole shard while that costs < 8 GiB
+            exchange_capacity = min(Ml, max(4096, (8 << 30) // rec))
+        cap = int(min(max(int(exchange_capacity), 1), Ml))
+        self.exchange_capacity = cap
+        off_sums = 4096
+        off_recv = off_sums + ((G * nb * 8 + 255) // 256) * 256
+        total = off_recv + cap * rec
+        with self._on_device():
+            base = ctypes.c_void_p()
+            _lib.check(lib.pk_peer_alloc(total, ctypes.byref(base)), "pk_peer_alloc")
+            handle = (ctypes.c_ubyte * _lib.PK_PEER_HANDLE_BYTES)()
+            _lib.check(lib.pk_peer_export(base, handle), "pk_peer_export")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            every = torch.zeros((G, _lib.PK_PEER_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(every.view(-1), mine, group=self._group)
+            every = every.cpu().numpy()
+            bases, opened, failure = [], [], None
+            for g in range(G):
+                if g == me:
+                    bases.append(int(base.value))
+                    continue
+                h = (ctypes.c_ubyte * _lib.PK_PEER_HANDLE_BYTES)(*[int(v) for v in every[g]])
+                p = ctypes.c_void_p()
+                if failure is None and lib.pk_peer_open(h, ctypes.byref(p)) != 0:
+                    failure = "pk_peer_open(rank %d): %s" % (g, _lib.last_error())
+                if failure is None:
+                    opened.append(p)
+                bases.append(int(p.value or 0))
+            # all ranks agree on the outcome before anyone touches peer memory
+            ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
+            if int(ok.item()) == 0:
+                for p in opened:
+                    lib.pk_peer_close(p)
+                dist.barrier(group=self._group)
+                lib.pk_peer_free(base)
+                raise _lib.ParakeetLibraryError("peer memory could not be mapped on every rank (%s); use "
+                                                "exchange='nccl'" % (failure or "another rank failed"))
+            i64 = torch.int64
+            tab = lambda off: torch.tensor([b + off for b in bases], dtype=i64, device=dev)
+            self._peer = dict(base=base, opened=opened, bases=bases, total=total,
+                              flags_tab=tab(0), sums_tab=tab(off_sums), recv_tab=tab(off_recv),
+                              sums_ptr=bases[me] + off_sums, recv_ptr=bases[me] + off_recv, epoch=0)
+            self._xplan = torch.zeros((_lib.PK_XPLAN_LONGS,), dtype=i64, device=dev)
+            self._peer_status = torch.zeros((1,), dtype=i64, device=dev)
+            self._anc_window = torch.zeros((Ml,), dtype=i64, device=dev)
+            self._send_capacity = max(1, (G - 1) * cap)   # one particle may own every output slot
+            self._push_ws = torch.zeros((4 * self._send_capacity,), dtype=torch.int32, device=dev)
+            torch.cuda.synchronize(dev)
+        dist.barrier(group=self._group)   # every mapping exists and every flag is zero before the first frame
+
+    def close(self):
+        """Unmap the peers' allocations and free this rank's (collective: call on every rank)."""
+        if self._peer is None:
+            return
+        torch, lib = self._torch, self._lib
+        with self._on_device():
+            torch.cuda.synchronize(self._device)
+            self._dist.barrier(group=self._group)
+            for p in self._peer["opened"]:
+                lib.pk_peer_close(p)
+            self._dist.barrier(group=self._group)
+            lib.pk_peer_free(self._peer["base"])
+        self._peer = None
+
+    def _barrier(self, st):
+        pr = self._peer
+        pr["epoch"] += 1
+        _lib.check(self._lib.pk_peer_barrier(_lib.ptr(pr["flags_tab"]), self.rank, self.world_size, pr["epoch"],
+                                             self._barrier_timeout_s, _lib.ptr(self._peer_status), st),
+                   "pk_peer_barrier")
+
+    def check_exchange(self):
+        """Raise if an earlier frame overflowed the exchange capacity or a peer missed a barrier (the
+        status word is sticky; reading it synchronises the stream)."""
+        if self._peer is None:
+            return
+        bits = int(self._peer_status.item())
+        if bits & _lib.PK_PEER_OVERFLOW:
+            raise _lib.ParakeetLibraryError(
+                "a resampling step had to move more than exchange_capacity=%d particles between ranks; the filter "
+                "state is void -- rebuild with a larger exchange_capacity or exchange='nccl'" % self.exchange_capacity)
+        if bits & _lib.PK_PEER_TIMEOUT:
+            raise _lib.ParakeetLibraryError("a rank did not reach a resampling barrier within %.0f s"
+                                            % self._barrier_timeout_s)
+
+    @property
+    def last_plan(self):
+        """Exchange plan of the last resampling step as a dict (peer mode: read back from the device)."""
+        if self._peer is None or self._frame == 0:
+            return self._last_plan
+        x = self._xplan.cpu().numpy()
+        G = self.world_size
+        return dict(n_lo=int(x[_lib.PK_XP_N_LO]), n_loc=int(x[_lib.PK_XP_N_LOC]), n_hi=int(x[_lib.PK_XP_N_HI]),
+                    emit_lo=int(x[_lib.PK_XP_EMIT_LO]), emit_n=int(x[_lib.PK_XP_EMIT_N]),
+                    n_below=int(x[_lib.PK_XP_N_BELOW]), n_above=int(x[_lib.PK_XP_N_ABOVE]),
+                    overflow=bool(x[_lib.PK_XP_OVERFLOW]),
+                    rank_n_lo=[int(v) for v in x[_lib.PK_XP_RANK_LO:_lib.PK_XP_RANK_LO + G]],
+                    rank_n_loc=[int(v) for v in x[_lib.PK_XP_RANK_LOC:_lib.PK_XP_RANK_LOC + G]])
+
+    def _resample_peer(self):
+        """low_variance_resample with every count on the device and both exchanges over peer memory."""
+        torch, lib, dist = self._torch, self._lib, self._dist
+        Ml, Mt, G, me, nb = self.num_particles, self.num_particles_total, self.world_size, self.rank, self._nb
+        pr = self._peer
+        with self._lock, self._on_device():
+            u01 = float(self._uniform())  # every rank must draw the same value (same seed / same source)
+            st = self._stream()
+            cur, nxt = self._cur, 1 - self._cur
+            pose_in, aux_in, slot_in = self._pose[cur], self._aux[cur], self._slot[cur]
+            status = _lib.ptr(self._peer_status)
+            # K3a + all-gather of the block totals in one kernel (stores into every rank's copy)
+            _lib.check(lib.pk_weight_scan_publish(_lib.ptr(pose_in), Ml, _lib.ptr(self._cumsum),
+                                                  _lib.ptr(self._block_sums), _lib.ptr(pr["sums_tab"]), me, G, st),
+                       "pk_weight_scan_publish")
+            self._barrier(st)
+            _lib.check(lib.pk_resample_thresholds(pr["sums_ptr"], G * nb, Mt, u01, _lib.ptr(self._plan),
+                                                  _lib.ptr(self._all_prefix), _lib.ptr(self._all_count), st),
+                       "pk_resample_thresholds")
+            _lib.check(lib.pk_exchange_plan(_lib.ptr(self._all_count), nb, G, me, Ml, self.exchange_capacity,
+                                            _lib.ptr(self._xplan), status, st), "pk_exchange_plan")
+            # ancestors of my own output window (entries owned by other ranks' particles stay untouched)
+            _lib.check(lib.pk_resample_ancestors(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
+                                                 _lib.ptr(self._plan), _lib.ptr(self._all_prefix),
+                                                 _lib.ptr(self._all_count), Mt, me * Ml, Ml,
+                                                 _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
+                                                 _lib.ptr(self._anc_window), _lib.ptr(self._big_runs), st),
+                       "pk_resample_ancestors")
+            # offspring that live on other ranks: header + landmark block straight into their receive buffers
+            _lib.check(lib.pk_push_particles(_lib.ptr(self._xplan), _lib.ptr(self._out_lo), Ml, me, _lib.ptr(pose_in),
+                                             _lib.ptr(aux_in), _lib.ptr(slot_in), _lib.ptr(self._pool), self.capacity,
+                                             self._dt, _lib.ptr(pr["recv_tab"]), self._send_capacity,
+                                             _lib.ptr(self._push_ws), st), "pk_push_particles")
+            self._barrier(st)
+            _lib.check(lib.pk_resample_gather_peer(
+                _lib.ptr(self._xplan), _lib.ptr(self._anc_window), _lib.ptr(self._out_lo), _lib.ptr(self._offspring), Ml,
+                self.particle_offset, _lib.ptr(pose_in), _lib.ptr(self._pose[nxt]), _lib.ptr(aux_in),
+                _lib.ptr(self._aux[nxt]), _lib.ptr(slot_in), _lib.ptr(self._slot[nxt]), pr["recv_ptr"],
+                self.exchange_capacity, _lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self._gather_ws),
+                _lib.ptr(self._n_copied), st), "pk_resample_gather_peer")
+            self._cur = nxt
+            if self.keep_trace:
+                # debugging / parity traces only: every rank scatters its offspring into a global list
+                anc_global = torch.zeros((Mt,), dtype=torch.int64, device=self._device)
+                _lib.check(lib.pk_resample_ancestors(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
+                                                     _lib.ptr(self._plan), _lib.ptr(self._all_prefix),
+                                                     _lib.ptr(self._all_count), Mt, 0, Mt,
+                                                     _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
+                                                     _lib.ptr(anc_global), _lib.ptr(self._big_runs), st),
+                           "pk_resample_ancestors(trace)")
+                dist.all_reduce(anc_global, group=self._group)
+                self.last_ancestors = anc_global[me * Ml:(me + 1) * Ml].clone()
 
     # noise for the parity mode: every rank draws the GLOBAL block and keeps its slice, so the
     # stream consumed is the one a single-process filter would consume
@@ -103,6 +289,9 @@ class ShardedFastSLAM(FastSLAM):
         return np.ascontiguousarray(z[lo:lo + M])
 
     def low_variance_resample(self):
+        """``FastSLAM.low_variance_resample`` (``prkt_core_v2.py:210-252``) over all shards."""
+        if self._peer is not None:
+            return self._resample_peer()
         torch, lib, dist = self._torch, self._lib, self._dist
         Ml, Mt, G, me, nb = self.num_particles, self.num_particles_total, self.world_size, self.rank, self._nb
         dev = self._device
@@ -120,7 +309,7 @@ class ShardedFastSLAM(FastSLAM):
                        "pk_resample_thresholds")
             E = self._all_count[self._rank_idx].cpu().tolist()   # outputs emitted before each rank (one small D2H)
             plan = plan_exchange(E, Ml, me)
-            self.last_plan = plan
+            self._last_plan = plan
             if plan["emit_n"] > self._emit.numel():
                 self._emit = torch.zeros((plan["emit_n"],), dtype=torch.int64, device=dev)
             # my particles' offspring: emit[k - emit_lo] = global ancestor index, ascending
@@ -187,6 +376,7 @@ class ShardedFastSLAM(FastSLAM):
                                               _lib.ptr(self._red_ws), self._stream()), "pk_summary_partial")
             dist.all_reduce(self._out5, group=self._group)
             s = self._out5.cpu().numpy()
+            self.check_exchange()
         count = float(self.num_particles_total)
         return (float(s[0] / count), float(s[1] / count), math.atan2(float(s[2]), float(s[3])),)
 
@@ -212,5 +402,7 @@ class ShardedFastSLAM(FastSLAM):
         out = dict(zip(("matched", "unmatched", "evaluated", "same_landmark", "promoted", "blocks_copied"),
                        [int(v) for v in t.cpu()]))
         out["flags"] = s["flags"]
-        out["migrated_in"] = int(self.last_plan["n_lo"] + self.last_plan["n_hi"]) if self.last_plan else 0
+        plan = self.last_plan
+        out["migrated_in"] = int(plan["n_lo"] + plan["n_hi"]) if plan else 0
+        self.check_exchange()
         return out

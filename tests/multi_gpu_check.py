@@ -39,7 +39,7 @@ def main():
         def __call__(self):
             return Time(0, self.ns)
 
-    def run(cls, dtype, **kw):
+    def run(cls, dtype, skew=False, **kw):
         clk = Clk()
         urng = random.Random(99)
         fs = cls(make_features(scn), num_particles=M, dtype=dtype, noise="philox", seed=7, uniform=urng.random,
@@ -54,6 +54,12 @@ def main():
             clk.ns += DT_NSEC
             fs.motion_update(tw)
             fs.measurement_update(scn.observations[t])
+            if skew:
+                # starve the particles of every odd rank's index range: about half of each even rank's
+                # offspring must move to a neighbour (large exchanges, both directions)
+                gidx = fs.particle_offset + torch.arange(fs.num_particles, device="cuda")
+                odd = ((gidx // Ml) + t) % 2 == 1
+                fs.pose[:, 3] *= torch.where(odd, 1e-3, 1.0).to(torch.float64)
             w = fs.pose[:, 3].clone()
             fs.low_variance_resample()
             if isinstance(fs, ShardedFastSLAM):
@@ -63,20 +69,24 @@ def main():
         return fs, out, maps, moved
 
     ok = True
-    for dtype in ("f64", "f32"):
-        fs_s, out_s, maps_s, moved = run(ShardedFastSLAM, dtype)
+    single = {}
+    for dtype, exchange, skew in (("f64", "peer", False), ("f32", "peer", False), ("f32", "peer", True),
+                                  ("f64", "nccl", False), ("f32", "nccl", True)):
+        fs_s, out_s, maps_s, moved = run(ShardedFastSLAM, dtype, skew, exchange=exchange)
         moved_t = torch.tensor([moved], device="cuda")
         dist.all_reduce(moved_t)
         # single-GPU reference on every rank (cheap at this size), compared on the rank's own slice
-        fs_1, out_1, maps_1, _ = run(FastSLAM, dtype)
+        if (dtype, skew) not in single:
+            single[(dtype, skew)] = run(FastSLAM, dtype, skew)
+        fs_1, out_1, maps_1, _ = single[(dtype, skew)]
         lo, hi = rank * Ml, (rank + 1) * Ml
         for t in range(frames):
             p_s, w_s, a_s, sum_s = out_s[t]
             p_1, w_1, a_1, sum_1 = out_1[t]
             same = (torch.equal(p_s, p_1[lo:hi]) and torch.equal(w_s, w_1[lo:hi]) and torch.equal(a_s, a_1[lo:hi]))
             if not same:
-                print("rank %d dtype %s frame %d: sharded != single (pose %s weight %s anc %s)" % (
-                    rank, dtype, t, torch.equal(p_s, p_1[lo:hi]), torch.equal(w_s, w_1[lo:hi]),
+                print("rank %d dtype %s %s skew=%s frame %d: sharded != single (pose %s weight %s anc %s)" % (
+                    rank, dtype, exchange, skew, t, torch.equal(p_s, p_1[lo:hi]), torch.equal(w_s, w_1[lo:hi]),
                     torch.equal(a_s, a_1[lo:hi])), flush=True)
                 ok = False
                 break
@@ -85,18 +95,34 @@ def main():
                 ok = False
         for name, a, b in zip(("mean", "covp", "covc", "meta", "ids", "nlive"), maps_s, maps_1):
             if not np.array_equal(a, b[lo:hi]):
-                print("rank %d dtype %s: landmark %s differs after %d frames" % (rank, dtype, name, frames), flush=True)
+                print("rank %d dtype %s %s skew=%s: landmark %s differs after %d frames" % (
+                    rank, dtype, exchange, skew, name, frames), flush=True)
                 ok = False
         b_s, b_1 = fs_s.best_particle(), fs_1.best_particle()
         if b_s != b_1:
             print("rank %d best particle differs" % rank, b_s, b_1, flush=True)
             ok = False
         if rank == 0:
-            print("dtype %s: %d particles over %d ranks, %d frames, %d particle migrations, identical=%s" % (
-                dtype, M, world, frames, int(moved_t.item()), ok), flush=True)
+            print("dtype %s exchange %s skew %s: %d particles over %d ranks, %d frames, %d particle migrations, "
+                  "identical=%s" % (dtype, exchange, skew, M, world, frames, int(moved_t.item()), ok), flush=True)
         if world > 1 and int(moved_t.item()) == 0:
             print("no particle crossed a shard boundary: the test exercised nothing", flush=True)
             ok = False
+        if skew and int(moved_t.item()) < frames * M // 8:
+            print("skewed run moved only %d particles" % int(moved_t.item()), flush=True)
+            ok = False
+        fs_s.close()
+    # a receive buffer that is too small must be reported, not overrun
+    if world > 1:
+        from parakeet_slam_b200._lib import ParakeetLibraryError
+        try:
+            fs_o, _, _, _ = run(ShardedFastSLAM, "f32", True, exchange="peer", exchange_capacity=16)
+            fs_o.check_exchange()
+            print("rank %d: exchange overflow was not reported" % rank, flush=True)
+            ok = False
+        except ParakeetLibraryError as exc:
+            if rank == 0:
+                print("overflow reported as expected:", str(exc)[:80], flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()

@@ -116,3 +116,97 @@ def test_exchange_over_gloo_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert sum(m for _, _, m in res) > 0     # some particles really crossed the shard boundary
+
+
+# ---- peer exchange: the device-resident plan (same C++ function on host and device) -------------------
+def _xplan_host(E, Ml, rank, cap):
+    import ctypes
+    from parakeet_slam_b200 import _lib
+    lib = _lib.load()
+    G = len(E) - 1
+    Ea = (ctypes.c_longlong * (G + 1))(*[int(v) for v in E])
+    out = (ctypes.c_longlong * _lib.PK_XPLAN_LONGS)()
+    _lib.check(lib.pk_exchange_plan_host(Ea, G, rank, Ml, cap, out), "pk_exchange_plan_host")
+    return np.array(list(out), dtype=np.int64)
+
+
+def _offspring_case(kind, M, rs):
+    if kind == "uniform":
+        return np.ones(M, dtype=np.int64)
+    if kind == "skewed":
+        w = rs.gamma(0.3, size=M)
+        off = np.diff(np.floor(np.concatenate([[0], np.cumsum(w)]) / w.sum() * M + rs.uniform())).astype(np.int64)
+        off[-1] += M - off.sum()
+        return off
+    off = np.zeros(M, dtype=np.int64)
+    if kind == "one_hot":
+        off[rs.randint(M)] = M
+    elif kind == "front":
+        off[:M // 4] = 4
+    elif kind == "back":
+        off[-(M // 2):] = 2
+    elif kind == "alternate_eighths":    # every other eighth of the filter dies
+        q = M // 8
+        for b in range(0, 8, 2):
+            off[b * q:(b + 1) * q] = 2
+    return off
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "one_hot", "front", "back", "alternate_eighths"])
+def test_device_plan_matches_host_plan_and_push_order(G, kind):
+    """pk_exchange_plan_host (the function the plan kernel runs) agrees with plan_exchange, and the
+    push kernel's index arithmetic -- emulated here step by step -- fills every rank's receive buffer
+    in exactly the order its output window expects."""
+    from parakeet_slam_b200 import _lib
+    rs = np.random.RandomState(G * 13 + len(kind))
+    Ml = 64
+    M = G * Ml
+    off = _offspring_case(kind, M, rs)
+    assert off.sum() == M
+    E = _emitted(off, G)
+    anc = np.repeat(np.arange(M), off)
+    out_lo_global = np.concatenate([[0], np.cumsum(off)])[:-1]
+    X = [_xplan_host(E, Ml, g, Ml) for g in range(G)]
+    recv = [dict() for _ in range(G)]
+    for g in range(G):
+        x, p = X[g], plan_exchange(E, Ml, g)
+        assert x[_lib.PK_XP_OVERFLOW] == 0
+        assert (x[_lib.PK_XP_N_LO], x[_lib.PK_XP_N_LOC], x[_lib.PK_XP_N_HI]) == (p["n_lo"], p["n_loc"], p["n_hi"])
+        assert (x[_lib.PK_XP_EMIT_LO], x[_lib.PK_XP_EMIT_N]) == (p["emit_lo"], p["emit_n"])
+        assert x[_lib.PK_XP_N_BELOW] == sum(p["send"][:g]) and x[_lib.PK_XP_N_ABOVE] == sum(p["send"][g + 1:])
+        assert x[_lib.PK_XP_N_SEND] == sum(p["send"]) - p["send"][g] and x[_lib.PK_XP_N_IN] == Ml - p["n_loc"]
+        for h in range(G):
+            ph = plan_exchange(E, Ml, h)
+            assert x[_lib.PK_XP_RANK_LO + h] == ph["n_lo"] and x[_lib.PK_XP_RANK_LOC + h] == ph["n_loc"]
+        # push_headers_kernel, one send item at a time
+        out_lo = out_lo_global[g * Ml:(g + 1) * Ml]
+        for j in range(int(x[_lib.PK_XP_N_SEND])):
+            nb_ = int(x[_lib.PK_XP_N_BELOW])
+            k = int(x[_lib.PK_XP_EMIT_LO]) + j if j < nb_ else int(x[_lib.PK_XP_ABOVE_START]) + (j - nb_)
+            a = int(np.searchsorted(out_lo, k, side="right")) - 1           # upper_bound - 1
+            h = k // Ml
+            assert h != g
+            k_local = k - h * Ml
+            r = k_local if h > g else k_local - int(x[_lib.PK_XP_RANK_LOC + h])
+            assert r not in recv[h]
+            recv[h][r] = g * Ml + a
+    for h in range(G):
+        win = anc[h * Ml:(h + 1) * Ml]
+        foreign = win[(win < h * Ml) | (win >= (h + 1) * Ml)]
+        assert sorted(recv[h]) == list(range(len(foreign)))
+        assert np.array_equal(np.array([recv[h][r] for r in range(len(foreign))], dtype=np.int64), foreign)
+
+
+def test_device_plan_flags_overflow():
+    from parakeet_slam_b200 import _lib
+    Ml, G = 64, 4
+    off = _offspring_case("front", G * Ml, np.random.RandomState(0))
+    E = _emitted(off, G)
+    need = max(Ml - plan_exchange(E, Ml, g)["n_loc"] for g in range(G))
+    assert need > 8
+    for g in range(G):
+        x = _xplan_host(E, Ml, g, 8)
+        assert x[_lib.PK_XP_OVERFLOW] == 1 and x[_lib.PK_XP_N_SEND] == 0 and x[_lib.PK_XP_N_IN] == 0
+        assert _xplan_host(E, Ml, g, need)[_lib.PK_XP_OVERFLOW] in (0, 1)
+    assert all(_xplan_host(E, Ml, g, Ml)[_lib.PK_XP_OVERFLOW] == 0 for g in range(G))
