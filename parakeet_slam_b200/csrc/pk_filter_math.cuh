@@ -91,13 +91,41 @@ __device__ __forceinline__ double pk_atan2(double y, double x) {
 constexpr double kLog2Pi = 1.8378770664093453;  // math.log(2*pi)
 
 // ---------------------------------------------------------------------------------------------
-// probability_of_match, exact fp64 (reference :383-455 with :457-544 inlined).
+// probability_of_match, exact fp64 (reference :383-455 with :457-544 inlined), in two halves:
+// match_prepare does the gates and the two Mahalanobis forms, match_finish the log / exp tail.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double match_likelihood(const Landmark& L, double px, double py, double pth, double beta,
-                                                   double orr, double og, double ob, double dirx, double diry,
-                                                   const pk_params& prm, unsigned& flags, double& pse_out) {
+// PK_MATCH_SKIP selects how a sole candidate is decided (all variants give identical results):
+//   0  always evaluate the full likelihood;
+//   1  prove positivity from the determinants' and forms' ranges (skips both logs and both exps);
+//   2  evaluate both pdf exponents (logs overlap with the bearing chain), skip only the exps.
+#ifndef PK_MATCH_SKIP
+#define PK_MATCH_SKIP 2
+#endif
+
+struct MatchPre {
+#if PK_MATCH_SKIP == 2
+    double a2, a3;  // exponents of the position / colour pdf
+#else
+    double maha2, det2, maha3, det3;
+#endif
+    double pse;
+    bool gated;
+    // `sure`: the likelihood is PROVABLY a positive, finite, normal double, so a caller that only needs
+    // the reference's match / no-match decision (`probability > 0.0`, :369-381) may skip match_finish.
+    // Proof (variant 2): a2, a3 in (-700, 700) keep bp = e^a2 and cp = e^a3, and 500*bp, 500*cp, inside the
+    // normal range; -700 < a2 + a3 < 690 keeps (500 bp)(500 cp) = 250000 e^(a2+a3) and its quotient by
+    // 250000 normal and finite -- nothing underflows to zero or overflows whatever the last-bit
+    // rounding of exp.  (Variant 1: det in (1e-100, 1e100) => |log det| < 230.3 and |maha| < 400 put both
+    // exponents inside (-318, 314), same conclusion.)
+    bool sure;
+};
+
+__device__ __forceinline__ MatchPre match_prepare(const Landmark& L, double px, double py, double pth, double beta,
+                                                  double orr, double og, double ob, double dirx, double diry,
+                                                  const pk_params& prm, unsigned& flags) {
     // Written without early exits: candidates that reach this point almost always pass the gates, and
-    // one straight-line block lets the independent chains (bearing, position pdf, colour pdf) overlap.
+    // one straight-line block lets the independent chains (bearing, position form, colour form) overlap.
+    MatchPre m;
     // colour gate :425-427, :441
     const double dr = orr - L.r, dg = og - L.g, db = ob - L.b;
     const double cdist = dr * dr + dg * dg + db * db;
@@ -105,7 +133,7 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
     // bearing gate :408-415, :433
     const double dx = L.x - px, dy = L.y - py;
     const double pse = pk_atan2(dy, dx);
-    pse_out = pse;
+    m.pse = pse;
     const double del = beta - (pse - pth);
     gated = gated || (fabs(del) > prm.bearing_gate);
     // prob_position_match :473-475 (robot-frame bearing used as if world frame, finding F4c)
@@ -119,7 +147,6 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
     const double a = L.sp[0], b10 = L.sp[2], d = L.sp[3];
     const double det2 = a * d - b10 * b10;
     const double maha2 = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det2;
-    const double bp = pk_exp(-0.5 * (2.0 * kLog2Pi + log(det2) + maha2));
     // 3-D colour pdf :530-544, lower triangle
     const double A = L.sc[0], B = L.sc[3], C = L.sc[6], D = L.sc[4], E = L.sc[7], F = L.sc[8];
     const double c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
@@ -127,11 +154,44 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
     const double det3 = A * c00 + B * c01 + C * c02;
     const double maha3 =
         (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0 * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
-    const double cp = pk_exp(-0.5 * (3.0 * kLog2Pi + log(det3) + maha3));
     if (!gated && (!(det2 > 0.0) || !(det3 > 0.0))) flags |= PK_FLAG_SINGULAR_COV;
+    m.gated = gated;
+#if PK_MATCH_SKIP == 2
+    m.a2 = -0.5 * (2.0 * kLog2Pi + log(det2) + maha2);
+    m.a3 = -0.5 * (3.0 * kLog2Pi + log(det3) + maha3);
+    const double a23 = m.a2 + m.a3;
+    m.sure = !gated && (m.a2 > -700.0) && (m.a2 < 700.0) && (m.a3 > -700.0) && (m.a3 < 700.0) && (a23 > -700.0) &&
+             (a23 < 690.0);
+#else
+    m.det2 = det2;
+    m.maha2 = maha2;
+    m.det3 = det3;
+    m.maha3 = maha3;
+    m.sure = (PK_MATCH_SKIP == 1) && !gated && (det2 > 1e-100) && (det2 < 1e100) && (det3 > 1e-100) && (det3 < 1e100) &&
+             (fabs(maha2) < 400.0) && (fabs(maha3) < 400.0);
+#endif
+    return m;
+}
+
+__device__ __forceinline__ double match_finish(const MatchPre& m) {
+#if PK_MATCH_SKIP == 2
+    const double bp = pk_exp(m.a2);
+    const double cp = pk_exp(m.a3);
+#else
+    const double bp = pk_exp(-0.5 * (2.0 * kLog2Pi + log(m.det2) + m.maha2));
+    const double cp = pk_exp(-0.5 * (3.0 * kLog2Pi + log(m.det3) + m.maha3));
+#endif
     // :439, :446, :455
     const double Lk = (500.0 * bp) * (500.0 * cp) / 250000.0;
-    return gated ? 0.0 : Lk;
+    return m.gated ? 0.0 : Lk;
+}
+
+__device__ __forceinline__ double match_likelihood(const Landmark& L, double px, double py, double pth, double beta,
+                                                   double orr, double og, double ob, double dirx, double diry,
+                                                   const pk_params& prm, unsigned& flags, double& pse_out) {
+    const MatchPre m = match_prepare(L, px, py, pth, beta, orr, og, ob, dirx, diry, prm, flags);
+    pse_out = m.pse;
+    return match_finish(m);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -318,21 +318,49 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const int cnt = act ? H[r].cnt : 0;
             // match_one :353-381: arg-max, strict '>' from 0.0, first (lowest slot) maximum wins
             double best = 0.0, pse = 0.0;
+            MatchPre pre;
+            pre.sure = false;
             best_pse = 0.0;
             bestj = -1;
             lastj = -1;
             if (cnt > 0) {
                 load_staged<T>(s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)w) * kRecBytes, L);
                 lastj = H[r].c0;
-                const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r],
-                                                   ob_dy[r], A.prm, st_flags, pse);
+                pre = match_prepare(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r], ob_dy[r], A.prm,
+                                    st_flags);
+                pse = pre.pse;
                 st_eval += 1;
+            }
+            // An item with a single colour-compatible landmark only needs the reference's decision
+            // `probability > 0.0` (:369-381), and match_prepare can usually PROVE it without the two logs
+            // and two exps of the pdf tails (MatchPre::sure).  The value itself is needed only to rank
+            // several candidates, or when the product may underflow (finding F3) -- a warp-uniform branch.
+#if PK_MATCH_SKIP == 0
+            if (cnt > 0) {
+                const double Lk = match_finish(pre);
                 if (Lk > 0.0) {
                     best = Lk;
                     bestj = lastj;
                     best_pse = pse;
                 }
             }
+#else
+            const bool need_value = cnt > 1 || (cnt == 1 && !pre.sure);
+            if (__any_sync(kFull, need_value)) {
+                if (cnt > 0) {
+                    const double Lk = match_finish(pre);
+                    if (Lk > 0.0) {
+                        best = Lk;
+                        bestj = lastj;
+                        best_pse = pse;
+                    }
+                }
+            } else if (cnt > 0) {
+                best = 1.0;  // some positive value: never compared against anything
+                bestj = lastj;
+                best_pse = pse;
+            }
+#endif
             if (__any_sync(kFull, cnt > 1)) {
                 if (cnt <= kMaxHits) {  // further colour-compatible landmarks, in slot order
                     const int maxcnt = __reduce_max_sync(kFull, cnt <= kMaxHits ? cnt : 0);

@@ -103,7 +103,7 @@ __device__ __forceinline__ long long count_le(dd P, double c, double u0, double 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_total, double u01,
-                  double* __restrict__ plan, double* __restrict__ block_prefix, long long* __restrict__ block_count) {
+                  double* __restrict__ plan, double* block_prefix, long long* block_count) {
     __shared__ double g_hi[kMaxScanGroups], g_lo[kMaxScanGroups];
     __shared__ long long g_cnt[kMaxScanGroups];
     __shared__ double s_r, s_u0;
@@ -112,12 +112,24 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
     const long long b0 = (long long)t * kGroupBlocks;
     const long long b1 = min(nb, b0 + kGroupBlocks);
     // phase A: per-thread sequential double-double fold of its group's block totals
+    // (loads are issued eight at a time so the fold does not pay one L2 round trip per block)
+    constexpr int kBatch = 8;
+    static_assert(kGroupBlocks % kBatch == 0, "batch size");
     dd acc{0.0, 0.0};
     if (t < ngroups) {
-        for (long long b = b0; b < b1; ++b) {
-            block_prefix[2 * b] = acc.hi;  // local exclusive prefix for now
-            block_prefix[2 * b + 1] = acc.lo;
-            acc = dd_add_d(acc, sums[b]);
+        for (long long bb = b0; bb < b1; bb += kBatch) {
+            double v[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) v[j] = (bb + j < b1) ? sums[bb + j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const long long b = bb + j;
+                if (b < b1) {
+                    block_prefix[2 * b] = acc.hi;  // local exclusive prefix for now
+                    block_prefix[2 * b + 1] = acc.lo;
+                    acc = dd_add_d(acc, v[j]);
+                }
+            }
         }
         g_hi[t] = acc.hi;
         g_lo[t] = acc.lo;
@@ -167,13 +179,27 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
     long long runmax = 0;
     if (t < ngroups) {
         const dd gb{g_hi[t], g_lo[t]};
-        for (long long b = b0; b < b1; ++b) {
-            const dd P = dd_add(gb, dd{block_prefix[2 * b], block_prefix[2 * b + 1]});
-            block_prefix[2 * b] = P.hi;
-            block_prefix[2 * b + 1] = P.lo;
-            const long long e = count_le(P, sums[b], u0, r, M_total);
-            runmax = max(runmax, e);
-            block_count[b + 1] = runmax;  // local running max for now
+        for (long long bb = b0; bb < b1; bb += kBatch) {
+            double ph[kBatch], pl[kBatch], sv[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const bool in = bb + j < b1;
+                ph[j] = in ? block_prefix[2 * (bb + j)] : 0.0;
+                pl[j] = in ? block_prefix[2 * (bb + j) + 1] : 0.0;
+                sv[j] = in ? sums[bb + j] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const long long b = bb + j;
+                if (b < b1) {
+                    const dd P = dd_add(gb, dd{ph[j], pl[j]});
+                    block_prefix[2 * b] = P.hi;
+                    block_prefix[2 * b + 1] = P.lo;
+                    const long long e = count_le(P, sv[j], u0, r, M_total);
+                    runmax = max(runmax, e);
+                    block_count[b + 1] = runmax;  // local running max for now
+                }
+            }
         }
         g_cnt[t] = runmax;
     }
@@ -199,10 +225,19 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
     __syncthreads();
     if (t < ngroups) {
         const long long gbase = g_cnt[t];
-        for (long long b = b0; b < b1; ++b) {
-            long long v = max(block_count[b + 1], gbase);
-            if (b == nb - 1) v = M_total;  // every output slot is assigned
-            block_count[b + 1] = v;
+        for (long long bb = b0; bb < b1; bb += kBatch) {
+            long long c[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) c[j] = (bb + j < b1) ? block_count[bb + j + 1] : 0;
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const long long b = bb + j;
+                if (b < b1) {
+                    long long v = max(c[j], gbase);
+                    if (b == nb - 1) v = M_total;  // every output slot is assigned
+                    block_count[b + 1] = v;
+                }
+            }
         }
     }
 }
