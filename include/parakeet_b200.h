@@ -54,6 +54,13 @@ extern "C" {
 #define PK_DTYPE_F32 0   /* landmark storage fp32 (arithmetic is fp64 either way) */
 #define PK_DTYPE_F64 1   /* landmark storage fp64: the parity instantiation */
 
+/* Spawn mode: every `dtype` argument is a layout code -- the storage type in the low
+ * byte and the number of orphan-reading slots per particle above it.  The orphan region
+ * [64-byte header: int total | n x 64-byte readings: double x, y, cos(ray), sin(ray), r, g, b, id]
+ * follows the cold region inside the particle's block and travels with it. */
+#define PK_MAX_ORPHANS 1024
+#define PK_DTYPE_WITH_ORPHANS(base, n) ((base) | ((n) << 8))
+
 #define PK_MAX_OBS 64        /* blobs per frame handled by one pk_measurement_update */
 #define PK_SCAN_BLOCK 1024   /* particles per weight-scan block (fixed: results must not depend on the shard count) */
 
@@ -68,6 +75,8 @@ extern "C" {
 #define PK_STAT_FLAGS 3          /* OR of PK_FLAG_* */
 #define PK_STAT_SAME_LANDMARK 4  /* updates that had to wait for an earlier blob on the same landmark */
 #define PK_STAT_PROMOTED 5       /* potential -> full promotions (prkt_core_v2.py:114-118) */
+#define PK_STAT_SPAWNED 6        /* potential landmarks created by pk_spawn_update (add_new_feature :653-680) */
+#define PK_STAT_ORPHANED 7       /* readings stored by pk_spawn_update (add_orphaned_reading :740-746) */
 #define PK_NUM_STATS 8
 
 /* peer (NVLink) exchange of the sharded filter */
@@ -95,6 +104,11 @@ extern "C" {
 #define PK_FLAG_NONFINITE_WEIGHT 2u  /* a particle weight became NaN/Inf */
 #define PK_FLAG_REPROMOTED 4u        /* a blob hit a landmark promoted earlier in the same frame
                                         (the reference raises KeyError there, prkt_core_v2.py:98,312) */
+#define PK_FLAG_MAP_FULL 8u          /* spawn mode: a new landmark did not fit the particle's capacity (dropped) */
+#define PK_FLAG_ORPHAN_EXPIRED 16u   /* spawn mode: the orphan ring overwrote its oldest reading (the reference
+                                        keeps every reading for ever; a reported deviation) */
+#define PK_FLAG_SPAWN_DEGENERATE 32u /* spawn mode: cross_readings found parallel rays (the reference raises
+                                        TypeError there, prkt_core_v2.py:665-667, 735-736); reading orphaned */
 
 /* Literals of the reference, gathered in one struct (SURVEY.md section 5 "Config / flags"). */
 typedef struct pk_params {
@@ -159,6 +173,23 @@ int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool,
                           int dtype, long long M, const double* obs_host, int K,
                           const pk_params* params, int* assoc, unsigned long long* stats,
                           void* stream);
+
+/* ---- K2b spawn mode: FilterParticle.add_hypothesis for every unseen blob (id 0) of the frame, in scan
+ *      order: find_nearest_reading / reading_distance_function / ray_intersect / color_distance
+ *      (prkt_core_v2.py:546-651), add_new_feature + cross_readings (:653-738) or
+ *      add_orphaned_reading (:740-746).  As WRITTEN this path is dead code (SURVEY.md finding F5); this
+ *      entry point implements the reference with the three documented patches of SURVEY.md A.6
+ *      (oracle/ref_shim.apply_spawn_patches), i.e. the behaviour the docstrings describe.  Call after
+ *      pk_measurement_update (which already applied the 0.1 weight factor and the next_id bump of the
+ *      unseen blobs, :95, :745-746) with the same obs_host and the assoc it wrote.  dtype must carry an
+ *      orphan-slot count.  pair_gate: largest colour distance that still pairs two readings. */
+int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool, int capacity,
+                    int dtype, long long M, const double* obs_host, int K, const int* assoc,
+                    double pair_gate, unsigned long long* stats, void* stream);
+/* Orphan readings of particles [p_lo, p_lo+count): totals[count] (readings ever stored) and
+ * readings[count][slots][8] doubles in ring order (tests, FilterParticle.hypothesis_set views). */
+int pk_orphans_export(const void* pool, int capacity, int dtype, const int* slot, long long p_lo,
+                      long long count, int* totals, double* readings, void* stream);
 
 /* ---- K3/K4 weight normaliser + systematic resampling plan:
  *      FastSLAM.low_variance_resample (prkt_core_v2.py:210-252) ------------------------------- */

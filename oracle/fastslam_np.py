@@ -70,7 +70,12 @@ class OracleState(object):
         self.live = np.zeros((M, N), dtype=bool)
         self.potential = np.zeros((M, N), dtype=bool)     # lives in potential_features, id = -(slot+1)  :287
         self.next_id = np.ones(M, dtype=np.int64)         # :292
+        self.ids = np.zeros((M, N), dtype=np.int64)       # |reference id| of each slot (0 = empty)
+        # spawn mode: hypothesis_set of every particle, insertion order,
+        # entries (id, x, y, heading + bearing, r, g, b)   :291, :745
+        self.orphans = [[] for _ in range(M)]
         if n:
+            self.ids[:, :n] = np.arange(1, n + 1)[None]
             self.mean[:, :n] = np.asarray(landmarks, dtype=np.float64)[None]
             self.cov[:, :n] = (np.identity(5) * preset_covar)[None, None]
             self.immutable[:, :n] = bool(immutable)
@@ -84,7 +89,7 @@ class OracleState(object):
     def copy(self):
         out = OracleState.__new__(OracleState)
         for k, v in self.__dict__.items():
-            setattr(out, k, v.copy())
+            setattr(out, k, [list(o) for o in v] if k == "orphans" else v.copy())
         return out
 
 
@@ -149,8 +154,8 @@ def obs_direction(bearing):
 def _pdf2_lower(ex, ey, a, b10, d):
     """2-D normal pdf, covariance [[a, b10],[b10, d]] (lower triangle), SciPy formula."""
     det = a * d - b10 * b10
-    maha = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det
     with np.errstate(invalid="ignore", divide="ignore"):
+        maha = (d * ex * ex - 2.0 * b10 * ex * ey + a * ey * ey) / det
         return np.exp(-0.5 * (2 * LOG_2PI + np.log(det) + maha))
 
 
@@ -166,9 +171,9 @@ def _pdf3_lower(e0, e1, e2, C):
     c12 = b * c - a * e
     c22 = a * d - b * b
     det = a * c00 + b * c01 + c * c02
-    maha = (c00 * e0 * e0 + c11 * e1 * e1 + c22 * e2 * e2
-            + 2.0 * (c01 * e0 * e1 + c02 * e0 * e2 + c12 * e1 * e2)) / det
     with np.errstate(invalid="ignore", divide="ignore"):
+        maha = (c00 * e0 * e0 + c11 * e1 * e1 + c22 * e2 * e2
+                + 2.0 * (c01 * e0 * e1 + c02 * e0 * e2 + c12 * e1 * e2)) / det
         return np.exp(-0.5 * (3 * LOG_2PI + np.log(det) + maha))
 
 
@@ -225,25 +230,120 @@ def associate(state: OracleState, obs):
     L = np.where(np.isnan(L), 0.0, L)   # ``nan > max`` is False in the reference loop
     best = np.argmax(L, axis=2)          # first occurrence of the maximum
     best_val = np.take_along_axis(L, best[:, :, None], axis=2)[:, :, 0]
-    ids = np.where(best_val > 0.0, best + 1, 0)
+    ids = np.where(best_val > 0.0, np.take_along_axis(state.ids, best, axis=1), 0)
     # potential features carry negative ids (:336, :367); with full features in the lower slots the slot
     # order is the reference's iteration order (feature_set first, then potential_features)
     pot = np.take_along_axis(state.potential, best, axis=1)
     ids = np.where(pot, -ids, ids)
+    state.last_best_slot = best
     return ids.astype(np.int32), best_val
 
 
 # --------------------------------------------------------------------------------------
 # EKF update + importance weight  (prkt_core_v2.py:88-124, 748-849, 897-930)
 # --------------------------------------------------------------------------------------
-def measurement_update(state: OracleState, obs, ids=None):
+# --------------------------------------------------------------------------------------
+# Spawn mode  (prkt_core_v2.py:546-746 with the patches P1-P3 of SURVEY.md A.6, i.e. what
+# oracle/ref_shim.apply_spawn_patches makes the reference execute)
+# --------------------------------------------------------------------------------------
+PAIR_GATE = 300.0 ** 0.5
+
+
+def ray_intersect(x1, y1, b1, x3, y3, b3):
+    """``ray_intersect`` (``:610-640``), operation for operation."""
+    as_ = (x1, y1)
+    ad_ = (math.cos(b1), math.sin(b1))
+    bs_ = (x3, y3)
+    bd_ = (math.cos(b3), math.sin(b3))
+    if (ad_[1] * bd_[0] - ad_[0] * bd_[1]) == 0:
+        return False
+    v = ((ad_[0] * bs_[1] - ad_[1] * bs_[0] + ad_[1] * as_[0] - ad_[0] * as_[1]) /
+         (ad_[1] * bd_[0] - ad_[0] * bd_[1]))
+    if abs(ad_[1]) < abs(ad_[0]):
+        u = (bs_[0] + bd_[0] * v - as_[0]) / (ad_[0])
+    else:
+        u = (bs_[1] + bd_[1] * v - as_[1]) / (ad_[1])
+    return u >= 0 and v >= 0
+
+
+def cross_readings(x1, y1, h1, x3, y3, h3):
+    """``cross_readings`` (``:682-738``): line-line intersection; ``None`` for parallel lines."""
+    x2 = x1 + math.cos(h1)
+    y2 = y1 + math.sin(h1)
+    x4 = x3 + math.cos(h3)
+    y4 = y3 + math.sin(h3)
+    t0 = x1 * y2 - y1 * x2
+    t1 = x3 - x4
+    t2 = x1 - x2
+    t3 = x3 * y4 - x4 * y3
+    t5 = y3 - y4
+    t6 = y1 - y2
+    den = t2 * t5 - t6 * t1
+    if den == 0:
+        return None
+    return ((t0 * t1 - t2 * t3) / den, (t0 * t5 - t6 * t3) / den)
+
+
+def add_hypothesis(state: OracleState, i, blob, gate=PAIR_GATE, orphan_capacity=None, flags=None):
+    """``add_hypothesis`` (``:546-563``) for particle ``i`` and one unseen blob (bearing, r, g, b).
+    Returns "spawned" or "orphaned"."""
+    x, y, th = (float(v) for v in state.pose[i])
+    beta, r, g, b = (float(v) for v in blob)
+    ang = beta + th                                               # :603
+    # find_nearest_reading (P1): hypothesis_set in insertion order, strict '<'
+    min_d, min_o = float("inf"), None
+    for o in state.orphans[i]:
+        _, ox, oy, oang, orr, og, ob = o
+        if ray_intersect(ox, oy, oang, x, y, ang):                # :605
+            d = math.sqrt(math.pow(orr - r, 2) + math.pow(og - g, 2) + math.pow(ob - b, 2))   # :642-651
+        else:
+            d = float("inf")
+        if d < min_d:
+            min_d, min_o = d, o
+    new_id = int(state.next_id[i])
+    if min_o is not None and min_d <= gate:
+        # add_new_feature :653-680
+        _, ox, oy, oang, orr, og, ob = min_o
+        inter = cross_readings(ox, oy, oang, x, y, ang)
+        if inter is not None:
+            live = state.live[i]
+            n_live = int(live.sum())
+            state.next_id[i] += 1                                 # :680
+            if n_live >= live.shape[0]:
+                if flags is not None:
+                    flags.add("map_full")
+                return "dropped"
+            j = n_live
+            state.mean[i, j] = (inter[0], inter[1], (orr + r) / 2, (og + g) / 2, (ob + b) / 2)
+            state.cov[i, j] = np.identity(5)
+            state.count[i, j] = 0
+            state.immutable[i, j] = False
+            state.live[i, j] = True
+            state.potential[i, j] = True                          # potential_features[-new_id] :679
+            state.ids[i, j] = new_id
+            return "spawned"
+        if flags is not None:
+            flags.add("degenerate")   # the reference raises TypeError here (:665-667)
+    # add_orphaned_reading :740-746 (P2: the pose is copied)
+    state.orphans[i].append((new_id, x, y, ang, r, g, b))
+    if orphan_capacity is not None and len(state.orphans[i]) > orphan_capacity:
+        state.orphans[i].pop(0)      # ring of the device build (reported deviation)
+        if flags is not None:
+            flags.add("expired")
+    state.next_id[i] += 1
+    return "orphaned"
+
+
+def measurement_update(state: OracleState, obs, ids=None, spawn=False, gate=PAIR_GATE, orphan_capacity=None):
     """One frame of ``cam_cb``'s per-particle body after the motion update: weights <- 1
     (``:73``), association of all blobs against the pre-update map (``:84``), then the K
     sequential updates in scan order (``:88-124``).  Mutates ``state``; returns ids [M,K]."""
     M = state.num_particles
     K = obs.shape[0]
+    slots = None
     if ids is None:
         ids, _ = associate(state, obs)
+        slots = state.last_best_slot
     state.weight = np.ones(M)
     Qt = np.identity(4) * QT_DIAG
     I5 = np.identity(5)
@@ -252,12 +352,16 @@ def measurement_update(state: OracleState, obs, ids=None):
         idk = ids[:, k]
         un = idk == 0
         # unseen blob: add_hypothesis -> add_orphaned_reading (:92-95, :546-563, :740-746)
-        state.next_id[un] += 1
+        if spawn:
+            for i in np.nonzero(un)[0]:
+                add_hypothesis(state, int(i), obs[k], gate=gate, orphan_capacity=orphan_capacity)
+        else:
+            state.next_id[un] += 1
         factor = np.full(M, NO_MATCH_WEIGHT)            # :95, :851-857
         m = ~un
         if m.any():
             r = rows[m]
-            j = np.abs(idk[m]) - 1
+            j = (np.abs(idk[m]) - 1) if slots is None else slots[m, k]
             mu = state.mean[r, j]                       # [m,5]
             Sg = state.cov[r, j]                        # [m,5,5]
             px = state.pose[r, 0]
@@ -343,8 +447,9 @@ def resample_searchsorted(weight, u01):
 
 def apply_ancestors(state: OracleState, anc):
     """``temp_particles.append(deepcopy(particle))`` (``:243``) for every ancestor."""
-    for name in ("pose", "weight", "mean", "cov", "count", "immutable", "live", "potential", "next_id"):
+    for name in ("pose", "weight", "mean", "cov", "count", "immutable", "live", "potential", "next_id", "ids"):
         setattr(state, name, getattr(state, name)[anc].copy())
+    state.orphans = [list(state.orphans[int(a)]) for a in anc]
 
 
 # --------------------------------------------------------------------------------------
@@ -363,12 +468,12 @@ def summary(pose):
 # --------------------------------------------------------------------------------------
 # One full frame  (cam_cb :59-137)
 # --------------------------------------------------------------------------------------
-def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=None):
+def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=None, spawn=False, orphan_capacity=None):
     """motion (``:75-77``) -> association + updates (``:84-124``) -> resample (``:137``).
     Returns (ids [M,K], pre-resample weights [M], ancestors [M], pose_pre [M,3])."""
     state.pose = motion_update(state.pose, noise, v, w, dt)
     pose_pre = state.pose.copy()
-    ids = measurement_update(state, obs)
+    ids = measurement_update(state, obs, spawn=spawn, orphan_capacity=orphan_capacity)
     wgt = state.weight.copy()
     if sequential_resample is None:
         sequential_resample = state.num_particles <= 4096
@@ -379,13 +484,15 @@ def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=Non
     return ids, wgt, anc, pose_pre
 
 
-def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), chunk=None, potential_slots=()):
+def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), chunk=None, potential_slots=(),
+                 spawn=False, known_map=True, capacity=None, orphan_capacity=None):
     """Run the restatement over a ``Scenario`` (same trace layout as
     ``oracle.ref_driver.run_reference``)."""
     T = scn.frames if frames is None else frames
     M = scn.num_particles if num_particles is None else num_particles
     K = scn.obs_per_frame
-    st = OracleState(M, scn.landmarks, preset_covar=scn.preset_covar, immutable=scn.immutable)
+    st = OracleState(M, scn.landmarks if known_map else None, preset_covar=scn.preset_covar, immutable=scn.immutable,
+                     capacity=capacity)
     for j in potential_slots:
         st.potential[:, j] = True
     trace = dict(pose_pre=np.zeros((T, M, 3)), pose_post=np.zeros((T, M, 3)),
@@ -396,7 +503,7 @@ def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), c
     for t in range(T):
         noise = next(stream)
         ids, wgt, anc, pose_pre = frame(st, scn.observations[t], noise, scn.v, scn.w, scn.dt,
-                                        float(scn.u01[t]))
+                                        float(scn.u01[t]), spawn=spawn, orphan_capacity=orphan_capacity)
         trace["assoc"][t] = ids
         trace["weight"][t] = wgt
         trace["ancestors"][t] = anc
@@ -409,5 +516,7 @@ def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), c
             trace["lm_cov"][t] = st.cov.copy()
             trace["lm_count"][t] = st.count.copy()
             trace.setdefault("lm_potential", {})[t] = st.potential.copy()
+            trace.setdefault("lm_ids", {})[t] = np.where(st.potential, -st.ids, st.ids) * st.live
+            trace.setdefault("orphans", {})[t] = [list(o) for o in st.orphans]
     trace["state"] = st
     return trace

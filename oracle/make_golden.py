@@ -68,6 +68,65 @@ def trace_fixture(name, scn, frames, checkpoints, spawn=False, known_map=True, p
         path, os.path.getsize(path) / 1024.0, float((tr["assoc"] == 0).mean()), worst_cross))
 
 
+def spawn_arrays(spawn_state, n_max, o_max):
+    """Pack ``ref_driver.spawn_state`` into arrays: landmarks sorted by |id| (signed ids, 0 padded),
+    orphaned readings in insertion order."""
+    M = len(spawn_state)
+    ids = np.zeros((M, n_max), dtype=np.int32)
+    mean = np.zeros((M, n_max, 5))
+    cov = np.zeros((M, n_max, 5, 5))
+    cnt = np.zeros((M, n_max), dtype=np.int32)
+    north = np.zeros(M, dtype=np.int32)
+    orph = np.zeros((M, o_max, 7))
+    for i, ps in enumerate(spawn_state):
+        for j, id_ in enumerate(sorted(ps["landmarks"], key=abs)):
+            m, c, n = ps["landmarks"][id_]
+            ids[i, j], mean[i, j], cov[i, j], cnt[i, j] = id_, m, c, n
+        north[i] = len(ps["orphans"])
+        for j, o in enumerate(ps["orphans"]):
+            orph[i, j] = o
+    return ids, mean, cov, cnt, north, orph
+
+
+def spawn_fixture(name, scn, frames, checkpoints):
+    """Unknown-map run of the reference with the three spawn patches of SURVEY.md A.6
+    (``ref_shim.apply_spawn_patches``): new potential landmarks, promotion, orphaned readings."""
+    tr = ref_driver.run_reference(scn, frames=frames, record_landmarks_at=checkpoints, spawn=True, known_map=False)
+    n_max = max(len(ps["landmarks"]) for t in checkpoints for ps in tr["spawn_state"][t])
+    o_max = max(len(ps["orphans"]) for t in checkpoints for ps in tr["spawn_state"][t])
+    out = dict(
+        scenario=np.array([scn.name]), trajectory=np.array([scn.meta["trajectory"]]),
+        num_particles=scn.num_particles, num_landmarks=scn.num_landmarks,
+        obs_per_frame=scn.obs_per_frame, frames=frames, v=scn.v, w=scn.w, dt=scn.dt,
+        immutable=scn.immutable, preset_covar=scn.preset_covar,
+        landmarks=scn.landmarks, observations=scn.observations[:frames], u01=scn.u01[:frames],
+        motion_seed=scn.motion_seed,
+        pose_pre=tr["pose_pre"], pose_post=tr["pose_post"], assoc=tr["assoc"].astype(np.int16),
+        weight=tr["weight"], ancestors=tr["ancestors"].astype(np.int32), summary=tr["summary"],
+        next_id=tr["next_id"].astype(np.int32), checkpoints=np.asarray(checkpoints),
+        pair_gate=300.0 ** 0.5, n_max=n_max, o_max=o_max,
+    )
+    worst_cross = 0.0
+    for t in checkpoints:
+        ids, mean, cov, cnt, north, orph = spawn_arrays(tr["spawn_state"][t], n_max, max(o_max, 1))
+        cp, cc, cross = _blockdiag_parts(cov)
+        worst_cross = max(worst_cross, cross)
+        out["sp_ids_%d" % t] = ids
+        out["sp_mean_%d" % t] = mean
+        out["sp_covp_%d" % t] = cp
+        out["sp_covc_%d" % t] = cc
+        out["sp_count_%d" % t] = cnt
+        out["sp_north_%d" % t] = north
+        out["sp_orph_%d" % t] = orph
+    out["max_cross_block"] = worst_cross
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    a = tr["assoc"]
+    print("wrote %s (%.1f KB): unmatched %.3f, potential %.3f, full %.3f of the pairs; <= %d landmarks, <= %d orphans "
+          "per particle; cross-block max %.1e" % (path, os.path.getsize(path) / 1024.0, float((a == 0).mean()),
+                                                   float((a < 0).mean()), float((a > 0).mean()), n_max, o_max, worst_cross))
+
+
 def unit_fixture(ref):
     """Known-answer vectors from direct calls of the reference's scalar methods."""
     core, msgs = ref.core, ref.msgs
@@ -317,6 +376,10 @@ def main(argv=None):
         "trace_corridor_potential_m24_t12",
         make_scenario("c1", num_particles=24, frames=12, trajectory="corridor", num_landmarks=16), 12,
         (0, 2, 3, 11), potential_slots=(1, 5, 8, 9, 12, 13, 14, 15))
+    jobs["spawn"] = lambda: spawn_fixture(
+        "trace_corridor_spawn_m24_t40",
+        make_scenario("c3", num_particles=24, num_landmarks=24, frames=40, obs_per_frame=8), 40,
+        (0, 1, 2, 5, 10, 20, 39))
     if args.full_c1:
         jobs["c1"] = lambda: trace_fixture(
             "trace_c1_m100_n20_t500", make_scenario("c1"), 500, (0, 99, 249, 499))

@@ -89,6 +89,26 @@ def potential_state(fs, n_slots):
     return pot
 
 
+def spawn_state(ref, fs):
+    """Spawn-mode state of every particle: landmarks keyed by SIGNED id (``feature_set`` ids > 0,
+    ``potential_features`` ids < 0) as (mean[5], cov[5,5], update_count), and the orphaned readings
+    ``hypothesis_set`` in insertion order as (id, x, y, heading + bearing, r, g, b)."""
+    out = []
+    for p in fs.particles:
+        lms = {}
+        for id_, f in list(p.feature_set.items()) + list(p.potential_features.items()):
+            lms[int(id_)] = (np.asarray(f.mean, dtype=np.float64).reshape(5).copy(),
+                             np.asarray(f.covar, dtype=np.float64).reshape(5, 5).copy(), int(f.update_count))
+        orphans = []
+        for id_, (state, blob) in p.hypothesis_set.items():
+            pos = state.pose.pose.position
+            h = float(ref.utils.quaternion_to_heading(state.pose.pose.orientation))
+            orphans.append((int(id_), float(np.asarray(pos.x).reshape(-1)[0]), float(np.asarray(pos.y).reshape(-1)[0]),
+                            float(blob.bearing) + h, float(blob.color.r), float(blob.color.g), float(blob.color.b)))
+        out.append(dict(landmarks=lms, orphans=orphans, next_id=int(p.next_id)))
+    return out
+
+
 def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmarks_at=(),
                   ref=None, spawn=False, known_map=True, timing=None, potential_slots=()):
     """Run the reference over ``frames`` frames.  Returns a dict of numpy traces:
@@ -169,10 +189,12 @@ def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmar
                 trace["pose_post"][t] = [pose_of(ref, p) for p in fs.particles]
                 trace["summary"][t] = [float(v) for v in fs.summary()]
                 trace["next_id"][t] = [p.next_id for p in fs.particles]
-                if t in record_landmarks_at:
+                if t in record_landmarks_at and not spawn:
                     mean, cov, cnt = landmark_state(fs, scn.num_landmarks)
                     trace["lm_mean"][t], trace["lm_cov"][t], trace["lm_count"][t] = mean, cov, cnt
                     trace.setdefault("lm_potential", {})[t] = potential_state(fs, scn.num_landmarks)
+                if spawn and t in record_landmarks_at:
+                    trace.setdefault("spawn_state", {})[t] = spawn_state(ref, fs)
                 if timing is not None and timing(t, trace["frame_seconds"][: t + 1]):
                     trace["frames_run"] = t + 1
                     break

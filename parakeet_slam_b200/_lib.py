@@ -21,8 +21,9 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.environ.get("PARAKEET_B200_LIB") or os.path.join(PKG_DIR, "libparakeet_b200.so")
 _LIB_OVERRIDDEN = bool(os.environ.get("PARAKEET_B200_LIB"))
-SOURCES = ("pk_abi.cu", "pk_motion.cu", "pk_measure.cu", "pk_resample.cu", "pk_probe.cu")
-HEADERS = (os.path.join(CSRC_DIR, "pk_common.cuh"), os.path.join(INCLUDE_DIR, "parakeet_b200.h"))
+SOURCES = ("pk_abi.cu", "pk_motion.cu", "pk_measure.cu", "pk_spawn.cu", "pk_resample.cu", "pk_probe.cu")
+HEADERS = (os.path.join(CSRC_DIR, "pk_common.cuh"), os.path.join(CSRC_DIR, "pk_filter_math.cuh"),
+           os.path.join(INCLUDE_DIR, "parakeet_b200.h"))
 
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17"]
@@ -37,8 +38,15 @@ PK_META_COUNT_MASK = 0x00FFFFFF
 PK_META_IMMUTABLE = 0x10000000
 PK_META_POTENTIAL = 0x20000000
 PK_STAT_MATCHED, PK_STAT_UNMATCHED, PK_STAT_EVALUATED, PK_STAT_FLAGS = 0, 1, 2, 3
-PK_STAT_SAME_LANDMARK, PK_STAT_PROMOTED = 4, 5
+PK_STAT_SAME_LANDMARK, PK_STAT_PROMOTED, PK_STAT_SPAWNED, PK_STAT_ORPHANED = 4, 5, 6, 7
 PK_FLAG_SINGULAR_COV, PK_FLAG_NONFINITE_WEIGHT, PK_FLAG_REPROMOTED = 1, 2, 4
+PK_FLAG_MAP_FULL, PK_FLAG_ORPHAN_EXPIRED, PK_FLAG_SPAWN_DEGENERATE = 8, 16, 32
+PK_MAX_ORPHANS = 1024
+
+
+def dtype_with_orphans(base: int, slots: int) -> int:
+    """``PK_DTYPE_WITH_ORPHANS``: layout code = storage type | orphan slots << 8."""
+    return base | (int(slots) << 8)
 PK_MAX_RANKS = 32
 PK_XPLAN_LONGS = 80
 PK_PEER_HANDLE_BYTES = 64
@@ -120,6 +128,8 @@ SIGNATURES = {
     "pk_motion_update": (_I, [_P, _LL, _P, _ULL, _ULL, _LL, _D, _D, _D, _P]),
     "pk_measurement_update": (_I, [_P, _P, _P, _P, _I, _I, _LL, _P, _I, ctypes.POINTER(PkParams),
                                    _P, _P, _P]),
+    "pk_spawn_update": (_I, [_P, _P, _P, _P, _I, _I, _LL, _P, _I, _P, _D, _P, _P]),
+    "pk_orphans_export": (_I, [_P, _I, _I, _P, _LL, _LL, _P, _P, _P]),
     "pk_num_scan_blocks": (_LL, [_LL]),
     "pk_weight_scan": (_I, [_P, _LL, _P, _P, _P]),
     "pk_resample_thresholds": (_I, [_P, _LL, _LL, _D, _P, _P, _P, _P]),

@@ -255,10 +255,17 @@ class FastSLAM(object):
     ``"philox"`` (on-device counter RNG) or a callable ``f(M) -> [M,3]`` standard normals;
     ``uniform`` callable for the resampling draw (default ``random.random`` as ``:226``);
     ``clock`` callable returning a ROS-like time (default ``rospy.Time.now``).
+    ``spawn=True`` enables the new-landmark path the reference's docstrings describe but its code never
+    reaches (SURVEY.md finding F5 / A.6: ``add_hypothesis`` ``:546-746`` with three documented patches):
+    unseen blobs are paired with earlier orphaned readings whose rays intersect and whose colours lie
+    within ``pair_gate`` (default ``sqrt(300)``), the pair is triangulated into a potential landmark
+    (id < 0) that is promoted after three updates.  ``orphan_capacity`` readings are kept per particle
+    (a ring; the reference keeps them for ever).  Needs ``capacity`` > number of preset landmarks.
     """
 
     def __init__(self, preset_features=[], *, num_particles=50, capacity=None, dtype="f64",
-                 device=None, noise="numpy", seed=0, uniform=None, clock=None, params=None):
+                 device=None, noise="numpy", seed=0, uniform=None, clock=None, params=None,
+                 spawn=False, orphan_capacity=32, pair_gate=300.0 ** 0.5):
         import torch
 
         _lib.require_device()
@@ -278,6 +285,14 @@ class FastSLAM(object):
             raise ValueError("dtype must be 'f32' or 'f64'")
         self.dtype = dtype
         self._dt = _lib.PK_DTYPE_F64 if dtype == "f64" else _lib.PK_DTYPE_F32
+        self.spawn = bool(spawn)
+        self.orphan_capacity = int(orphan_capacity) if self.spawn else 0
+        self.pair_gate = float(pair_gate)
+        if self.spawn:
+            if not 0 < self.orphan_capacity <= _lib.PK_MAX_ORPHANS:
+                raise ValueError("orphan_capacity must be in [1, %d]" % _lib.PK_MAX_ORPHANS)
+            # layout code: storage type | orphan slots (the orphan region lives inside each particle's block)
+            self._dt = _lib.dtype_with_orphans(self._dt, self.orphan_capacity)
         self._noise = noise
         if not (noise in ("numpy", "philox") or callable(noise)):
             raise ValueError("noise must be 'numpy', 'philox' or a callable")
@@ -413,6 +428,12 @@ class FastSLAM(object):
                 _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
                 self.capacity, self._dt, M, obs.ctypes.data, K, ctypes.byref(self.params),
                 _lib.ptr(self._assoc), _lib.ptr(self._stats), self._stream()), "pk_measurement_update")
+            if self.spawn and K:
+                # add_hypothesis for every unseen blob (:92-94), after the frame's associations were made
+                _lib.check(lib.pk_spawn_update(
+                    _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
+                    self.capacity, self._dt, M, obs.ctypes.data, K, _lib.ptr(self._assoc), self.pair_gate,
+                    _lib.ptr(self._stats), self._stream()), "pk_spawn_update")
             self._last_K = K
             if self.keep_trace:
                 self.last_assoc = self._assoc[:, :K].clone()
@@ -548,6 +569,7 @@ class FastSLAM(object):
         return dict(matched=int(s[_lib.PK_STAT_MATCHED]), unmatched=int(s[_lib.PK_STAT_UNMATCHED]),
                     evaluated=int(s[_lib.PK_STAT_EVALUATED]), flags=int(s[_lib.PK_STAT_FLAGS]),
                     same_landmark=int(s[_lib.PK_STAT_SAME_LANDMARK]), promoted=int(s[_lib.PK_STAT_PROMOTED]),
+                    spawned=int(s[_lib.PK_STAT_SPAWNED]), orphaned=int(s[_lib.PK_STAT_ORPHANED]),
                     blocks_copied=int(self._n_copied.item()))
 
     def export_maps(self, lo=0, count=None):
@@ -570,6 +592,31 @@ class FastSLAM(object):
             nlive = self.aux[lo:lo + count, 0].cpu().numpy()
             return (mean5.cpu().numpy(), covp.cpu().numpy().reshape(count, N, 2, 2),
                     covc.cpu().numpy().reshape(count, N, 3, 3), meta.cpu().numpy(), ids.cpu().numpy(), nlive)
+
+    def export_orphans(self, lo=0, count=None):
+        """Spawn mode: the stored orphan readings of particles [lo, lo+count), oldest first, as a list of
+        ``[n_i, 8]`` arrays (x, y, cos(ray), sin(ray), r, g, b, id) and the totals ever stored."""
+        torch, lib = self._torch, self._lib
+        if not self.spawn:
+            raise ValueError("export_orphans needs spawn=True")
+        count = self.num_particles - lo if count is None else count
+        S = self.orphan_capacity
+        with self._lock, self._on_device():
+            totals = torch.zeros((max(count, 1),), dtype=torch.int32, device=self._device)
+            readings = torch.zeros((max(count, 1), S, 8), dtype=torch.float64, device=self._device)
+            if count:
+                _lib.check(lib.pk_orphans_export(_lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self.slot), lo,
+                                                 count, _lib.ptr(totals), _lib.ptr(readings), self._stream()),
+                           "pk_orphans_export")
+            totals = totals.cpu().numpy()[:count]
+            readings = readings.cpu().numpy()[:count]
+        out = []
+        for i in range(count):
+            t = int(totals[i])
+            live = min(t, S)
+            start = t % S if t > S else 0
+            out.append(readings[i][[(start + j) % S for j in range(live)]].copy())
+        return out, totals
 
     def import_maps(self, lo, mean5, covp, covc, meta, ids, n_live=None):
         """Overwrite the landmark state of particles [lo, lo+count) from fp64 arrays shaped like the
@@ -611,6 +658,20 @@ class FastSLAM(object):
                 p.potential_features[int(ids[0, j])] = f
             else:
                 p.feature_set[int(ids[0, j])] = f
+        if self.spawn:
+            # hypothesis_set {id: (state, blob)} (:291, :745); the device keeps the reading's world-frame
+            # ray, so the view reports it as heading = ray angle with a zero bearing (the same ray)
+            from .rosless import messages
+            readings, _ = self.export_orphans(i, 1)
+            for row in readings[0]:
+                st = Odometry()
+                st.pose.pose.position.x = float(row[0])
+                st.pose.pose.position.y = float(row[1])
+                st.pose.pose.orientation = heading_to_quaternion(math.atan2(float(row[3]), float(row[2])))
+                blob = messages.Blob()
+                blob.bearing = 0.0
+                blob.color.r, blob.color.g, blob.color.b = float(row[4]), float(row[5]), float(row[6])
+                p.hypothesis_set[int(row[7])] = (st, blob)
         return p
 
     def state_dict(self):

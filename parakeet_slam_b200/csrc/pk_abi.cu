@@ -48,7 +48,7 @@ __global__ void init_particles_kernel(double* __restrict__ pose4, int* __restric
 }
 
 template <typename T>
-__global__ void map_broadcast_kernel(unsigned char* __restrict__ pool, int capacity, long long slot_lo, long long n_slots,
+__global__ void map_broadcast_kernel(unsigned char* __restrict__ pool, int capacity, size_t bbytes, long long slot_lo, long long n_slots,
                                      int n, const double* __restrict__ mean5, const double* __restrict__ covp,
                                      const double* __restrict__ covc, const int* __restrict__ meta,
                                      const int* __restrict__ ids) {
@@ -69,19 +69,19 @@ __global__ void map_broadcast_kernel(unsigned char* __restrict__ pool, int capac
     for (int q = 0; q < 9; ++q) L.sc[q] = covc[9 * j + q];
     L.meta = meta[j];
     L.id = ids[j];
-    unsigned char* block = pool + (size_t)s * block_bytes(capacity, Rec<T>::kDtype);
+    unsigned char* block = pool + (size_t)s * bbytes;
     store_landmark<T>(block, capacity, j, L);
 }
 
 template <typename T, bool kImport>
-__global__ void map_xfer_kernel(unsigned char* __restrict__ pool, int capacity, const int* __restrict__ slot,
+__global__ void map_xfer_kernel(unsigned char* __restrict__ pool, int capacity, size_t bbytes, const int* __restrict__ slot,
                                 long long p_lo, long long count, double* __restrict__ mean5, double* __restrict__ covp,
                                 double* __restrict__ covc, int* __restrict__ meta, int* __restrict__ ids) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count * capacity) return;
     long long pi = t / capacity;
     int j = (int)(t % capacity);
-    unsigned char* block = pool + (size_t)slot[p_lo + pi] * block_bytes(capacity, Rec<T>::kDtype);
+    unsigned char* block = pool + (size_t)slot[p_lo + pi] * bbytes;
     Landmark L;
     if (kImport) {
         L.x = mean5[5 * t + 0];
@@ -166,7 +166,7 @@ int pk_map_broadcast(void* pool, int capacity, int dtype, long long slot_lo, lon
                      const double* mean5, const double* covp, const double* covc, const int* meta, const int* ids,
                      void* stream) {
     PK_CHECK_ARG(pool != nullptr, "pool is NULL");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(n >= 0 && n <= capacity, "n out of range");
     PK_CHECK_ARG(slot_hi >= slot_lo && slot_lo >= 0, "slot range");
     if (n == 0 || slot_hi == slot_lo) return PK_OK;
@@ -175,12 +175,13 @@ int pk_map_broadcast(void* pool, int capacity, int dtype, long long slot_lo, lon
     const int threads = 256;
     long long blocks = (total + threads - 1) / threads;
     PK_CHECK_ARG(blocks < (1ll << 31), "too many blocks");
-    if (dtype == PK_DTYPE_F32)
+    const size_t bb = block_bytes(capacity, dtype);
+    if (dtype_base(dtype) == PK_DTYPE_F32)
         map_broadcast_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-            (unsigned char*)pool, capacity, slot_lo, slot_hi - slot_lo, n, mean5, covp, covc, meta, ids);
+            (unsigned char*)pool, capacity, bb, slot_lo, slot_hi - slot_lo, n, mean5, covp, covc, meta, ids);
     else
         map_broadcast_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-            (unsigned char*)pool, capacity, slot_lo, slot_hi - slot_lo, n, mean5, covp, covc, meta, ids);
+            (unsigned char*)pool, capacity, bb, slot_lo, slot_hi - slot_lo, n, mean5, covp, covc, meta, ids);
     PK_LAUNCH_CHECK("map_broadcast_kernel");
     return PK_OK;
 }
@@ -188,7 +189,7 @@ int pk_map_broadcast(void* pool, int capacity, int dtype, long long slot_lo, lon
 static int map_xfer(bool import, void* pool, int capacity, int dtype, const int* slot, long long p_lo, long long count,
                     double* mean5, double* covp, double* covc, int* meta, int* ids, void* stream) {
     PK_CHECK_ARG(pool && slot && mean5 && covp && covc && meta && ids, "null pointer");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(capacity > 0 && count >= 0 && p_lo >= 0, "sizes");
     if (count == 0) return PK_OK;
     long long total = count * capacity;
@@ -197,16 +198,17 @@ static int map_xfer(bool import, void* pool, int capacity, int dtype, const int*
     PK_CHECK_ARG(blocks < (1ll << 31), "too many blocks");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* pl = (unsigned char*)pool;
-    if (dtype == PK_DTYPE_F32) {
+    const size_t bb = block_bytes(capacity, dtype);
+    if (dtype_base(dtype) == PK_DTYPE_F32) {
         if (import)
-            map_xfer_kernel<float, true><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, slot, p_lo, count, mean5, covp, covc, meta, ids);
+            map_xfer_kernel<float, true><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, bb, slot, p_lo, count, mean5, covp, covc, meta, ids);
         else
-            map_xfer_kernel<float, false><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, slot, p_lo, count, mean5, covp, covc, meta, ids);
+            map_xfer_kernel<float, false><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, bb, slot, p_lo, count, mean5, covp, covc, meta, ids);
     } else {
         if (import)
-            map_xfer_kernel<double, true><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, slot, p_lo, count, mean5, covp, covc, meta, ids);
+            map_xfer_kernel<double, true><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, bb, slot, p_lo, count, mean5, covp, covc, meta, ids);
         else
-            map_xfer_kernel<double, false><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, slot, p_lo, count, mean5, covp, covc, meta, ids);
+            map_xfer_kernel<double, false><<<(unsigned)blocks, threads, 0, st>>>(pl, capacity, bb, slot, p_lo, count, mean5, covp, covc, meta, ids);
     }
     PK_LAUNCH_CHECK("map_xfer_kernel");
     return PK_OK;

@@ -95,12 +95,32 @@ struct Landmark {
     int id;
 };
 
+// `dtype` arguments carry a LAYOUT CODE: the storage type in the low byte and, in spawn mode, the number
+// of orphan-reading slots per particle above it (PK_DTYPE_WITH_ORPHANS).  The orphan region
+// [64-byte header | n x 64-byte readings] follows the cold region inside the particle's block, so
+// it is copied (and migrates between ranks) with the map.
+__host__ __device__ inline int dtype_base(int dtype) { return dtype & 0xff; }
+__host__ __device__ inline int dtype_orphans(int dtype) { return (dtype >> 8) & 0xffff; }
+__host__ __device__ inline bool dtype_valid(int dtype) {
+    return (dtype_base(dtype) == PK_DTYPE_F32 || dtype_base(dtype) == PK_DTYPE_F64) && (dtype >> 24) == 0 &&
+           dtype_orphans(dtype) <= PK_MAX_ORPHANS;
+}
+constexpr int kOrphanHeaderBytes = 64;  // int total (readings ever stored; ring position = total % slots)
+constexpr int kOrphanBytes = 64;        // double x, y, cos(ray), sin(ray), r, g, b, id
+
 __host__ __device__ inline size_t hot_bytes(int) { return 4; }
-__host__ __device__ inline size_t cold_bytes(int dtype) { return dtype == PK_DTYPE_F64 ? sizeof(ColdD) : sizeof(ColdF); }
+__host__ __device__ inline size_t cold_bytes(int dtype) { return dtype_base(dtype) == PK_DTYPE_F64 ? sizeof(ColdD) : sizeof(ColdF); }
 // hot region padded to 16 B so the cold records and TMA bulk copies stay 16-byte aligned
 __host__ __device__ inline size_t hot_region_bytes(int capacity) { return ((size_t)capacity * 4 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t block_bytes(int capacity, int dtype) {
+__host__ __device__ inline size_t orphan_offset(int capacity, int dtype) {
     return hot_region_bytes(capacity) + (size_t)capacity * cold_bytes(dtype);
+}
+__host__ __device__ inline size_t orphan_region_bytes(int dtype) {
+    const int n = dtype_orphans(dtype);
+    return n ? (size_t)kOrphanHeaderBytes + (size_t)n * kOrphanBytes : 0;
+}
+__host__ __device__ inline size_t block_bytes(int capacity, int dtype) {
+    return orphan_offset(capacity, dtype) + orphan_region_bytes(dtype);
 }
 
 #ifdef __CUDACC__

@@ -569,7 +569,7 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
                                      long long M, const double* obs_host, int K, const pk_params* params, int* assoc,
                                      unsigned long long* stats, void* stream) {
     PK_CHECK_ARG(pose4 && aux2 && slot && pool, "null state pointer");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(M >= 0, "M < 0");
     PK_CHECK_ARG(K >= 0 && K <= PK_MAX_OBS, "K must be in [0, PK_MAX_OBS]");
     PK_CHECK_ARG(capacity >= 0 && capacity < (1 << 20), "capacity must be < 2^20");
@@ -630,6 +630,6 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
     if (g >= 0.0) bound = floor(g + 2.0 * sqrt(3.0 * g) + 3.0) + 1.0;
     if (!(g == g)) bound = 2.0e9;  // NaN gate: `abs(cd) > nan` is False, everything passes
     args.key_thr = (int)(bound > 2.0e9 ? 2.0e9 : bound);
-    if (dtype == PK_DTYPE_F32) return dispatch_measure<float>(args, st);
+    if (dtype_base(dtype) == PK_DTYPE_F32) return dispatch_measure<float>(args, st);
     return dispatch_measure<double>(args, st);
 }

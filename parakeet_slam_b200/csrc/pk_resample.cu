@@ -644,7 +644,7 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
                    long long dst_stride, int hot_b, int cold_b, int capacity, const int* __restrict__ src_slot, const int* __restrict__ dst_slot,
                    const int* __restrict__ nlive, long long n_max, const long long* __restrict__ n_dev,
                    const unsigned long long* __restrict__ dst_tab, const int* __restrict__ dst_rank,
-                   const long long* __restrict__ skip_flag) {
+                   const long long* __restrict__ skip_flag, long long orph_off, int orph_len) {
     __shared__ __align__(128) unsigned char buf[kCopyBufs][kCopyChunk];
     __shared__ uint64_t bar[kCopyBufs];
     if (threadIdx.x != 0) return;
@@ -657,22 +657,25 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
     // chunk stream state: issue side (li_*) and drain side (ld_*)
     struct Cursor {
         long long item;
-        int seg;        // 0 = hot range, 1 = cold range
+        int seg;        // 0 = hot range, 1 = cold range, 2 = orphan region (spawn mode)
         long long off;  // offset inside the segment
     };
     auto seg_len = [&](long long item, int seg) -> long long {
         if (src_slot[item] < 0) return 0;  // entry not served by this launch (e.g. filled from a receive buffer)
         const int nl = nlive ? min(nlive[item], capacity) : capacity;
         // hot keys are 4 B each: round the range up to the 16 B granularity of a bulk copy
+        if (seg == 2) return (long long)orph_len;
         return seg == 0 ? (((long long)nl * hot_b + 15) & ~15ll) : (long long)nl * cold_b;
     };
-    auto seg_base = [&](int seg) -> long long { return seg == 0 ? 0 : (long long)hot_region_bytes(capacity); };
+    auto seg_base = [&](int seg) -> long long {
+        return seg == 0 ? 0 : (seg == 1 ? (long long)hot_region_bytes(capacity) : orph_off);
+    };
     auto advance = [&](Cursor& c, long long stride) {
         // move to the next chunk, skipping empty segments; item strides over the grid
         c.off += kCopyChunk;
         while (c.item < n && c.off >= seg_len(c.item, c.seg)) {
             c.off = 0;
-            if (++c.seg > 1) {
+            if (++c.seg > 2) {
                 c.seg = 0;
                 c.item += stride;
             }
@@ -918,7 +921,9 @@ static int copy_blocks_launch(const void* src, void* dst, int capacity, int dtyp
     copy_blocks_kernel<<<(unsigned)grid, 32, 0, st>>>((const unsigned char*)src, (unsigned char*)dst, src_stride,
                                                      dst_stride, (int)hot_bytes(dtype),
                                                      (int)cold_bytes(dtype), capacity, src_slot, dst_slot, nlive, n_max,
-                                                     n_dev, dst_tab, dst_rank, skip_flag);
+                                                     n_dev, dst_tab, dst_rank, skip_flag,
+                                                     (long long)orphan_offset(capacity, dtype),
+                                                     (int)orphan_region_bytes(dtype));
     PK_LAUNCH_CHECK("copy_blocks_kernel");
     return PK_OK;
 }
@@ -930,7 +935,7 @@ int pk_resample_gather(const long long* ancestors, const int* offspring, long lo
                      workspace && n_copied_out,
                  "null pointer");
     PK_CHECK_ARG(M > 0 && M < (1ll << 31), "M");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(pose4_in != pose4_out && slot_in != slot_out && aux2_in != aux2_out, "gather is out of place");
     cudaStream_t st = (cudaStream_t)stream;
     GatherWs g = carve(workspace, M);
@@ -962,7 +967,7 @@ int pk_pack_particles(const long long* emit_run, long long n, long long particle
     PK_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return PK_OK;
     PK_CHECK_ARG(emit_run && pose4 && aux2 && slot && pool && out && workspace, "null pointer");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     cudaStream_t st = (cudaStream_t)stream;
     const long long stride = pk_particle_record_bytes(capacity, dtype);
     int* src_slot = workspace;
@@ -1037,7 +1042,7 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
     PK_CHECK_ARG(n_lo >= 0 && n_loc >= 0 && n_lo + n_loc <= Ml, "window split");
     PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
     PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     return gather_sharded_impl(local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
@@ -1046,7 +1051,7 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
 int pk_copy_blocks(const void* pool_src, void* pool_dst, int capacity, int dtype, const int* src_slot,
                    const int* dst_slot, const int* n_live, long long n_max, const long long* n_dev, void* stream) {
     PK_CHECK_ARG(pool_src && pool_dst && src_slot && dst_slot, "null pointer");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(capacity > 0 && n_max >= 0, "sizes");
     if (n_max == 0) return PK_OK;
     return copy_blocks_launch(pool_src, pool_dst, capacity, dtype, src_slot, dst_slot, n_live, n_max, n_dev,
@@ -1132,7 +1137,7 @@ int pk_push_particles(const long long* xplan, const long long* out_lo, long long
                       const unsigned long long* peer_recv_tab, long long send_capacity, int* workspace, void* stream) {
     PK_CHECK_ARG(xplan && out_lo && pose4 && aux2 && slot && pool && peer_recv_tab && workspace, "null pointer");
     PK_CHECK_ARG(Ml > 0 && send_capacity >= 0 && send_capacity < (1ll << 31), "sizes");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     if (send_capacity == 0) return PK_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const long long stride = pk_particle_record_bytes(capacity, dtype);
@@ -1160,7 +1165,7 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                      slot_out && pool && workspace && total_dead_out && recv,
                  "null pointer");
     PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31) && recv_capacity >= 0, "sizes");
-    PK_CHECK_ARG(dtype == PK_DTYPE_F32 || dtype == PK_DTYPE_F64, "dtype");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     return gather_sharded_impl(anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);

@@ -22,13 +22,15 @@ def make_features(scn):
     return feats
 
 
-def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=(), noise="numpy", potential_slots=()):
+def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=(), noise="numpy", potential_slots=(),
+               spawn=False, known_map=True, capacity=None, orphan_capacity=32):
     from parakeet_slam_b200.core import FastSLAM
     T = scn.frames if frames is None else frames
     M = scn.num_particles if num_particles is None else num_particles
     K = scn.obs_per_frame
     clock.set(0.0)
-    fs = FastSLAM(make_features(scn), num_particles=M, dtype=dtype, noise=noise)
+    fs = FastSLAM(make_features(scn) if known_map else [], num_particles=M, dtype=dtype, noise=noise, spawn=spawn,
+                  capacity=capacity, orphan_capacity=orphan_capacity)
     fs.keep_trace = True
     if len(potential_slots):
         # turn some preset landmarks into POTENTIAL features (id < 0), as potential_features[-id] of the reference
@@ -68,5 +70,9 @@ def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=()
             tr["lm_mean"][t], tr["lm_covp"][t], tr["lm_covc"][t] = mean5, covp, covc
             tr["lm_count"][t] = meta & 0x00FFFFFF
             tr.setdefault("lm_potential", {})[t] = (meta & 0x20000000) != 0
+            live = np.arange(ids.shape[1])[None, :] < nlive[:, None]
+            tr.setdefault("lm_ids", {})[t] = np.where(live, ids, 0)
+            if spawn:
+                tr.setdefault("orphans", {})[t] = fs.export_orphans()[0]
     tr["filter"] = fs
     return tr

@@ -119,3 +119,47 @@ def test_trace(name):
         assert (g["assoc"] < 0).any() and (g["assoc"][-1] > 0).all()
         assert g["lm_potential_%d" % cps[0]].any() and not g["lm_potential_%d" % cps[-1]][:, list(pot)].all()
     assert float(g["max_cross_block"]) == 0.0
+
+
+def _sorted_spawn_state(ids, mean, cov, cnt, n_max):
+    """Oracle landmark arrays -> the fixture's layout (landmarks sorted by |id|, zero padded)."""
+    M = ids.shape[0]
+    o_ids = np.zeros((M, n_max), dtype=np.int64)
+    o_mean = np.zeros((M, n_max, 5))
+    o_cov = np.zeros((M, n_max, 5, 5))
+    o_cnt = np.zeros((M, n_max), dtype=np.int64)
+    for i in range(M):
+        js = [j for j in range(ids.shape[1]) if ids[i, j] != 0]
+        js.sort(key=lambda j: abs(int(ids[i, j])))
+        assert len(js) <= n_max
+        for q, j in enumerate(js):
+            o_ids[i, q], o_mean[i, q], o_cov[i, q], o_cnt[i, q] = ids[i, j], mean[i, j], cov[i, j], cnt[i, j]
+    return o_ids, o_mean, o_cov, o_cnt
+
+
+def test_spawn_trace():
+    """Spawn mode: the restatement against the reference run with the three documented
+    patches -- new potential landmarks, their promotion, the orphaned readings."""
+    g = load_trace("trace_corridor_spawn_m24_t40")
+    scn = scenario_from_trace(g)
+    cps = tuple(int(c) for c in g["checkpoints"])
+    n_max = int(g["n_max"])
+    tr = onp.run_scenario(scn, record_landmarks_at=cps, spawn=True, known_map=False, capacity=2 * n_max)
+    assert np.array_equal(tr["assoc"], g["assoc"])
+    assert np.array_equal(tr["ancestors"], g["ancestors"])
+    assert np.array_equal(tr["next_id"], g["next_id"])
+    assert np.max(np.abs(tr["pose_post"] - g["pose_post"])) < 1e-12
+    assert _rel(tr["weight"], g["weight"]) < 1e-9
+    for t in cps:
+        ids, mean, cov, cnt = _sorted_spawn_state(tr["lm_ids"][t], tr["lm_mean"][t], tr["lm_cov"][t], tr["lm_count"][t], n_max)
+        assert np.array_equal(ids, g["sp_ids_%d" % t])
+        assert np.max(np.abs(mean - g["sp_mean_%d" % t])) < 1e-9
+        assert np.max(np.abs(cov[..., :2, :2] - g["sp_covp_%d" % t])) < 1e-10
+        assert np.max(np.abs(cov[..., 2:, 2:] - g["sp_covc_%d" % t])) < 1e-10
+        assert np.array_equal(cnt, g["sp_count_%d" % t])
+        for i, orph in enumerate(tr["orphans"][t]):
+            assert len(orph) == int(g["sp_north_%d" % t][i])
+            if orph:
+                assert np.max(np.abs(np.asarray(orph) - g["sp_orph_%d" % t][i, :len(orph)])) < 1e-12
+    a = g["assoc"]
+    assert (a == 0).any() and (a < 0).any() and (a > 0).any()      # orphans, potential and promoted landmarks all occur
