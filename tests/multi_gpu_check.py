@@ -39,11 +39,13 @@ def main():
         def __call__(self):
             return Time(0, self.ns)
 
-    def run(cls, dtype, skew=False, **kw):
+    def run(cls, dtype, skew=False, spawn=False, **kw):
         clk = Clk()
         urng = random.Random(99)
-        fs = cls(make_features(scn), num_particles=M, dtype=dtype, noise="philox", seed=7, uniform=urng.random,
-                 clock=clk, **kw)
+        if spawn:   # unknown map: the orphan region of every block must migrate with it
+            kw = dict(kw, spawn=True, capacity=32, orphan_capacity=16)
+        fs = cls([] if spawn else make_features(scn), num_particles=M, dtype=dtype, noise="philox", seed=7,
+                 uniform=urng.random, clock=clk, **kw)
         fs.keep_trace = True
         tw = messages.Twist()
         tw.linear.x, tw.angular.z = scn.v, scn.w
@@ -66,19 +68,24 @@ def main():
                 moved += fs.last_plan["n_lo"] + fs.last_plan["n_hi"]
             out.append((fs.pose[:, :3].clone(), w, fs.last_ancestors.clone(), fs.summary()))
         maps = fs.export_maps()
+        if spawn:
+            rows, totals = fs.export_orphans()
+            maps = tuple(maps) + (totals, np.concatenate([r.reshape(-1) for r in rows] + [np.zeros(0)]),
+                                  np.array([len(r) for r in rows]))
         return fs, out, maps, moved
 
     ok = True
     single = {}
-    for dtype, exchange, skew in (("f64", "peer", False), ("f32", "peer", False), ("f32", "peer", True),
-                                  ("f64", "nccl", False), ("f32", "nccl", True)):
-        fs_s, out_s, maps_s, moved = run(ShardedFastSLAM, dtype, skew, exchange=exchange)
+    for dtype, exchange, skew, spawn in (("f64", "peer", False, False), ("f32", "peer", False, False),
+                                         ("f32", "peer", True, False), ("f64", "peer", True, True),
+                                         ("f64", "nccl", False, False), ("f32", "nccl", True, True)):
+        fs_s, out_s, maps_s, moved = run(ShardedFastSLAM, dtype, skew, spawn, exchange=exchange)
         moved_t = torch.tensor([moved], device="cuda")
         dist.all_reduce(moved_t)
         # single-GPU reference on every rank (cheap at this size), compared on the rank's own slice
-        if (dtype, skew) not in single:
-            single[(dtype, skew)] = run(FastSLAM, dtype, skew)
-        fs_1, out_1, maps_1, _ = single[(dtype, skew)]
+        if (dtype, skew, spawn) not in single:
+            single[(dtype, skew, spawn)] = run(FastSLAM, dtype, skew, spawn)
+        fs_1, out_1, maps_1, _ = single[(dtype, skew, spawn)]
         lo, hi = rank * Ml, (rank + 1) * Ml
         for t in range(frames):
             p_s, w_s, a_s, sum_s = out_s[t]
@@ -93,6 +100,19 @@ def main():
             if max(abs(x - y) for x, y in zip(sum_s, sum_1)) > 1e-12:
                 print("rank %d summary differs" % rank, sum_s, sum_1, flush=True)
                 ok = False
+        if spawn:
+            # orphan readings: totals per particle, and the concatenated readings of the rank's slice
+            counts_1 = maps_1[8]
+            off = np.concatenate([[0], np.cumsum(counts_1)]) * 8
+            maps_1 = tuple(maps_1[:6]) + (maps_1[6], maps_1[7][off[lo]:off[hi]], counts_1)
+            maps_s = tuple(maps_s[:6]) + (maps_s[6], maps_s[7], maps_s[8])
+            if not (np.array_equal(maps_s[6], maps_1[6][lo:hi]) and np.array_equal(maps_s[7], maps_1[7])
+                    and np.array_equal(maps_s[8], maps_1[8][lo:hi])):
+                print("rank %d dtype %s %s: orphan readings differ" % (rank, dtype, exchange), flush=True)
+                ok = False
+            if int(maps_1[6].max()) == 0:
+                print("spawn run stored no reading: the test exercised nothing", flush=True)
+                ok = False
         for name, a, b in zip(("mean", "covp", "covc", "meta", "ids", "nlive"), maps_s, maps_1):
             if not np.array_equal(a, b[lo:hi]):
                 print("rank %d dtype %s %s skew=%s: landmark %s differs after %d frames" % (
@@ -103,8 +123,8 @@ def main():
             print("rank %d best particle differs" % rank, b_s, b_1, flush=True)
             ok = False
         if rank == 0:
-            print("dtype %s exchange %s skew %s: %d particles over %d ranks, %d frames, %d particle migrations, "
-                  "identical=%s" % (dtype, exchange, skew, M, world, frames, int(moved_t.item()), ok), flush=True)
+            print("dtype %s exchange %s skew %s spawn %s: %d particles over %d ranks, %d frames, %d particle migrations, "
+                  "identical=%s" % (dtype, exchange, skew, spawn, M, world, frames, int(moved_t.item()), ok), flush=True)
         if world > 1 and int(moved_t.item()) == 0:
             print("no particle crossed a shard boundary: the test exercised nothing", flush=True)
             ok = False

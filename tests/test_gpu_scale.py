@@ -299,3 +299,64 @@ def test_empty_scan_and_too_many_blobs():
     V.last_sensor_reading = None
     with pytest.raises(AttributeError):          # as the reference: scan.observes on None (:344)
         fs.cam_cb(V())
+
+
+def test_config3_size_spawn_properties():
+    """BASELINE config 3 shape -- 2^22 particles, capacity 256, UNKNOWN map, spawn mode (82 GB of particle blocks):
+    size-independent properties of the new-landmark path (id bookkeeping along every lineage, sign <-> potential
+    flag, block permutation through the resamples, counters that add up)."""
+    import torch
+    from parakeet_slam_b200.core import FastSLAM
+    from parakeet_slam_b200.rosless import Time, messages
+    from parakeet_slam_b200.scenario import DT_NSEC, make_scenario
+    free, _ = torch.cuda.mem_get_info()
+    M = 1 << 22
+    if free < 110e9:
+        M = 1 << 20
+    N, T, K = 256, 5, 8
+    scn = make_scenario("c3", num_particles=M, num_landmarks=N, frames=T, obs_per_frame=K)
+
+    class Clk(object):
+        ns = 0
+
+        def __call__(self):
+            return Time(0, self.ns)
+    clk = Clk()
+    urng = random.Random(9)
+    fs = FastSLAM([], num_particles=M, capacity=N, dtype="f32", noise="philox", seed=5, uniform=urng.random, clock=clk,
+                  spawn=True, orphan_capacity=32)
+    tw = messages.Twist()
+    tw.linear.x, tw.angular.z = scn.v, scn.w
+    fs.last_control = tw
+    spawned = orphaned = 0
+    for t in range(T):
+        clk.ns += DT_NSEC
+        fs.motion_update(tw)
+        fs.measurement_update(scn.observations[t])
+        s = fs.stats()
+        assert s["matched"] + s["unmatched"] == M * K
+        assert s["spawned"] + s["orphaned"] == s["unmatched"]      # every unseen blob ends in exactly one of the two
+        # allowed: ring expiry (16) and, with fp32 storage, PK_FLAG_SINGULAR_COV (1): a landmark triangulated from two
+        # nearly coincident rays sits almost on the robot, its first update collapses the position covariance to
+        # ~0.1/h^2 along h, and the fp32 lower triangle can then round to det <= 0 (the likelihood is NaN -> no match,
+        # as `nan > max` is False in the reference loop)
+        assert (s["flags"] & ~(16 | 1)) == 0, s["flags"]
+        spawned += s["spawned"]
+        orphaned += s["orphaned"]
+        fs.low_variance_resample()
+    assert spawned > 0 and orphaned > 0
+    aux = fs.aux.cpu().numpy()
+    n_live, next_id = aux[:, 0].astype(np.int64), aux[:, 1].astype(np.int64)
+    assert n_live.min() >= 0 and n_live.max() <= N
+    # along every surviving lineage: ids consumed = readings stored + landmarks spawned
+    sample = np.linspace(0, M - 1, 2048).astype(np.int64)
+    for i in sample[:64]:
+        rows, totals = fs.export_orphans(int(i), 1)
+        assert next_id[i] - 1 == int(totals[0]) + n_live[i], (i, next_id[i], totals[0], n_live[i])
+        mean5, covp, covc, meta, ids, nl = fs.export_maps(int(i), 1)
+        live_ids = ids[0, :int(nl[0])]
+        assert len(set(np.abs(live_ids))) == len(live_ids) and (live_ids != 0).all()
+        assert np.all((live_ids < 0) == ((meta[0, :int(nl[0])] & 0x20000000) != 0))    # sign <-> potential flag
+        assert np.isfinite(mean5[0, :int(nl[0])]).all()
+    slot = fs.slot.cpu().numpy()
+    assert len(np.unique(slot)) == M                               # blocks stay a permutation through the resamples
