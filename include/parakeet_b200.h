@@ -174,6 +174,14 @@ int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool,
                           const pk_params* params, int* assoc, unsigned long long* stats,
                           void* stream);
 
+/* Same with the scan resident on the device (obs_dev[K][4]; e.g. written by pk_simulate_scan), so a frame
+ * never visits the host.  table_ws: pk_obs_table_bytes() of device scratch. */
+long long pk_obs_table_bytes(void);
+int pk_measurement_update_dev(double* pose4, int* aux2, const int* slot, void* pool, int capacity,
+                              int dtype, long long M, const double* obs_dev, int K,
+                              const pk_params* params, int* assoc, unsigned long long* stats,
+                              void* table_ws, void* stream);
+
 /* ---- K2b spawn mode: FilterParticle.add_hypothesis for every unseen blob (id 0) of the frame, in scan
  *      order: find_nearest_reading / reading_distance_function / ray_intersect / color_distance
  *      (prkt_core_v2.py:546-651), add_new_feature + cross_readings (:653-738) or
@@ -186,6 +194,9 @@ int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool,
 int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool, int capacity,
                     int dtype, long long M, const double* obs_host, int K, const int* assoc,
                     double pair_gate, unsigned long long* stats, void* stream);
+int pk_spawn_update_dev(const double* pose4, int* aux2, const int* slot, void* pool, int capacity,
+                        int dtype, long long M, const double* obs_dev, int K, const int* assoc,
+                        double pair_gate, unsigned long long* stats, void* stream);
 /* Orphan readings of particles [p_lo, p_lo+count): totals[count] (readings ever stored) and
  * readings[count][slots][8] doubles in ring order (tests, FilterParticle.hypothesis_set views). */
 int pk_orphans_export(const void* pool, int capacity, int dtype, const int* slot, long long p_lo,
@@ -312,6 +323,27 @@ int pk_summary_partial(const double* pose4, long long M, double* out5, double* w
 /* best[0] = max weight, best[1] = index of its first occurrence (as double). workspace 2*1024. */
 int pk_best_particle(const double* pose4, long long M, double* best2, double* workspace,
                      void* stream);
+
+/* ---- tools around the filter -------------------------------------- */
+/* Scan simulator standing in for the un-vendored viz_feature_sim node (VizScan of K Blobs, matrix.py:35-39,
+ * prkt_core_v2.py:344): the K landmarks of landmarks5[N][5] (x, y, r, g, b; device) nearest the true pose, in
+ * ascending distance order, bearing = wrap_pi(atan2(ly-y, lx-x) - theta) + sigma_bearing * z0, colour = truth +
+ * sigma_color * z1..3.  noise4[K][4]: injected standard normals (device), or NULL for on-device counter noise
+ * keyed by (seed, frame).  workspace: N doubles.  obs_out[K][4] and landmark_out[K] (nullable) stay on the device. */
+int pk_simulate_scan(const double* landmarks5, int N, double x, double y, double theta, int K,
+                     const double* noise4, unsigned long long seed, unsigned long long frame,
+                     double sigma_bearing, double sigma_color, double* workspace, double* obs_out,
+                     int* landmark_out, void* stream);
+/* Accuracy analysis (the working form of analyze_slam.py:1-36, utils.py heading_error / minimize_angle):
+ * out8 = sum w, sum w^2, sum (x-xt)^2, sum (y-yt)^2, sum minimize_angle(theta-tt)^2, sum x, sum y, max w over
+ * the particles.  workspace: 8*512 doubles. */
+int pk_accuracy(const double* pose4, long long M, double x_true, double y_true, double theta_true,
+                double* out8, double* workspace, void* stream);
+/* Per true landmark j (ids j+1, load_feature_list :294-299): err2_out[j] = sum over particles of the squared
+ * position error of the landmark carrying that id, count_out[j] = particles that hold it. */
+int pk_map_error(const void* pool, int capacity, int dtype, const int* slot, const int* aux2,
+                 long long M, const double* truth5, int N, double* err2_out,
+                 unsigned long long* count_out, void* stream);
 
 /* ---- probes: the per-landmark math one triple per thread (back the scalar helper methods of
  *      FilterParticle -- probability_of_match prkt_core_v2.py:383-455, the EKF pieces :748-930 --

@@ -21,7 +21,7 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.environ.get("PARAKEET_B200_LIB") or os.path.join(PKG_DIR, "libparakeet_b200.so")
 _LIB_OVERRIDDEN = bool(os.environ.get("PARAKEET_B200_LIB"))
-SOURCES = ("pk_abi.cu", "pk_motion.cu", "pk_measure.cu", "pk_spawn.cu", "pk_resample.cu", "pk_probe.cu")
+SOURCES = ("pk_abi.cu", "pk_motion.cu", "pk_measure.cu", "pk_spawn.cu", "pk_resample.cu", "pk_probe.cu", "pk_sim.cu")
 HEADERS = (os.path.join(CSRC_DIR, "pk_common.cuh"), os.path.join(CSRC_DIR, "pk_filter_math.cuh"),
            os.path.join(INCLUDE_DIR, "parakeet_b200.h"))
 
@@ -128,6 +128,13 @@ SIGNATURES = {
     "pk_motion_update": (_I, [_P, _LL, _P, _ULL, _ULL, _LL, _D, _D, _D, _P]),
     "pk_measurement_update": (_I, [_P, _P, _P, _P, _I, _I, _LL, _P, _I, ctypes.POINTER(PkParams),
                                    _P, _P, _P]),
+    "pk_obs_table_bytes": (_LL, []),
+    "pk_measurement_update_dev": (_I, [_P, _P, _P, _P, _I, _I, _LL, _P, _I, ctypes.POINTER(PkParams),
+                                       _P, _P, _P, _P]),
+    "pk_spawn_update_dev": (_I, [_P, _P, _P, _P, _I, _I, _LL, _P, _I, _P, _D, _P, _P]),
+    "pk_simulate_scan": (_I, [_P, _I, _D, _D, _D, _I, _P, _ULL, _ULL, _D, _D, _P, _P, _P, _P]),
+    "pk_accuracy": (_I, [_P, _LL, _D, _D, _D, _P, _P, _P]),
+    "pk_map_error": (_I, [_P, _I, _I, _P, _P, _LL, _P, _I, _P, _P, _P]),
     "pk_spawn_update": (_I, [_P, _P, _P, _P, _I, _I, _LL, _P, _I, _P, _D, _P, _P]),
     "pk_orphans_export": (_I, [_P, _I, _I, _P, _LL, _LL, _P, _P, _P]),
     "pk_num_scan_blocks": (_LL, [_LL]),

@@ -344,6 +344,7 @@ class FastSLAM(object):
         self._out5 = torch.zeros((5,), dtype=f64, device=dev)
         self._best2 = torch.zeros((2,), dtype=f64, device=dev)
         self._assoc = None
+        self._obs_table = None
         self._noise_pinned = None
         self._noise_dev = None
 
@@ -403,6 +404,8 @@ class FastSLAM(object):
             raise AttributeError("'NoneType' object has no attribute 'observes'")
         if isinstance(scan, np.ndarray):
             return np.ascontiguousarray(scan, dtype=np.float64).reshape(-1, 4)
+        if hasattr(scan, "is_cuda"):
+            return scan            # device-resident scan (BearingSimulator): handed to the kernels as is
         blobs = scan.observes
         obs = np.empty((len(blobs), 4), dtype=np.float64)
         for k, b in enumerate(blobs):
@@ -413,27 +416,44 @@ class FastSLAM(object):
         return obs
 
     def measurement_update(self, obs):
-        """The per-particle body of ``cam_cb`` (``:73, :84-124``) for a ``[K,4]`` host array of
-        blobs, as ONE fused kernel.  Also the v1 core's name for the same step
-        (``prkt_core.py:159-236``)."""
+        """The per-particle body of ``cam_cb`` (``:73, :84-124``) for a ``[K,4]`` array of blobs, as ONE fused
+        kernel.  ``obs`` is a host array (the blob table rides in the kernel arguments) or a CUDA tensor, e.g.
+        a ``BearingSimulator`` scan (the table is then built on the device and nothing visits the host).  Also
+        the v1 core's name for the same step (``prkt_core.py:159-236``)."""
         torch, lib, M = self._torch, self._lib, self.num_particles
-        obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 4)
-        K = obs.shape[0]
+        on_device = hasattr(obs, "is_cuda") and obs.is_cuda
+        if on_device:
+            if obs.dtype != torch.float64 or obs.dim() != 2 or obs.shape[1] != 4 or not obs.is_contiguous():
+                raise ValueError("a device scan must be a contiguous float64 [K, 4] tensor")
+        else:
+            obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 4)
+        K = int(obs.shape[0])
         if K > _lib.PK_MAX_OBS:
             raise ValueError("at most %d blobs per frame (got %d)" % (_lib.PK_MAX_OBS, K))
         with self._lock, self._on_device():
             if self._assoc is None or self._assoc.shape[1] != K:
                 self._assoc = torch.zeros((M, max(K, 1)), dtype=torch.int32, device=self._device)
-            _lib.check(lib.pk_measurement_update(
-                _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
-                self.capacity, self._dt, M, obs.ctypes.data, K, ctypes.byref(self.params),
-                _lib.ptr(self._assoc), _lib.ptr(self._stats), self._stream()), "pk_measurement_update")
+            if on_device:
+                if self._obs_table is None:
+                    self._obs_table = torch.zeros((int(lib.pk_obs_table_bytes()),), dtype=torch.uint8,
+                                                  device=self._device)
+                _lib.check(lib.pk_measurement_update_dev(
+                    _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
+                    self.capacity, self._dt, M, _lib.ptr(obs), K, ctypes.byref(self.params),
+                    _lib.ptr(self._assoc), _lib.ptr(self._stats), _lib.ptr(self._obs_table), self._stream()),
+                    "pk_measurement_update_dev")
+            else:
+                _lib.check(lib.pk_measurement_update(
+                    _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
+                    self.capacity, self._dt, M, obs.ctypes.data, K, ctypes.byref(self.params),
+                    _lib.ptr(self._assoc), _lib.ptr(self._stats), self._stream()), "pk_measurement_update")
             if self.spawn and K:
                 # add_hypothesis for every unseen blob (:92-94), after the frame's associations were made
-                _lib.check(lib.pk_spawn_update(
-                    _lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
-                    self.capacity, self._dt, M, obs.ctypes.data, K, _lib.ptr(self._assoc), self.pair_gate,
-                    _lib.ptr(self._stats), self._stream()), "pk_spawn_update")
+                fn = lib.pk_spawn_update_dev if on_device else lib.pk_spawn_update
+                _lib.check(fn(_lib.ptr(self.pose), _lib.ptr(self.aux), _lib.ptr(self.slot), _lib.ptr(self._pool),
+                              self.capacity, self._dt, M, _lib.ptr(obs) if on_device else obs.ctypes.data, K,
+                              _lib.ptr(self._assoc), self.pair_gate, _lib.ptr(self._stats), self._stream()),
+                           "pk_spawn_update")
             self._last_K = K
             if self.keep_trace:
                 self.last_assoc = self._assoc[:, :K].clone()

@@ -86,6 +86,14 @@ struct Rec<double> {
     static constexpr int kDtype = PK_DTYPE_F64;
 };
 
+// Per-frame blob table of the measurement kernels: built on the host from obs_host (kernel argument, no
+// copy) or by obs_table_kernel from a device-resident scan (pk_measurement_update_dev).
+struct ObsTable {
+    double beta[PK_MAX_OBS], cr[PK_MAX_OBS], cg[PK_MAX_OBS], cb[PK_MAX_OBS];
+    double dirx[PK_MAX_OBS], diry[PK_MAX_OBS];  // unit((cos b, sin b, 0)) of closest_point :510
+    unsigned okey[PK_MAX_OBS];                  // colour keys of the blobs
+};
+
 // fp64 working copy of one landmark
 struct Landmark {
     double x, y, r, g, b;

@@ -74,9 +74,8 @@ struct MeasureArgs {
     int keys_off;     // offset of the key ring inside a warp's shared memory
     int rec_off;      // offset of the record staging area
     pk_params prm;
-    double beta[PK_MAX_OBS], cr[PK_MAX_OBS], cg[PK_MAX_OBS], cb[PK_MAX_OBS];
-    double dirx[PK_MAX_OBS], diry[PK_MAX_OBS];  // unit((cos b, sin b, 0)) of closest_point :510
-    unsigned okey[PK_MAX_OBS];                  // colour keys of the blobs
+    const ObsTable* tab_dev;  // device-resident blob table (pk_measurement_update_dev), else NULL
+    ObsTable tab;             // blob table passed by value (host scan)
 };
 
 // fixed part of a warp's shared memory; the key ring [kStages][group][kKeyStride] and the record
@@ -130,6 +129,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
     const long long my_groups = (gw < n_groups) ? (n_groups - gw + total_warps - 1) / total_warps : 0;
 
+    const ObsTable* OT = A.tab_dev ? A.tab_dev : &A.tab;
     // this lane's items: item w = r * 32 + lane -> (particle pl, blob k) within a group
     int it_pl[R], it_k[R];
     unsigned it_key[R];
@@ -138,7 +138,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         const int w = r * 32 + lane;
         it_pl[r] = w / K;
         it_k[r] = w - it_pl[r] * K;
-        it_key[r] = (it_pl[r] < GP) ? A.okey[it_k[r]] : 0u;
+        it_key[r] = (it_pl[r] < GP) ? OT->okey[it_k[r]] : 0u;
     }
 
     // the blob of this lane's item(s) never changes: keep its values in registers
@@ -146,12 +146,12 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int k = (it_pl[r] < GP) ? it_k[r] : 0;
-        ob_beta[r] = A.beta[k];
-        ob_r[r] = A.cr[k];
-        ob_g[r] = A.cg[k];
-        ob_b[r] = A.cb[k];
-        ob_dx[r] = A.dirx[k];
-        ob_dy[r] = A.diry[k];
+        ob_beta[r] = OT->beta[k];
+        ob_r[r] = OT->cr[k];
+        ob_g[r] = OT->cg[k];
+        ob_b[r] = OT->cb[k];
+        ob_dx[r] = OT->dirx[k];
+        ob_dy[r] = OT->diry[k];
     }
 
     if (lane == 0) {
@@ -567,9 +567,32 @@ static int dispatch_measure(MeasureArgs& args, cudaStream_t st) {
 
 using namespace pk;
 
-extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype,
-                                     long long M, const double* obs_host, int K, const pk_params* params, int* assoc,
-                                     unsigned long long* stats, void* stream) {
+// blob table from a device-resident scan: one thread per blob, the arithmetic of the host path
+// (closest_point :510 / utils.py:69-76 with separate roundings; cos/sin are CUDA's, <= 2 ulp from libm)
+__global__ void obs_table_kernel(const double* __restrict__ obs, int K, pk::ObsTable* __restrict__ tab) {
+    const int k = threadIdx.x;
+    if (k >= PK_MAX_OBS) return;
+    if (k >= K) {
+        tab->okey[k] = 0u;
+        return;
+    }
+    const double beta = obs[4 * k], r = obs[4 * k + 1], g = obs[4 * k + 2], b = obs[4 * k + 3];
+    double s, c;
+    sincos(beta, &s, &c);
+    const double length = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(c, c), __dmul_rn(s, s)), 0.0));
+    const double inv = __ddiv_rn(1.0, length);
+    tab->beta[k] = beta;
+    tab->cr[k] = r;
+    tab->cg[k] = g;
+    tab->cb[k] = b;
+    tab->dirx[k] = __dmul_rn(c, inv);
+    tab->diry[k] = __dmul_rn(s, inv);
+    tab->okey[k] = pk::color_key(r, g, b);
+}
+
+static int measurement_common(double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype, long long M,
+                              const double* obs_host, const double* obs_dev, void* table_ws, int K,
+                              const pk_params* params, int* assoc, unsigned long long* stats, void* stream) {
     PK_CHECK_ARG(pose4 && aux2 && slot && pool, "null state pointer");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(M >= 0, "M < 0");
@@ -584,7 +607,7 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
         PK_LAUNCH_CHECK("reset_weight_kernel");
         return PK_OK;
     }
-    PK_CHECK_ARG(obs_host != nullptr && assoc != nullptr, "obs_host / assoc is NULL");
+    PK_CHECK_ARG((obs_host != nullptr || obs_dev != nullptr) && assoc != nullptr, "obs / assoc is NULL");
     if (stats != nullptr) PK_CUDA(cudaMemsetAsync(stats, 0, PK_NUM_STATS * sizeof(unsigned long long), st));
 
     static thread_local MeasureArgs args;
@@ -603,25 +626,34 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
     if (group > kMaxGroup) group = kMaxGroup;
     args.group = group;
     args.prm = *params;
-    auto key_of = [](double c) -> unsigned {
-        if (!(c == c)) return 0u;  // NaN
-        c = c < 0.0 ? 0.0 : (c > 255.0 ? 255.0 : c);
-        return (unsigned)nearbyint(c);
-    };
-    for (int k = 0; k < PK_MAX_OBS; ++k) args.okey[k] = 0u;
-    for (int k = 0; k < K; ++k) {
-        const double beta = obs_host[4 * k + 0];
-        args.beta[k] = beta;
-        args.cr[k] = obs_host[4 * k + 1];
-        args.cg[k] = obs_host[4 * k + 2];
-        args.cb[k] = obs_host[4 * k + 3];
-        // closest_point :510 / utils.py:69-76: unit((cos b, sin b, 0.0)) = scale(v, 1.0/length)
-        volatile double c = cos(beta), s = sin(beta);
-        volatile double length = sqrt(c * c + s * s + 0.0 * 0.0);
-        volatile double inv = 1.0 / length;
-        args.dirx[k] = c * inv;
-        args.diry[k] = s * inv;
-        args.okey[k] = key_of(args.cr[k]) | (key_of(args.cg[k]) << 8) | (key_of(args.cb[k]) << 16);
+    args.tab_dev = nullptr;
+    if (obs_dev != nullptr) {
+        PK_CHECK_ARG(table_ws != nullptr, "table workspace is NULL");
+        obs_table_kernel<<<1, PK_MAX_OBS, 0, st>>>(obs_dev, K, (ObsTable*)table_ws);
+        PK_LAUNCH_CHECK("obs_table_kernel");
+        args.tab_dev = (const ObsTable*)table_ws;
+    } else {
+        auto key_of = [](double c) -> unsigned {
+            if (!(c == c)) return 0u;  // NaN
+            c = c < 0.0 ? 0.0 : (c > 255.0 ? 255.0 : c);
+            return (unsigned)nearbyint(c);
+        };
+        ObsTable& T = args.tab;
+        for (int k = 0; k < PK_MAX_OBS; ++k) T.okey[k] = 0u;
+        for (int k = 0; k < K; ++k) {
+            const double beta = obs_host[4 * k + 0];
+            T.beta[k] = beta;
+            T.cr[k] = obs_host[4 * k + 1];
+            T.cg[k] = obs_host[4 * k + 2];
+            T.cb[k] = obs_host[4 * k + 3];
+            // closest_point :510 / utils.py:69-76: unit((cos b, sin b, 0.0)) = scale(v, 1.0/length)
+            volatile double c = cos(beta), s = sin(beta);
+            volatile double length = sqrt(c * c + s * s + 0.0 * 0.0);
+            volatile double inv = 1.0 / length;
+            T.dirx[k] = c * inv;
+            T.diry[k] = s * inv;
+            T.okey[k] = key_of(T.cr[k]) | (key_of(T.cg[k]) << 8) | (key_of(T.cb[k]) << 16);
+        }
     }
     // Colour screen bound (DESIGN.md "colour keys").  Keys are the colours clamped to [0,255] and
     // rounded, so per channel |key difference| <= |true difference| + 1.  If the exact gate accepts
@@ -634,4 +666,22 @@ extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, 
     args.key_thr = (int)(bound > 2.0e9 ? 2.0e9 : bound);
     if (dtype_base(dtype) == PK_DTYPE_F32) return dispatch_measure<float>(args, st);
     return dispatch_measure<double>(args, st);
+}
+
+extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype,
+                                     long long M, const double* obs_host, int K, const pk_params* params, int* assoc,
+                                     unsigned long long* stats, void* stream) {
+    PK_CHECK_ARG(K == 0 || M == 0 || obs_host != nullptr, "obs_host is NULL");
+    return measurement_common(pose4, aux2, slot, pool, capacity, dtype, M, obs_host, nullptr, nullptr, K, params, assoc,
+                              stats, stream);
+}
+
+extern "C" long long pk_obs_table_bytes(void) { return (long long)sizeof(ObsTable); }
+
+extern "C" int pk_measurement_update_dev(double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype,
+                                         long long M, const double* obs_dev, int K, const pk_params* params, int* assoc,
+                                         unsigned long long* stats, void* table_ws, void* stream) {
+    PK_CHECK_ARG(K == 0 || M == 0 || obs_dev != nullptr, "obs_dev is NULL");
+    return measurement_common(pose4, aux2, slot, pool, capacity, dtype, M, nullptr, obs_dev, table_ws, K, params, assoc,
+                              stats, stream);
 }

@@ -41,6 +41,7 @@ struct SpawnArgs {
     int K;
     int slots;
     double gate;
+    const double* obs_dev;  // device-resident scan [K][4] (pk_spawn_update_dev), else NULL
     double beta[PK_MAX_OBS], cr[PK_MAX_OBS], cg[PK_MAX_OBS], cb[PK_MAX_OBS];
 };
 
@@ -126,7 +127,10 @@ spawn_kernel(const __grid_constant__ SpawnArgs A) {
             int id_next = A.aux2[2 * q + 1] - __popcll(qmask);
             for (unsigned long long rest = qmask; rest; rest &= rest - 1ull) {
                 const int k = __ffsll((long long)rest) - 1;
-                const double beta = A.beta[k], orr = A.cr[k], og = A.cg[k], ob = A.cb[k];
+                const double beta = A.obs_dev ? A.obs_dev[4 * k] : A.beta[k];
+                const double orr = A.obs_dev ? A.obs_dev[4 * k + 1] : A.cr[k];
+                const double og = A.obs_dev ? A.obs_dev[4 * k + 2] : A.cg[k];
+                const double ob = A.obs_dev ? A.obs_dev[4 * k + 3] : A.cb[k];
                 // world-frame ray of the new reading: b2 = blob2.bearing + heading (:603)
                 const double ang = __dadd_rn(beta, pth);
                 double bd0, bd1;
@@ -231,9 +235,9 @@ using namespace pk;
 
 extern "C" {
 
-int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype, long long M,
-                    const double* obs_host, int K, const int* assoc, double pair_gate, unsigned long long* stats,
-                    void* stream) {
+static int spawn_common(const double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype, long long M,
+                        const double* obs_host, const double* obs_dev, int K, const int* assoc, double pair_gate,
+                        unsigned long long* stats, void* stream) {
     PK_CHECK_ARG(pose4 && aux2 && slot && pool, "null state pointer");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
     PK_CHECK_ARG(dtype_orphans(dtype) > 0, "dtype carries no orphan slots (PK_DTYPE_WITH_ORPHANS)");
@@ -241,8 +245,9 @@ int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool,
     PK_CHECK_ARG(K >= 0 && K <= PK_MAX_OBS, "K must be in [0, PK_MAX_OBS]");
     PK_CHECK_ARG(capacity >= 0, "capacity");
     if (M == 0 || K == 0) return PK_OK;
-    PK_CHECK_ARG(obs_host != nullptr && assoc != nullptr, "obs_host / assoc is NULL");
+    PK_CHECK_ARG((obs_host != nullptr || obs_dev != nullptr) && assoc != nullptr, "obs / assoc is NULL");
     static thread_local SpawnArgs args;
+    args.obs_dev = obs_dev;
     args.pose4 = pose4;
     args.aux2 = aux2;
     args.slot = slot;
@@ -256,7 +261,7 @@ int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool,
     args.K = K;
     args.slots = dtype_orphans(dtype);
     args.gate = pair_gate;
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K && obs_host != nullptr; ++k) {
         args.beta[k] = obs_host[4 * k + 0];
         args.cr[k] = obs_host[4 * k + 1];
         args.cg[k] = obs_host[4 * k + 2];
@@ -273,6 +278,20 @@ int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool,
         spawn_kernel<double><<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(args);
     PK_LAUNCH_CHECK("spawn_kernel");
     return PK_OK;
+}
+
+int pk_spawn_update(const double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype, long long M,
+                    const double* obs_host, int K, const int* assoc, double pair_gate, unsigned long long* stats,
+                    void* stream) {
+    PK_CHECK_ARG(K == 0 || M == 0 || obs_host != nullptr, "obs_host is NULL");
+    return spawn_common(pose4, aux2, slot, pool, capacity, dtype, M, obs_host, nullptr, K, assoc, pair_gate, stats, stream);
+}
+
+int pk_spawn_update_dev(const double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype, long long M,
+                        const double* obs_dev, int K, const int* assoc, double pair_gate, unsigned long long* stats,
+                        void* stream) {
+    PK_CHECK_ARG(K == 0 || M == 0 || obs_dev != nullptr, "obs_dev is NULL");
+    return spawn_common(pose4, aux2, slot, pool, capacity, dtype, M, nullptr, obs_dev, K, assoc, pair_gate, stats, stream);
 }
 
 int pk_orphans_export(const void* pool, int capacity, int dtype, const int* slot, long long p_lo, long long count,
