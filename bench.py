@@ -370,6 +370,8 @@ def run_ours(args):
                 "bound": "hbm", "kernel": "measure_kernel<%s>" % ("float" if args.dtype == "f32" else "double"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_kind, "traffic": traffic,
+                "limiter": "not HBM: fp64 dependent-latency / issue (12 warps per SM at 168 registers; DRAM throughput "
+                           "~27 % of peak under ncu) -- see profiles/r1_summary.md",
                 "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_kernels_ncu.csv)",
                 "algorithmic_bytes_per_launch": bytes_particle * M_local,
                 "algorithmic_bytes_per_particle": bytes_particle,
