@@ -229,17 +229,17 @@ def run_ours(args):
         exchange = args.exchange
         try:
             fs = ShardedFastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
-                                 uniform=urng.random, clock=clk, exchange=exchange)
+                                 uniform=urng.random, clock=clk, exchange=exchange, arithmetic=args.arith)
         except _lib.ParakeetLibraryError as exc:
             if exchange != "peer":
                 raise
             # CUDA IPC unavailable on this box: same filter over NCCL (both are GPU paths); say so in the line
             exchange = "nccl (peer memory unavailable: %s)" % str(exc)[:120]
             fs = ShardedFastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
-                                 uniform=urng.random, clock=clk, exchange="nccl")
+                                 uniform=urng.random, clock=clk, exchange="nccl", arithmetic=args.arith)
     else:
         fs = FastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
-                      uniform=urng.random, clock=clk)
+                      uniform=urng.random, clock=clk, arithmetic=args.arith)
     tw = messages.Twist()
     tw.linear.x, tw.angular.z = scn.v, scn.w
     fs.last_control = tw
@@ -349,14 +349,16 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": args.arith, "data": "synthetic",
             "config": {
                 "workload": "BASELINE config 2: 2^20 particles x 64 landmarks, 8 bearings/frame, single B200"
                             if world == 1 and M_local == PARTICLES_PER_GPU and N == LANDMARKS else
                             "%d particles x %d landmarks, 8 bearings/frame over %d GPU(s) (config-2 shard per GPU)"
                             % (M_total, N, world),
                 "particles": M_total, "particles_per_gpu": M_local, "landmarks": N, "blobs_per_frame": K,
-                "landmark_storage": args.dtype, "arithmetic": "fp64", "motion_noise": "philox4x32-10 on device",
+                "landmark_storage": args.dtype,
+                "arithmetic": "fp64" if args.arith == "f64" else
+                              "fp32 landmark algebra in K2 (gates, Mahalanobis forms, EKF); fp64 poses, weights, resampling", "motion_noise": "philox4x32-10 on device",
                 "resample": "systematic every frame, copy-on-resample (duplicates only)",
                 "l2": "inputs larger than L2 (%.1f GB landmark pool per GPU vs 126 MB)"
                       % (M_local * N * rec_b / 1e9),
@@ -403,6 +405,8 @@ def main(argv=None):
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="landmark storage type")
     ap.add_argument("--particles-per-gpu", type=int, default=PARTICLES_PER_GPU)
     ap.add_argument("--landmarks", type=int, default=LANDMARKS)
+    ap.add_argument("--arith", default="f64", choices=["f64", "f32"],
+                    help="arithmetic of the landmark algebra in K2 (f32 needs --dtype f32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="cross-shard exchange engine of the sharded filter (N > 1)")

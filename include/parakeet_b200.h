@@ -59,6 +59,12 @@ extern "C" {
  * [64-byte header: int total | n x 64-byte readings: double x, y, cos(ray), sin(ray), r, g, b, id]
  * follows the cold region inside the particle's block and travels with it. */
 #define PK_MAX_ORPHANS 1024
+/* Arithmetic flag of the layout code (pk_measurement_update only; needs PK_DTYPE_F32 storage): the landmark
+ * algebra of K2 -- gates, Mahalanobis forms, EKF gain and covariance update -- runs in fp32 on the fp32 records;
+ * poses, pose-landmark differences, the importance weight (its exp and the scan-order product) and everything
+ * in resampling stay fp64.  The match / no-match decision (fp64 underflow of the likelihood) is taken
+ * from the pdf exponents.  Throughput mode: >= 90 % of the reference's indices, state to fp32 rounding. */
+#define PK_DTYPE_ARITH_F32 0x1000000
 #define PK_DTYPE_WITH_ORPHANS(base, n) ((base) | ((n) << 8))
 
 #define PK_MAX_OBS 64        /* blobs per frame handled by one pk_measurement_update */

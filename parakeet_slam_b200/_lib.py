@@ -42,6 +42,7 @@ PK_STAT_SAME_LANDMARK, PK_STAT_PROMOTED, PK_STAT_SPAWNED, PK_STAT_ORPHANED = 4, 
 PK_FLAG_SINGULAR_COV, PK_FLAG_NONFINITE_WEIGHT, PK_FLAG_REPROMOTED = 1, 2, 4
 PK_FLAG_MAP_FULL, PK_FLAG_ORPHAN_EXPIRED, PK_FLAG_SPAWN_DEGENERATE = 8, 16, 32
 PK_MAX_ORPHANS = 1024
+PK_DTYPE_ARITH_F32 = 0x1000000
 
 
 def dtype_with_orphans(base: int, slots: int) -> int:

@@ -107,11 +107,23 @@ struct Landmark {
 // of orphan-reading slots per particle above it (PK_DTYPE_WITH_ORPHANS).  The orphan region
 // [64-byte header | n x 64-byte readings] follows the cold region inside the particle's block, so
 // it is copied (and migrates between ranks) with the map.
+// fp32 working copy (PK_DTYPE_ARITH_F32: fp32 landmark algebra on fp32 storage; poses, weights and the
+// resampling stay fp64).  Covariance blocks keep the stored lower triangles only.
+struct LandmarkF {
+    float x, y, r, g, b;
+    float sp[3];  // S00, S10, S11
+    float sc[6];  // C00, C10, C11, C20, C21, C22
+    int meta;
+    int id;
+};
+
 __host__ __device__ inline int dtype_base(int dtype) { return dtype & 0xff; }
 __host__ __device__ inline int dtype_orphans(int dtype) { return (dtype >> 8) & 0xffff; }
+__host__ __device__ inline bool dtype_arith_f32(int dtype) { return (dtype & PK_DTYPE_ARITH_F32) != 0; }
 __host__ __device__ inline bool dtype_valid(int dtype) {
-    return (dtype_base(dtype) == PK_DTYPE_F32 || dtype_base(dtype) == PK_DTYPE_F64) && (dtype >> 24) == 0 &&
-           dtype_orphans(dtype) <= PK_MAX_ORPHANS;
+    return (dtype_base(dtype) == PK_DTYPE_F32 || dtype_base(dtype) == PK_DTYPE_F64) &&
+           (dtype & ~(0xffffff | PK_DTYPE_ARITH_F32)) == 0 && dtype_orphans(dtype) <= PK_MAX_ORPHANS &&
+           !(dtype_arith_f32(dtype) && dtype_base(dtype) != PK_DTYPE_F32);
 }
 constexpr int kOrphanHeaderBytes = 64;  // int total (readings ever stored; ring position = total % slots)
 constexpr int kOrphanBytes = 64;        // double x, y, cos(ray), sin(ray), r, g, b, id
@@ -273,6 +285,53 @@ __device__ __forceinline__ void store_landmark<double>(unsigned char* block, int
     stcg16(cp + 144, make_int4(L.id, L.meta, 0, 0));
 }
 
+// ---- fp32 working copy <-> the 64-byte f32 record: plain bit moves, no conversions -----------------
+__device__ __forceinline__ void decode_cold_f(const int4* c, LandmarkF& L) {
+    L.r = __int_as_float(c[0].x);
+    L.g = __int_as_float(c[0].y);
+    L.b = __int_as_float(c[0].z);
+    L.x = __int_as_float(c[0].w);
+    L.y = __int_as_float(c[1].x);
+    L.sp[0] = __int_as_float(c[1].y);
+    L.sp[1] = __int_as_float(c[1].z);
+    L.sp[2] = __int_as_float(c[1].w);
+    L.sc[0] = __int_as_float(c[2].x);
+    L.sc[1] = __int_as_float(c[2].y);
+    L.sc[2] = __int_as_float(c[2].z);
+    L.sc[3] = __int_as_float(c[2].w);
+    L.sc[4] = __int_as_float(c[3].x);
+    L.sc[5] = __int_as_float(c[3].y);
+    L.id = c[3].z;
+    L.meta = c[3].w;
+}
+template <typename T>
+__device__ __forceinline__ void load_landmark(const unsigned char* block, int capacity, int j, LandmarkF& L) {
+    static_assert(sizeof(typename Rec<T>::Cold) == 64, "fp32 arithmetic needs fp32 storage");
+    const unsigned char* cp = cold_ptr<T>(block, capacity, j);
+    int4 c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = ldcg16(cp + 16 * i);
+    decode_cold_f(c, L);
+}
+__device__ __forceinline__ unsigned color_key_f(float r, float g, float b) {
+    const unsigned kr = (unsigned)__float2int_rn(fminf(fmaxf(r, 0.0f), 255.0f));
+    const unsigned kg = (unsigned)__float2int_rn(fminf(fmaxf(g, 0.0f), 255.0f));
+    const unsigned kb = (unsigned)__float2int_rn(fminf(fmaxf(b, 0.0f), 255.0f));
+    return kr | (kg << 8) | (kb << 16);
+}
+template <typename T>
+__device__ __forceinline__ void store_landmark(unsigned char* block, int capacity, int j, const LandmarkF& L) {
+    static_assert(sizeof(typename Rec<T>::Cold) == 64, "fp32 arithmetic needs fp32 storage");
+    unsigned char* cp = const_cast<unsigned char*>(cold_ptr<T>(block, capacity, j));
+#define PK_FI(v) __float_as_int(v)
+    __stcg(reinterpret_cast<unsigned*>(block) + j, color_key_f(L.r, L.g, L.b));
+    stcg16(cp, make_int4(PK_FI(L.r), PK_FI(L.g), PK_FI(L.b), PK_FI(L.x)));
+    stcg16(cp + 16, make_int4(PK_FI(L.y), PK_FI(L.sp[0]), PK_FI(L.sp[1]), PK_FI(L.sp[2])));
+    stcg16(cp + 32, make_int4(PK_FI(L.sc[0]), PK_FI(L.sc[1]), PK_FI(L.sc[2]), PK_FI(L.sc[3])));
+    stcg16(cp + 48, make_int4(PK_FI(L.sc[4]), PK_FI(L.sc[5]), L.id, L.meta));
+#undef PK_FI
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D TMA bulk copies (cp.async.bulk; SASS: UBLKCP / SYNCS)
 // ---------------------------------------------------------------------------------------------
@@ -395,6 +454,15 @@ __device__ __forceinline__ void load_staged(uint32_t rec, Landmark& L) {
 #pragma unroll
     for (int i = 0; i < kWords; ++i) c[i] = lds16_a(rec + 16 * i);
     decode_cold<T>(c, L);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_staged(uint32_t rec, LandmarkF& L) {
+    static_assert(sizeof(typename Rec<T>::Cold) == 64, "fp32 arithmetic needs fp32 storage");
+    int4 c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = lds16_a(rec + 16 * i);
+    decode_cold_f(c, L);
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {

@@ -295,6 +295,146 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     return factor;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 landmark algebra (PK_DTYPE_ARITH_F32): the same formulas on the fp32 record, symmetric blocks as
+// stored (lower triangles).  Differences pose - landmark are formed in fp64 (poses are fp64 and may be far from
+// the origin) and then rounded; the importance factor's exp and everything downstream of it is fp64.  No exp
+// is needed for the association: the reference's decision `probability > 0.0` is an fp64 underflow test
+// (finding F3), equivalent to thresholds on the two pdf exponents, and ranking several candidates by
+// bp*cp is ranking by a2 + a3.
+// ---------------------------------------------------------------------------------------------
+struct MatchPreF {
+    float a2, a3, pse;
+    bool gated;
+    bool sure;  // == the likelihood is positive in fp64: a2, a3 and a2 + a3 above log(2^-1075) = -745.13
+};
+
+constexpr float kLog2PiF = 1.8378770664093453f;
+constexpr float kUnderflowF = -745.13f;
+
+__device__ __forceinline__ MatchPreF match_prepare(const LandmarkF& L, double px, double py, double pth, float beta, float orr,
+                                                   float og, float ob, float dirx, float diry, const pk_params& prm,
+                                                   unsigned& flags) {
+    MatchPreF m;
+    const float dr = orr - L.r, dg = og - L.g, db = ob - L.b;
+    const float cdist = dr * dr + dg * dg + db * db;
+    bool gated = fabsf(cdist) > (float)prm.color_gate;                                  // :441
+    const float dx = (float)((double)L.x - px), dy = (float)((double)L.y - py);
+    const float pse = atan2f(dy, dx);                                                   // :408 / :473
+    m.pse = pse;
+    const float del = beta - (pse - (float)pth);
+    gated = gated || (fabsf(del) > (float)prm.bearing_gate);                            // :433
+    gated = gated || (fabsf(pse - beta) > (float)prm.position_gate);                    // :474
+    const float t = dx * dirx + dy * diry;                                              // closest_point :509-522
+    const float ex = (t < 0.0f) ? -dx : dirx * t - dx;                                  // near - landmark
+    const float ey = (t < 0.0f) ? -dy : diry * t - dy;
+    const float a = L.sp[0], b10 = L.sp[1], d = L.sp[2];
+    const float det2 = a * d - b10 * b10;
+    const float maha2 = (d * ex * ex - 2.0f * b10 * ex * ey + a * ey * ey) / det2;
+    const float A = L.sc[0], B = L.sc[1], C = L.sc[3], D = L.sc[2], E = L.sc[4], F = L.sc[5];
+    const float c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
+    const float c11 = A * F - C * C, c12 = B * C - A * E, c22 = A * D - B * B;
+    const float det3 = A * c00 + B * c01 + C * c02;
+    const float maha3 =
+        (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0f * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
+    if (!gated && (!(det2 > 0.0f) || !(det3 > 0.0f))) flags |= PK_FLAG_SINGULAR_COV;
+    m.gated = gated;
+    m.a2 = -0.5f * (2.0f * kLog2PiF + logf(det2) + maha2);
+    m.a3 = -0.5f * (3.0f * kLog2PiF + logf(det3) + maha3);
+    m.sure = !gated && (m.a2 > kUnderflowF) && (m.a3 > kUnderflowF) && (m.a2 + m.a3 > kUnderflowF);
+    return m;
+}
+
+// rank value: 0 = no match, otherwise increasing with the likelihood (log domain, shifted positive)
+__device__ __forceinline__ double match_finish(const MatchPreF& m) {
+    return m.sure ? (double)(m.a2 + m.a3) + 2048.0 : 0.0;
+}
+
+__device__ __forceinline__ double match_likelihood(const LandmarkF& L, double px, double py, double pth, float beta, float orr,
+                                                   float og, float ob, float dirx, float diry, const pk_params& prm,
+                                                   unsigned& flags, float& pse_out) {
+    const MatchPreF m = match_prepare(L, px, py, pth, beta, orr, og, ob, dirx, diry, prm, flags);
+    pse_out = m.pse;
+    return match_finish(m);
+}
+
+__device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double py, float beta, float orr, float og, float ob,
+                                                const pk_params& prm, int& id_out, unsigned& flags, int& promoted,
+                                                bool& changed_out, bool have_zb = false, float zb_in = 0.0f) {
+    id_out = L.id;
+    const float qt = (float)prm.qt_diag;
+    const float dx = (float)((double)L.x - px), dy = (float)((double)L.y - py);
+    const float q = dx * dx + dy * dy;                                                   // :785
+    const float hx = (q == 0.0f) ? 0.0f : dy / q;                                        // :788-797 (as written, F4b)
+    const float hy = (q == 0.0f) ? 0.0f : dx / q;
+    const float zb = have_zb ? zb_in : atan2f(dy, dx);                                   // :871 (world frame, F4a)
+    const float a = L.sp[0], b = L.sp[1], d = L.sp[2];                                   // S00, S10 (= S01), S11
+    const float t0 = hx * a + hy * b, t1 = hx * b + hy * d;
+    const float s = t0 * hx + t1 * hy + qt;                                              // :817-819
+    const float S00 = L.sc[0] + qt, S10 = L.sc[1], S11 = L.sc[2] + qt, S20 = L.sc[3], S21 = L.sc[4], S22 = L.sc[5] + qt;
+    const float inv_s = 1.0f / s;
+    // symmetric 3x3 inverse
+    const float C00 = S11 * S22 - S21 * S21, C01 = S21 * S20 - S10 * S22, C02 = S10 * S21 - S11 * S20;
+    const float detS = S00 * C00 + S10 * C01 + S20 * C02;
+    if (!(detS != 0.0f)) flags |= PK_FLAG_SINGULAR_COV;
+    const float idet = 1.0f / detS;
+    const float I00 = C00 * idet, I10 = C01 * idet, I20 = C02 * idet;
+    const float I11 = (S00 * S22 - S20 * S20) * idet, I21 = (S20 * S10 - S00 * S21) * idet, I22 = (S00 * S11 - S10 * S10) * idet;
+    const float d0 = beta - zb, d1 = orr - L.r, d2 = og - L.g, d3 = ob - L.b;          // :911 / :846, no wrapping (F4e)
+    const float fro = sqrtf(s * s + S00 * S00 + S11 * S11 + S22 * S22 + 2.0f * (S10 * S10 + S20 * S20 + S21 * S21));
+    const float y1 = d1 * I00 + d2 * I10 + d3 * I20;
+    const float y2 = d1 * I10 + d2 * I11 + d3 * I21;
+    const float y3 = d1 * I20 + d2 * I21 + d3 * I22;
+    const float maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
+    // importance_factor :844-849: the exp and the product that follows stay fp64 (weights span hundreds of decades)
+    double factor = (double)(1.0f / sqrtf(2.0f * 3.14159265358979f * fro)) * pk_exp(-0.5 * (double)maha);
+
+    bool changed = false;
+    if (!(L.meta & PK_META_IMMUTABLE)) {
+        const float kp0 = (a * hx + b * hy) * inv_s, kp1 = (b * hx + d * hy) * inv_s;  // :833
+        const float c00 = L.sc[0], c10 = L.sc[1], c11 = L.sc[2], c20 = L.sc[3], c21 = L.sc[4], c22 = L.sc[5];
+        const float K00 = c00 * I00 + c10 * I10 + c20 * I20, K01 = c00 * I10 + c10 * I11 + c20 * I21,
+                    K02 = c00 * I20 + c10 * I21 + c20 * I22;
+        const float K10 = c10 * I00 + c11 * I10 + c21 * I20, K11 = c10 * I10 + c11 * I11 + c21 * I21,
+                    K12 = c10 * I20 + c11 * I21 + c21 * I22;
+        const float K20 = c20 * I00 + c21 * I10 + c22 * I20, K21 = c20 * I10 + c21 * I11 + c22 * I21,
+                    K22 = c20 * I20 + c21 * I21 + c22 * I22;
+        L.x += kp0 * d0;                                                                  // :909-914
+        L.y += kp1 * d0;
+        L.r += K00 * d1 + K01 * d2 + K02 * d3;
+        L.g += K10 * d1 + K11 * d2 + K12 * d3;
+        L.b += K20 * d1 + K21 * d2 + K22 * d3;
+        const float m00 = 1.0f - kp0 * hx, m01 = -(kp0 * hy), m10 = -(kp1 * hx), m11 = 1.0f - kp1 * hy;   // :926-930
+        L.sp[0] = m00 * a + m01 * b;
+        L.sp[1] = m10 * a + m11 * b;
+        L.sp[2] = m10 * b + m11 * d;
+        const float A00 = 1.0f - K00, A10 = -K10, A11 = 1.0f - K11, A20 = -K20, A21 = -K21, A22 = 1.0f - K22;
+        L.sc[0] = A00 * c00 - K01 * c10 - K02 * c20;
+        L.sc[1] = A10 * c00 + A11 * c10 - K12 * c20;
+        L.sc[2] = A10 * c10 + A11 * c11 - K12 * c21;
+        L.sc[3] = A20 * c00 + A21 * c10 + A22 * c20;
+        L.sc[4] = A20 * c10 + A21 * c11 + A22 * c21;
+        L.sc[5] = A20 * c20 + A21 * c21 + A22 * c22;
+        int cnt = (L.meta & PK_META_COUNT_MASK) + 2;
+        if (cnt > PK_META_COUNT_MASK) cnt = PK_META_COUNT_MASK;
+        L.meta = (L.meta & ~PK_META_COUNT_MASK) | cnt;
+        changed = true;
+    }
+    if (id_out < 0) {
+        factor = prm.no_match_weight;
+        if (L.meta & PK_META_POTENTIAL) {
+            if ((L.meta & PK_META_COUNT_MASK) > prm.promote_count) {
+                L.meta &= ~PK_META_POTENTIAL;
+                L.id = -L.id;
+                promoted += 1;
+                changed = true;
+            }
+        }
+    }
+    changed_out = changed;
+    return factor;
+}
+
 template <typename T>
 __device__ __forceinline__ double ekf_update(unsigned char* block, int capacity, int j, double px, double py,
                                              double beta, double orr, double og, double ob, const pk_params& prm,

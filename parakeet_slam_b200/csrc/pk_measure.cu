@@ -80,17 +80,20 @@ struct MeasureArgs {
 
 // fixed part of a warp's shared memory; the key ring [kStages][group][kKeyStride] and the record
 // staging area [2][32 * R] follow at keys_off / rec_off
-struct alignas(128) WarpSmem {
+template <int R>
+struct alignas(128) WarpSmemT {
+    static constexpr int kItems = 32 * R;
     double pose[4][kMaxGroup][4];
-    double factor[kMaxItems];
-    int ids[kMaxItems];
-    int bj[kMaxItems];
+    double factor[kItems];
+    int ids[kItems];
+    int bj[kItems];
     int slot_s[4][kMaxGroup];
     int nlive_s[4][kMaxGroup];
     int nsteps_s[4];
-    int more_hits[2][kMaxItems][kMaxHits - 2];  // third and later hits of an item (rare)
+    int more_hits[2][kItems][kMaxHits - 2];  // third and later hits of an item (rare)
     uint64_t key_bar[kStages];
 };
+static_assert(kMaxItems == 64, "R <= 2");
 
 // how many candidates per item get a shared-memory staging slot: two for the 64-byte f32 record, one for f64
 template <typename T>
@@ -104,15 +107,26 @@ struct Hits {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, int R>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, PK_MEASURE_MINB)
+// LM selects the arithmetic of the landmark algebra: Landmark (fp64, every instantiation that must reproduce the
+// reference) or LandmarkF (fp32 on fp32 storage, PK_DTYPE_ARITH_F32)
+#ifndef PK_MEASURE_MINB_F32
+#define PK_MEASURE_MINB_F32 8
+#endif
+template <typename LM> struct ArithOf { using S = double; using Pre = MatchPre; static constexpr int kMinB = PK_MEASURE_MINB; };
+template <> struct ArithOf<LandmarkF> { using S = float; using Pre = MatchPreF; static constexpr int kMinB = PK_MEASURE_MINB_F32; };
+
+template <typename T, int R, typename LM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, ArithOf<LM>::kMinB)
 measure_kernel(const __grid_constant__ MeasureArgs A) {
     using Cold = typename Rec<T>::Cold;
+    using S_t = typename ArithOf<LM>::S;
+    using Pre_t = typename ArithOf<LM>::Pre;
     constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
     constexpr int kStaged = staged_candidates<T>();  // candidates per item prefetched into shared memory
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + (size_t)warp * A.warp_smem;
+    using WarpSmem = WarpSmemT<R>;
     WarpSmem& S = *reinterpret_cast<WarpSmem*>(wbase);
     const uint32_t s_base = smem_u32(wbase);
     const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
@@ -142,16 +156,16 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     }
 
     // the blob of this lane's item(s) never changes: keep its values in registers
-    double ob_beta[R], ob_r[R], ob_g[R], ob_b[R], ob_dx[R], ob_dy[R];
+    S_t ob_beta[R], ob_r[R], ob_g[R], ob_b[R], ob_dx[R], ob_dy[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int k = (it_pl[r] < GP) ? it_k[r] : 0;
-        ob_beta[r] = OT->beta[k];
-        ob_r[r] = OT->cr[k];
-        ob_g[r] = OT->cg[k];
-        ob_b[r] = OT->cb[k];
-        ob_dx[r] = OT->dirx[k];
-        ob_dy[r] = OT->diry[k];
+        ob_beta[r] = (S_t)OT->beta[k];
+        ob_r[r] = (S_t)OT->cr[k];
+        ob_g[r] = (S_t)OT->cg[k];
+        ob_b[r] = (S_t)OT->cb[k];
+        ob_dx[r] = (S_t)OT->dirx[k];
+        ob_dy[r] = (S_t)OT->diry[k];
     }
 
     if (lane == 0) {
@@ -306,9 +320,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         // this group's records were committed one group ago; the next group's may still be in flight
         if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
         // per-lane association result of the (last) evaluated round, kept in registers
-        double best_pse = 0.0;
+        S_t best_pse = 0;
         int bestj = -1, lastj = -1;
-        Landmark L;
+        LM L;
         // ---- association (:84, match_features_to_scan): every blob against the PRE-update map ----
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -319,10 +333,11 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
             const int cnt = act ? H[r].cnt : 0;
             // match_one :353-381: arg-max, strict '>' from 0.0, first (lowest slot) maximum wins
-            double best = 0.0, pse = 0.0;
-            MatchPre pre;
+            double best = 0.0;
+            S_t pse = 0;
+            Pre_t pre;
             pre.sure = false;
-            best_pse = 0.0;
+            best_pse = 0;
             bestj = -1;
             lastj = -1;
             if (cnt > 0) {
@@ -377,8 +392,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                             else
                                 load_landmark<T>(block, cap, j, L);
                             lastj = j;
-                            const double dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
-                            need = !(fabs(dr * dr + dg * dg + db * db) > A.prm.color_gate);
+                            const S_t dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
+                            need = !(fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate);
                         }
                         if (!__any_sync(kFull, need)) continue;
                         if (need) {
@@ -412,8 +427,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                             if (j >= nlive || (int)__dp4a(dk, dk, 0u) > key_thr) continue;
                             double cr_, cg_, cb_;
                             load_colour<T>(block, cap, j, cr_, cg_, cb_);
-                            const double dr = ob_r[r] - cr_, dg = ob_g[r] - cg_, db = ob_b[r] - cb_;
-                            if (fabs(dr * dr + dg * dg + db * db) > A.prm.color_gate) continue;
+                            const S_t dr = ob_r[r] - (S_t)cr_, dg = ob_g[r] - (S_t)cg_, db = ob_b[r] - (S_t)cb_;
+                            if (fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate) continue;
                             load_landmark<T>(block, cap, j, L);
                             lastj = j;
                             const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
@@ -430,7 +445,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             }
             if (R > 1 && act) {
                 S.bj[w] = bestj;
-                S.factor[w] = best_pse;
+                S.factor[w] = (double)best_pse;
             }
         }
         if (R > 1) __syncwarp();
@@ -444,7 +459,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1];
             if (R > 1) {
                 bestj = act ? S.bj[w] : -1;
-                best_pse = act ? S.factor[w] : 0.0;
+                best_pse = act ? (S_t)S.factor[w] : (S_t)0;
                 lastj = -1;  // records are re-read: an earlier round may have rewritten them
             }
             const bool matched = act && bestj >= 0;
@@ -532,35 +547,35 @@ __global__ void reset_weight_kernel(double* __restrict__ pose4, long long M) {
     if (i < M) pose4[4 * i + 3] = 1.0;  // cam_cb :73 with an empty scan
 }
 
-template <typename T, int R>
+template <typename T, int R, typename LM>
 static int launch_measure(MeasureArgs& args, cudaStream_t st) {
     static int configured_smem = -1;
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    args.keys_off = (int)align128(sizeof(WarpSmem));
+    args.keys_off = (int)align128(sizeof(WarpSmemT<R>));
     args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
     args.warp_smem = (int)align128(args.rec_off + (size_t)2 * staged_candidates<T>() * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
     if ((int)smem > configured_smem) {
-        PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, R, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_smem = (int)smem;
     }
     int ctas_per_sm = 0;
-    PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T, R>, kWarpsPerCta * 32, smem));
+    PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T, R, LM>, kWarpsPerCta * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const long long n_groups = (args.M + args.group - 1) / args.group;
     long long grid = (long long)num_sms() * ctas_per_sm;
     const long long need = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    measure_kernel<T, R><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(args);
+    measure_kernel<T, R, LM><<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(args);
     PK_LAUNCH_CHECK("measure_kernel");
     return PK_OK;
 }
 
-template <typename T>
+template <typename T, typename LM>
 static int dispatch_measure(MeasureArgs& args, cudaStream_t st) {
-    if (args.K <= 32) return launch_measure<T, 1>(args, st);
-    return launch_measure<T, 2>(args, st);
+    if (args.K <= 32) return launch_measure<T, 1, LM>(args, st);
+    return launch_measure<T, 2, LM>(args, st);
 }
 
 }  // namespace pk
@@ -664,8 +679,9 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     if (g >= 0.0) bound = floor(g + 2.0 * sqrt(3.0 * g) + 3.0) + 1.0;
     if (!(g == g)) bound = 2.0e9;  // NaN gate: `abs(cd) > nan` is False, everything passes
     args.key_thr = (int)(bound > 2.0e9 ? 2.0e9 : bound);
-    if (dtype_base(dtype) == PK_DTYPE_F32) return dispatch_measure<float>(args, st);
-    return dispatch_measure<double>(args, st);
+    if (dtype_arith_f32(dtype)) return dispatch_measure<float, LandmarkF>(args, st);
+    if (dtype_base(dtype) == PK_DTYPE_F32) return dispatch_measure<float, Landmark>(args, st);
+    return dispatch_measure<double, Landmark>(args, st);
 }
 
 extern "C" int pk_measurement_update(double* pose4, int* aux2, const int* slot, void* pool, int capacity, int dtype,

@@ -271,3 +271,81 @@ def test_spawn_ring_and_capacity_flags(lib):
     assert int(fs.aux[:, 0].max()) == 2
     p = fs.particles[0]                                # host view: potential / full landmarks and hypothesis_set
     assert len(p.feature_set) + len(p.potential_features) <= 2 and 0 < len(p.hypothesis_set) <= 32
+
+
+# ---- fp32 landmark algebra (PK_DTYPE_ARITH_F32): the throughput instantiation --------------------------------
+@pytest.mark.parametrize("name", TRACE_FIXTURES)
+def test_trace_f32_arithmetic(lib, name):
+    """fp32 storage AND fp32 landmark algebra (poses, weights, resampling stay fp64): >= 90 % of the reference's
+    association / resampling indices (BASELINE.json target), frame 0 identical, weights of frame 0 to 1e-3."""
+    from device_harness import run_device
+    g = load_trace(name)
+    scn = scenario_from_trace(g)
+    pot = tuple(int(j) for j in g["potential_slots"]) if "potential_slots" in g.files else ()
+    tr = run_device(scn, "f32", potential_slots=pot, arithmetic="f32")
+    a, r = _check_trace(tr, g, (), exact=False, tol_state=1e-5, tol_weight=1e-3, min_index_match=0.90)
+    assert np.array_equal(tr["assoc"][0], g["assoc"][0])
+    assert np.array_equal(tr["ancestors"][0], g["ancestors"][0])
+    big = g["weight"][0] > 1e-300
+    assert _rel(tr["weight"][0][big], g["weight"][0][big]) < 1e-3
+    print("fp32 arithmetic, %s: assoc %.4f ancestors %.4f identical" % (name, a, r))
+
+
+def test_f32_arithmetic_state_against_oracle(lib):
+    """One frame from identical state, 4096 particles: what fp32 algebra does to a single update -- associations
+    identical, weights to 1e-4 relative, landmark means to 1e-5 relative (BASELINE tolerance), covariances to 1e-5
+    absolute; then 10 frames: indices >= 90 % identical, pose estimate unchanged to 1e-3 m."""
+    import random
+    import torch
+    from device_harness import make_features
+    from oracle import fastslam_np as onp
+    from parakeet_slam_b200.core import FastSLAM
+    from parakeet_slam_b200.rosless import Time, messages
+    from parakeet_slam_b200.scenario import DT_NSEC, make_scenario
+    M, N, T = 4096, 64, 10
+    scn = make_scenario("c2", num_particles=M, num_landmarks=N, frames=T)
+    rs = np.random.RandomState(5)
+    blocks = [rs.standard_normal((M, 3)) for _ in range(T)]
+    it = iter(blocks)
+
+    class Clk(object):
+        ns = 0
+
+        def __call__(self):
+            return Time(0, self.ns)
+    clk = Clk()
+    urng = random.Random(8)
+    fs = FastSLAM(make_features(scn), num_particles=M, dtype="f32", arithmetic="f32", noise=lambda m: next(it),
+                  uniform=urng.random, clock=clk)
+    fs.keep_trace = True
+    tw = messages.Twist()
+    tw.linear.x, tw.angular.z = scn.v, scn.w
+    fs.last_control = tw
+    st = onp.OracleState(M, scn.landmarks, preset_covar=scn.preset_covar)
+    urng2 = random.Random(8)
+    match = []
+    for t in range(T):
+        clk.ns += DT_NSEC
+        fs.motion_update(tw)
+        fs.measurement_update(scn.observations[t])
+        if t == 0:
+            mean5, covp, covc, meta, ids_, nlive = fs.export_maps()
+            w0 = fs.pose[:, 3].cpu().numpy()
+        fs.low_variance_resample()
+        if t == 0:
+            st0 = st.copy()
+            st0.pose = onp.motion_update(st0.pose, blocks[0], scn.v, scn.w, scn.dt)
+            ids0 = onp.measurement_update(st0, scn.observations[0])
+            assert np.array_equal(fs.last_assoc.cpu().numpy(), ids0)
+            assert np.max(np.abs(w0 - st0.weight) / st0.weight) < 1e-4
+            assert np.max(np.abs(mean5 - st0.mean) / np.maximum(np.abs(st0.mean), 1e-3)) < 1e-5
+            assert np.max(np.abs(covp - st0.cov[..., :2, :2])) < 1e-5
+            assert np.max(np.abs(covc - st0.cov[..., 2:, 2:])) < 1e-5
+        ids, wgt, anc, _ = onp.frame(st, scn.observations[t], blocks[t], scn.v, scn.w, scn.dt, urng2.random(),
+                                     sequential_resample=False)
+        match.append((float((fs.last_assoc.cpu().numpy() == ids).mean()),
+                      float((fs.last_ancestors.cpu().numpy() == anc).mean())))
+    assert min(m for m, _ in match) >= 0.90 and min(r for _, r in match) >= 0.90, match
+    est, ref = np.array(fs.summary()), np.array(onp.summary(st.pose))
+    assert np.max(np.abs(est - ref)) < 1e-3
+    assert fs.stats()["flags"] == 0
