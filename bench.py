@@ -320,11 +320,51 @@ def run_ours(args):
     sync_all()
     e2e_ms = max(e_start.elapsed_time(e_stop), 1e3 * (time.perf_counter() - t0))
 
+    # ---- the same steps with fp64 landmark algebra (the 100 %-index-parity instantiation), for the record ------
+    alt_ms_total = alt_ms_measure = 0.0
+    alt = None
+    if args.arith == "f32" and not args.no_f64_block:
+        urng_alt = random.Random(12345)
+        clk_alt = _Clock()
+        if world > 1:
+            fs.close()
+            fs_alt = ShardedFastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
+                                     uniform=urng_alt.random, clock=clk_alt, arithmetic="f64",
+                                     exchange=exchange if exchange in ("peer", "nccl") else "nccl")
+        else:
+            fs_alt = FastSLAM(feats, num_particles=M_total, dtype=args.dtype, noise="philox", seed=2024,
+                              uniform=urng_alt.random, clock=clk_alt, arithmetic="f64")
+        fs_alt.last_control = tw
+
+        def alt_step(t, events=None):
+            clk_alt.ns += DT_NSEC
+            fs_alt.motion_update(tw)
+            if events:
+                events[0].record()
+            fs_alt.measurement_update(scn.observations[t])
+            if events:
+                events[1].record()
+            fs_alt.low_variance_resample()
+        for t in range(warm + (8 if world > 1 else 0)):
+            alt_step(t)
+        sync_all()
+        a0, a1 = ev(), ev()
+        alt_events = [[ev(), ev()] for _ in range(steps)]
+        a0.record()
+        for s_ in range(steps):
+            alt_step(warm + s_, alt_events[s_])
+        a1.record()
+        sync_all()
+        alt_ms_total = a0.elapsed_time(a1)
+        alt_ms_measure = sum(e[0].elapsed_time(e[1]) for e in alt_events) / steps
+        alt = True
+
     # ---- reduce over ranks: max time -------------------------------------------------------------
-    times = torch.tensor([ms_total, e2e_ms, ms_measure, ms_motion, ms_resample], dtype=torch.float64, device="cuda")
+    times = torch.tensor([ms_total, e2e_ms, ms_measure, ms_motion, ms_resample, alt_ms_total, alt_ms_measure],
+                         dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, ms_measure, ms_motion, ms_resample = [float(x) for x in times.cpu()]
+    ms_total, e2e_ms, ms_measure, ms_motion, ms_resample, alt_ms_total, alt_ms_measure = [float(x) for x in times.cpu()]
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -341,7 +381,7 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
-                tr = json.load(fh)["measure_kernel<float>"]
+                tr = json.load(fh)["measure_kernel<float,f32>" if args.arith == "f32" else "measure_kernel<float>"]
             if (args.dtype, M_local, N, K) == (tr["dtype"], tr["particles_per_gpu"], tr["landmarks"], tr["blobs"]):
                 traffic = tr["dram_bytes"]
         except Exception:
@@ -369,11 +409,14 @@ def run_ours(args):
             },
             "kernel_ms": {"motion": ms_motion, "measure": ms_measure, "resample_total": ms_resample},
             "roofline": {
-                "bound": "hbm", "kernel": "measure_kernel<%s>" % ("float" if args.dtype == "f32" else "double"),
+                "bound": "hbm", "kernel": "measure_kernel<%s%s>" % ("float" if args.dtype == "f32" else "double",
+                                                                   ", fp32 algebra" if args.arith == "f32" else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_kind, "traffic": traffic,
-                "limiter": "not HBM: fp64 dependent-latency / issue (12 warps per SM at 168 registers; DRAM throughput "
-                           "~27 % of peak under ncu) -- see profiles/r1_summary.md",
+                "limiter": ("fp32 landmark algebra: instruction issue (~65 % busy) with 16 warps per SM; DRAM traffic per "
+                            "launch / K2 time is the HBM utilisation -- see profiles/r1_summary.md") if args.arith == "f32"
+                           else ("not HBM: fp64 dependent-latency / issue (12 warps per SM at 168 registers; DRAM "
+                                 "throughput ~27 % of peak under ncu) -- see profiles/r1_summary.md"),
                 "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_kernels_ncu.csv)",
                 "algorithmic_bytes_per_launch": bytes_particle * M_local,
                 "algorithmic_bytes_per_particle": bytes_particle,
@@ -388,6 +431,14 @@ def run_ours(args):
             "clocks": clocks,
             "summary_last": list(est),
         }
+        if alt:
+            line["f64_arithmetic"] = {
+                "note": "same workload and steps with fp64 landmark algebra (FastSLAM(arithmetic='f64')): the instantiation "
+                        "whose indices are bit-exact on every reference fixture with fp64 storage",
+                "value": updates / (alt_ms_total * 1e-3), "unit": UNIT, "ms_per_step": alt_ms_total / steps,
+                "measure_ms": alt_ms_measure,
+                "roofline_frac": bytes_particle * M_local / (alt_ms_measure * 1e-3) / 1e9 / peak,
+            }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -405,9 +456,11 @@ def main(argv=None):
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="landmark storage type")
     ap.add_argument("--particles-per-gpu", type=int, default=PARTICLES_PER_GPU)
     ap.add_argument("--landmarks", type=int, default=LANDMARKS)
-    ap.add_argument("--arith", default="f64", choices=["f64", "f32"],
-                    help="arithmetic of the landmark algebra in K2 (f32 needs --dtype f32)")
+    ap.add_argument("--arith", default="f32", choices=["f64", "f32"],
+                    help="arithmetic of the landmark algebra in K2 (f32 needs --dtype f32); poses, weights and "
+                         "resampling are fp64 either way")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-f64-block", action="store_true", help="skip the secondary fp64-arithmetic measurement")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="cross-shard exchange engine of the sharded filter (N > 1)")
     args = ap.parse_args(argv)

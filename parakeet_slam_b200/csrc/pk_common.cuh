@@ -252,16 +252,24 @@ __device__ __forceinline__ void load_landmark(const unsigned char* block, int ca
 template <typename T>
 __device__ __forceinline__ void load_staged(uint32_t rec, Landmark& L);
 
+// kNoKey: "previous key unknown, always store it".  A 4-byte key store dirties a whole 32-byte sector (one
+// fill read + one write back per sector); the key of a landmark that is merely refined almost never changes, so
+// callers that know the previous key pass it and the store is skipped when it is still right.
+constexpr unsigned kNoKey = 0xffffffffu;
+
 template <typename T>
-__device__ __forceinline__ void store_landmark(unsigned char* block, int capacity, int j, const Landmark& L);
+__device__ __forceinline__ void store_landmark(unsigned char* block, int capacity, int j, const Landmark& L,
+                                               unsigned old_key = kNoKey);
 
 template <>
-__device__ __forceinline__ void store_landmark<float>(unsigned char* block, int capacity, int j, const Landmark& L) {
+__device__ __forceinline__ void store_landmark<float>(unsigned char* block, int capacity, int j, const Landmark& L,
+                                                      unsigned old_key) {
     unsigned char* cp = const_cast<unsigned char*>(cold_ptr<float>(block, capacity, j));
 #define PK_F(v) __float_as_int((float)(v))
     const float fr = (float)L.r, fg = (float)L.g, fb = (float)L.b;
     // the key is derived from the STORED (rounded) colour so screen and exact test see one value
-    __stcg(reinterpret_cast<unsigned*>(block) + j, color_key((double)fr, (double)fg, (double)fb));
+    const unsigned key = color_key((double)fr, (double)fg, (double)fb);
+    if (key != old_key) __stcg(reinterpret_cast<unsigned*>(block) + j, key);
     stcg16(cp, make_int4(__float_as_int(fr), __float_as_int(fg), __float_as_int(fb), PK_F(L.x)));
     stcg16(cp + 16, make_int4(PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[2]), PK_F(L.sp[3])));
     stcg16(cp + 32, make_int4(PK_F(L.sc[0]), PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[6])));
@@ -270,9 +278,11 @@ __device__ __forceinline__ void store_landmark<float>(unsigned char* block, int 
 }
 
 template <>
-__device__ __forceinline__ void store_landmark<double>(unsigned char* block, int capacity, int j, const Landmark& L) {
+__device__ __forceinline__ void store_landmark<double>(unsigned char* block, int capacity, int j, const Landmark& L,
+                                                       unsigned old_key) {
     unsigned char* cp = const_cast<unsigned char*>(cold_ptr<double>(block, capacity, j));
-    __stcg(reinterpret_cast<unsigned*>(block) + j, color_key(L.r, L.g, L.b));
+    const unsigned key = color_key(L.r, L.g, L.b);
+    if (key != old_key) __stcg(reinterpret_cast<unsigned*>(block) + j, key);
     stcg16(cp, mk_i4(L.r, L.g));
     stcg16(cp + 16, mk_i4(L.b, L.x));
     stcg16(cp + 32, mk_i4(L.y, L.sp[0]));
@@ -320,11 +330,13 @@ __device__ __forceinline__ unsigned color_key_f(float r, float g, float b) {
     return kr | (kg << 8) | (kb << 16);
 }
 template <typename T>
-__device__ __forceinline__ void store_landmark(unsigned char* block, int capacity, int j, const LandmarkF& L) {
+__device__ __forceinline__ void store_landmark(unsigned char* block, int capacity, int j, const LandmarkF& L,
+                                               unsigned old_key = kNoKey) {
     static_assert(sizeof(typename Rec<T>::Cold) == 64, "fp32 arithmetic needs fp32 storage");
     unsigned char* cp = const_cast<unsigned char*>(cold_ptr<T>(block, capacity, j));
 #define PK_FI(v) __float_as_int(v)
-    __stcg(reinterpret_cast<unsigned*>(block) + j, color_key_f(L.r, L.g, L.b));
+    const unsigned key = color_key_f(L.r, L.g, L.b);
+    if (key != old_key) __stcg(reinterpret_cast<unsigned*>(block) + j, key);
     stcg16(cp, make_int4(PK_FI(L.r), PK_FI(L.g), PK_FI(L.b), PK_FI(L.x)));
     stcg16(cp + 16, make_int4(PK_FI(L.y), PK_FI(L.sp[0]), PK_FI(L.sp[1]), PK_FI(L.sp[2])));
     stcg16(cp + 32, make_int4(PK_FI(L.sc[0]), PK_FI(L.sc[1]), PK_FI(L.sc[2]), PK_FI(L.sc[3])));
@@ -455,6 +467,13 @@ __device__ __forceinline__ void load_staged(uint32_t rec, Landmark& L) {
     for (int i = 0; i < kWords; ++i) c[i] = lds16_a(rec + 16 * i);
     decode_cold<T>(c, L);
 }
+
+// key the record currently has in the hot region (always derived from the stored colour)
+__device__ __forceinline__ unsigned stored_key(const Landmark& L, int dtype_tag) {
+    if (dtype_tag == PK_DTYPE_F32) return color_key((double)(float)L.r, (double)(float)L.g, (double)(float)L.b);
+    return color_key(L.r, L.g, L.b);
+}
+__device__ __forceinline__ unsigned stored_key(const LandmarkF& L, int) { return color_key_f(L.r, L.g, L.b); }
 
 template <typename T>
 __device__ __forceinline__ void load_staged(uint32_t rec, LandmarkF& L) {

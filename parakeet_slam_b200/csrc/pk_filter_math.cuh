@@ -303,6 +303,26 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
 // (finding F3), equivalent to thresholds on the two pdf exponents, and ranking several candidates by
 // bp*cp is ranking by a2 + a3.
 // ---------------------------------------------------------------------------------------------
+// Branch-free atan2 in fp32: the reduction of pk_atan2 (one division, |t| <= tan(pi/8)) with the degree-9 odd
+// polynomial of Cephes' atanf (error < 2e-7 rad); fast division (2 ulp).
+__device__ __forceinline__ float pk_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool steep = ay > ax;
+    const float mx = steep ? ay : ax, mn = steep ? ax : ay;
+    const bool big = mn > 0.41421356f * mx;
+    const float num = big ? mn - mx : mn;
+    const float den = big ? mn + mx : mx;
+    float t = __fdividef(num, den);
+    if (den == 0.0f) t = 0.0f;
+    const float z = t * t;
+    const float p = ((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f;
+    float r = fmaf(t * z, p, t);
+    if (big) r += 0.78539816339744831f;
+    if (steep) r = 1.57079632679489662f - r;
+    if (signbit(x)) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
 struct MatchPreF {
     float a2, a3, pse;
     bool gated;
@@ -320,7 +340,7 @@ __device__ __forceinline__ MatchPreF match_prepare(const LandmarkF& L, double px
     const float cdist = dr * dr + dg * dg + db * db;
     bool gated = fabsf(cdist) > (float)prm.color_gate;                                  // :441
     const float dx = (float)((double)L.x - px), dy = (float)((double)L.y - py);
-    const float pse = atan2f(dy, dx);                                                   // :408 / :473
+    const float pse = pk_atan2f(dy, dx);                                                // :408 / :473
     m.pse = pse;
     const float del = beta - (pse - (float)pth);
     gated = gated || (fabsf(del) > (float)prm.bearing_gate);                            // :433
@@ -330,17 +350,18 @@ __device__ __forceinline__ MatchPreF match_prepare(const LandmarkF& L, double px
     const float ey = (t < 0.0f) ? -dy : diry * t - dy;
     const float a = L.sp[0], b10 = L.sp[1], d = L.sp[2];
     const float det2 = a * d - b10 * b10;
-    const float maha2 = (d * ex * ex - 2.0f * b10 * ex * ey + a * ey * ey) / det2;
+    const float maha2 = __fdividef(d * ex * ex - 2.0f * b10 * ex * ey + a * ey * ey, det2);
     const float A = L.sc[0], B = L.sc[1], C = L.sc[3], D = L.sc[2], E = L.sc[4], F = L.sc[5];
     const float c00 = D * F - E * E, c01 = C * E - B * F, c02 = B * E - C * D;
     const float c11 = A * F - C * C, c12 = B * C - A * E, c22 = A * D - B * B;
     const float det3 = A * c00 + B * c01 + C * c02;
-    const float maha3 =
-        (c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0f * (c01 * dr * dg + c02 * dr * db + c12 * dg * db)) / det3;
+    const float maha3 = __fdividef(
+        c00 * dr * dr + c11 * dg * dg + c22 * db * db + 2.0f * (c01 * dr * dg + c02 * dr * db + c12 * dg * db), det3);
     if (!gated && (!(det2 > 0.0f) || !(det3 > 0.0f))) flags |= PK_FLAG_SINGULAR_COV;
     m.gated = gated;
-    m.a2 = -0.5f * (2.0f * kLog2PiF + logf(det2) + maha2);
-    m.a3 = -0.5f * (3.0f * kLog2PiF + logf(det3) + maha3);
+    // the exponents only feed decisions and rankings: the hardware log2 (abs. error ~1e-6 in the log) is enough
+    m.a2 = -0.5f * (2.0f * kLog2PiF + __logf(det2) + maha2);
+    m.a3 = -0.5f * (3.0f * kLog2PiF + __logf(det3) + maha3);
     m.sure = !gated && (m.a2 > kUnderflowF) && (m.a3 > kUnderflowF) && (m.a2 + m.a3 > kUnderflowF);
     return m;
 }
@@ -365,19 +386,21 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
     const float qt = (float)prm.qt_diag;
     const float dx = (float)((double)L.x - px), dy = (float)((double)L.y - py);
     const float q = dx * dx + dy * dy;                                                   // :785
-    const float hx = (q == 0.0f) ? 0.0f : dy / q;                                        // :788-797 (as written, F4b)
-    const float hy = (q == 0.0f) ? 0.0f : dx / q;
-    const float zb = have_zb ? zb_in : atan2f(dy, dx);                                   // :871 (world frame, F4a)
+    const float inv_q = __fdividef(1.0f, q);
+    const float hx = (q == 0.0f) ? 0.0f : dy * inv_q;                                    // :788-797 (as written, F4b)
+    const float hy = (q == 0.0f) ? 0.0f : dx * inv_q;
+    float zb = zb_in;                                                                    // :871 (world frame, F4a)
+    if (!have_zb) zb = pk_atan2f(dy, dx);
     const float a = L.sp[0], b = L.sp[1], d = L.sp[2];                                   // S00, S10 (= S01), S11
     const float t0 = hx * a + hy * b, t1 = hx * b + hy * d;
     const float s = t0 * hx + t1 * hy + qt;                                              // :817-819
     const float S00 = L.sc[0] + qt, S10 = L.sc[1], S11 = L.sc[2] + qt, S20 = L.sc[3], S21 = L.sc[4], S22 = L.sc[5] + qt;
-    const float inv_s = 1.0f / s;
+    const float inv_s = __fdividef(1.0f, s);
     // symmetric 3x3 inverse
     const float C00 = S11 * S22 - S21 * S21, C01 = S21 * S20 - S10 * S22, C02 = S10 * S21 - S11 * S20;
     const float detS = S00 * C00 + S10 * C01 + S20 * C02;
     if (!(detS != 0.0f)) flags |= PK_FLAG_SINGULAR_COV;
-    const float idet = 1.0f / detS;
+    const float idet = __fdividef(1.0f, detS);
     const float I00 = C00 * idet, I10 = C01 * idet, I20 = C02 * idet;
     const float I11 = (S00 * S22 - S20 * S20) * idet, I21 = (S20 * S10 - S00 * S21) * idet, I22 = (S00 * S11 - S10 * S10) * idet;
     const float d0 = beta - zb, d1 = orr - L.r, d2 = og - L.g, d3 = ob - L.b;          // :911 / :846, no wrapping (F4e)
@@ -387,7 +410,7 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
     const float y3 = d1 * I20 + d2 * I21 + d3 * I22;
     const float maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
     // importance_factor :844-849: the exp and the product that follows stay fp64 (weights span hundreds of decades)
-    double factor = (double)(1.0f / sqrtf(2.0f * 3.14159265358979f * fro)) * pk_exp(-0.5 * (double)maha);
+    double factor = (double)rsqrtf(2.0f * 3.14159265358979f * fro) * pk_exp(-0.5 * (double)maha);
 
     bool changed = false;
     if (!(L.meta & PK_META_IMMUTABLE)) {

@@ -96,9 +96,12 @@ struct alignas(128) WarpSmemT {
 static_assert(kMaxItems == 64, "R <= 2");
 
 // how many candidates per item get a shared-memory staging slot: two for the 64-byte f32 record, one for f64
-template <typename T>
+#ifndef PK_STAGED_F32
+#define PK_STAGED_F32 2
+#endif
+template <typename T, typename LM = Landmark>
 __host__ __device__ constexpr int staged_candidates() {
-    return sizeof(typename Rec<T>::Cold) <= 64 ? 2 : 1;
+    return sizeof(LM) == sizeof(LandmarkF) ? PK_STAGED_F32 : (sizeof(typename Rec<T>::Cold) <= 64 ? 2 : 1);
 }
 
 // per-item screen result, kept in registers between screen(g) and evaluate(g)
@@ -122,7 +125,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     using S_t = typename ArithOf<LM>::S;
     using Pre_t = typename ArithOf<LM>::Pre;
     constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
-    constexpr int kStaged = staged_candidates<T>();  // candidates per item prefetched into shared memory
+    constexpr int kStaged = staged_candidates<T, LM>();  // candidates per item prefetched into shared memory
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + (size_t)warp * A.warp_smem;
@@ -263,6 +266,10 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 const int nl = act ? max(0, min(kChunk, S.nlive_s[gi][pl] - step * kChunk)) : 0;
                 const uint32_t kp = s_keys + ((stage * (unsigned)GP + (unsigned)pl) * kKeyStride) * 4u;
                 const unsigned mykey = it_key[r];
+                // three integer instructions per key: |difference| per byte, dot product accumulated onto
+                // -(threshold + 1) (negative <=> inside the bound), and a funnel shift that pushes the sign bit
+                // into the hit mask (key i of a 32-key half ends up at bit 31 - i: reversed afterwards)
+                const unsigned neg_thr1 = (unsigned)(-(key_thr + 1));
                 unsigned lo = 0u, hi = 0u;
 #pragma unroll
                 for (int q = 0; q < kChunk / 4; ++q) {
@@ -271,14 +278,11 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const unsigned d = __vabsdiffu4(kk[e], mykey);
-                        const int sq = (int)__dp4a(d, d, 0u);
-                        const int bit = 4 * q + e;
-                        if (sq <= key_thr) {
-                            if (bit < 32) lo |= 1u << (bit & 31); else hi |= 1u << (bit & 31);
-                        }
+                        const unsigned sgn = __dp4a(d, d, neg_thr1);
+                        if (4 * q + e < 32) lo = __funnelshift_l(sgn, lo, 1); else hi = __funnelshift_l(sgn, hi, 1);
                     }
                 }
-                unsigned long long m = ((unsigned long long)hi << 32) | lo;
+                unsigned long long m = ((unsigned long long)__brev(hi) << 32) | __brev(lo);
                 m &= (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);  // keys beyond n_live are stale
                 while (m) {  // about one hit per item
                     const int j = step * kChunk + __ffsll((long long)m) - 1;
@@ -292,19 +296,30 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             __syncwarp();  // every lane is done with this key stage before it is refilled
             ++s_cnt;
         }
-        // request the cold record of each item's first hit into the lane's own staging slot:
-        // per-lane addresses -> cp.async (LDGSTS), one commit group per screened group
+        // request the cold record of each item's first hit(s) into the lane's staging slot.  The 32 slots of a
+        // round are consecutive in shared memory, so the warp fetches them TOGETHER: instruction i moves 16-byte
+        // chunk i*32+lane of that 32-record strip, i.e. the lanes of one instruction cover whole records and every
+        // 32-byte sector is requested once.  (Each lane copying its own record 16 bytes at a time asks L2 for every
+        // sector twice, from different instructions; the second request missed as well and DRAM read the records
+        // twice -- 1.53 GB instead of ~1 GB per launch under ncu.)
+        constexpr int kChunksPerRec = (int)(kRecBytes / 16u);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int c = 0; c < kStaged; ++c) {
-                if (H[r].cnt > c) {
-                    const unsigned char* src = cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap,
-                                                           c == 0 ? H[r].c0 : H[r].c1);
-                    const uint32_t dst =
-                        s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
+                const bool have = H[r].cnt > c;
+                unsigned long long src = 0ull;
+                if (have)
+                    src = (unsigned long long)cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap,
+                                                          c == 0 ? H[r].c0 : H[r].c1);
+                if (!__any_sync(kFull, have)) continue;
+                const uint32_t strip = s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)(r * 32)) * kRecBytes;
 #pragma unroll
-                    for (unsigned q = 0; q < kRecBytes / 16u; ++q) cp_async16_a(dst + 16u * q, src + 16u * q);
+                for (int i = 0; i < kChunksPerRec; ++i) {
+                    const int chunk = i * 32 + lane;
+                    const int rec = chunk / kChunksPerRec, part = chunk - rec * kChunksPerRec;
+                    const unsigned long long sp = __shfl_sync(kFull, src, rec);
+                    if (sp) cp_async16_a(strip + 16u * (unsigned)chunk, reinterpret_cast<const unsigned char*>(sp) + 16 * part);
                 }
             }
         }
@@ -480,9 +495,13 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     bool changed = false;
                     // the bearing computed during association is that of the PRE-update landmark: it can be
                     // re-used only if no earlier blob of this frame has moved the landmark since
+                    // L holds the stored colours here, so its key is the one in the hot region: the fp32 instantiation is
+                    // memory-latency bound and skips the key store when the update leaves the key alone (-8 % K2 time,
+                    // ~0.5 GB less DRAM traffic per launch); the fp64 one is issue bound, where the extra key costs 2 %
+                    const unsigned key_before = (sizeof(LM) == sizeof(LandmarkF)) ? stored_key(L, Rec<T>::kDtype) : kNoKey;
                     factor = ekf_update_lm(L, px, py, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], A.prm, id_out, st_flags,
                                            promoted, changed, !fresh, best_pse);
-                    if (changed) store_landmark<T>(block, cap, bestj, L);
+                    if (changed) store_landmark<T>(block, cap, bestj, L, key_before);
                     st_promoted += promoted;
                     if (q > 0) st_same += 1;
                 }
@@ -490,24 +509,41 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             }
             if (act) {
                 A.assoc[(p0 + pl) * K + k] = id_out;
-                S.factor[w] = factor;
-                S.ids[w] = id_out;
+                if (R > 1) {
+                    S.factor[w] = factor;
+                    S.ids[w] = id_out;
+                }
                 if (matched) st_matched += 1; else st_unmatched += 1;
             }
-        }
-        __syncwarp();
-        if (lane < gpn) {
-            // particles[i].weight = 1 (:73); weight *= factor in scan order (:95, :124)
-            double wgt = 1.0;
-            int orphans = 0;
-            for (int k = 0; k < K; ++k) {
-                wgt *= S.factor[lane * K + k];
-                orphans += (S.ids[lane * K + k] == 0);
+            if (R == 1) {
+                // particles[i].weight = 1 (:73); weight *= factor in scan order (:95, :124): every lane folds the K
+                // factors of its own particle (lanes pl*K .. pl*K+K-1), the particle's first lane stores
+                const int base = pl * K;
+                double wgt = 1.0;
+                for (int k2 = 0; k2 < K; ++k2) wgt *= __shfl_sync(kFull, factor, base + k2);
+                const unsigned unseen = __ballot_sync(kFull, act && id_out == 0);
+                if (act && k == 0) {
+                    if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
+                    A.pose4[4 * (p0 + pl) + 3] = wgt;
+                    // add_orphaned_reading bumps next_id once per unseen blob (:745-746)
+                    const int orphans = __popc((unseen >> base) & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)));
+                    if (orphans) A.aux2[2 * (p0 + pl) + 1] += orphans;
+                }
             }
-            if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
-            A.pose4[4 * (p0 + lane) + 3] = wgt;
-            // add_orphaned_reading bumps next_id once per unseen blob (:745-746)
-            if (orphans) A.aux2[2 * (p0 + lane) + 1] += orphans;
+        }
+        if (R > 1) {
+            __syncwarp();
+            if (lane < gpn) {
+                double wgt = 1.0;
+                int orphans = 0;
+                for (int k = 0; k < K; ++k) {
+                    wgt *= S.factor[lane * K + k];
+                    orphans += (S.ids[lane * K + k] == 0);
+                }
+                if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
+                A.pose4[4 * (p0 + lane) + 3] = wgt;
+                if (orphans) A.aux2[2 * (p0 + lane) + 1] += orphans;
+            }
         }
         __syncwarp();
     };
@@ -553,7 +589,7 @@ static int launch_measure(MeasureArgs& args, cudaStream_t st) {
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     args.keys_off = (int)align128(sizeof(WarpSmemT<R>));
     args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
-    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * staged_candidates<T>() * 32 * R * sizeof(typename Rec<T>::Cold));
+    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * staged_candidates<T, LM>() * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
     if ((int)smem > configured_smem) {
         PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, R, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -24,7 +24,8 @@ namespace pk {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kScanWarps = 4;
-constexpr int kGroupBlocks = 32;   // scan blocks folded sequentially by one thread in K3b
+constexpr int kMinGroupBlocks = 8;  // scan blocks folded sequentially by one thread in K3b (doubles while > 1024 groups)
+constexpr int kMaxGroupBlocks = 32;
 constexpr int kMaxScanGroups = 1024;
 
 __device__ __forceinline__ int padded(int e) { return e + (e >> 5); }
@@ -103,7 +104,7 @@ __device__ __forceinline__ long long count_le(dd P, double c, double u0, double 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_total, double u01,
-                  double* __restrict__ plan, double* block_prefix, long long* block_count) {
+                  double* __restrict__ plan, double* block_prefix, long long* block_count, int kGroupBlocks) {
     __shared__ double g_hi[kMaxScanGroups], g_lo[kMaxScanGroups];
     __shared__ long long g_cnt[kMaxScanGroups];
     __shared__ double s_r, s_u0;
@@ -114,7 +115,7 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
     // phase A: per-thread sequential double-double fold of its group's block totals
     // (loads are issued eight at a time so the fold does not pay one L2 round trip per block)
     constexpr int kBatch = 8;
-    static_assert(kGroupBlocks % kBatch == 0, "batch size");
+    static_assert(kMinGroupBlocks % kBatch == 0, "batch size");
     dd acc{0.0, 0.0};
     if (t < ngroups) {
         for (long long bb = b0; bb < b1; bb += kBatch) {
@@ -313,25 +314,32 @@ dead_scan_kernel(const int* __restrict__ offspring, long long M, int* __restrict
 __global__ void __launch_bounds__(1024)
 block_offsets_kernel(const int* __restrict__ block_dead, long long nb, int* __restrict__ block_off,
                      long long* __restrict__ total_out) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x;
+    __shared__ int warp_tot[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long per = (nb + 1023) / 1024;
     const long long b0 = t * per, b1 = min(nb, b0 + per);
     int s = 0;
     for (long long b = b0; b < b1; ++b) s += block_dead[b];
-    part[t] = s;
+    // exclusive scan of the 1024 per-thread sums: warp scan, then a scan of the 32 warp totals
+    int incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (t == 0) {
-        int run = 0;
-        for (int q = 0; q < 1024; ++q) {
-            const int cur = part[q];
-            part[q] = run;
-            run += cur;
+    if (warp == 0) {
+        const int wt = warp_tot[lane];
+        int wi = wt;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFullMask, wi, o);
+            if (lane >= o) wi += v;
         }
-        if (total_out) *total_out = run;
+        warp_tot[lane] = wi - wt;  // exclusive
+        if (lane == 31 && total_out) *total_out = wi;
     }
     __syncthreads();
-    int run = part[t];
+    int run = warp_tot[warp] + incl - s;
     for (long long b = b0; b < b1; ++b) {
         block_off[b] = run;
         run += block_dead[b];
@@ -876,9 +884,12 @@ int pk_resample_thresholds(const double* all_block_sums, long long nb_total, lon
                            double* block_prefix, long long* block_count, void* stream) {
     PK_CHECK_ARG(all_block_sums && plan && block_prefix && block_count, "null pointer");
     PK_CHECK_ARG(nb_total > 0 && M_total > 0, "sizes");
-    PK_CHECK_ARG(nb_total <= (long long)kGroupBlocks * kMaxScanGroups, "more than 2^25 particles in one filter");
+    PK_CHECK_ARG(nb_total <= (long long)kMaxGroupBlocks * kMaxScanGroups, "more than 2^25 particles in one filter");
+    // the fold tree depends on the TOTAL block count only, never on how the blocks are spread over ranks
+    int group = kMinGroupBlocks;
+    while ((long long)group * kMaxScanGroups < nb_total) group *= 2;
     thresholds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(all_block_sums, nb_total, M_total, u01, plan, block_prefix,
-                                                           block_count);
+                                                           block_count, group);
     PK_LAUNCH_CHECK("thresholds_kernel");
     return PK_OK;
 }

@@ -68,7 +68,8 @@ def main(argv):
             if "measure_kernel" in kernel and "dram__bytes_read.sum" in got:
                 rd = to_bytes(*got["dram__bytes_read.sum"])
                 wr = to_bytes(*got["dram__bytes_write.sum"])
-                key = "measure_kernel<float>" if "float" in kernel else "measure_kernel<double>"
+                key = ("measure_kernel<float,f32>" if "LandmarkF" in kernel else
+                       "measure_kernel<float>" if "float" in kernel else "measure_kernel<double>")
                 traffic[key] = dict(dram_bytes_read=rd, dram_bytes_write=wr, dram_bytes=rd + wr,
                                     grid=got.get("launch__grid_size", ("", ""))[0],
                                     block=got.get("launch__block_size", ("", ""))[0],
