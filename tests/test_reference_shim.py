@@ -65,3 +65,43 @@ def test_unmodified_ros_node_runs_on_the_fakes():
         x, y, h = node.core.summary()
     assert np.isfinite([x, y, h]).all() and 0.0 < x < 0.2
     assert fake_rospy.published["/slam_estimate"] >= 9
+
+
+def test_analysis_helpers_match_reference_utils():
+    """parakeet_slam_b200.analysis.SlamAnalyzer.calc_errors against the reference's utils.calc_errors
+    (utils.py:83-205) on random (location, goal) pairs; host arithmetic on both sides."""
+    from parakeet_slam_b200.analysis import SlamAnalyzer
+    ref = ref_shim.load_reference(with_ros_node=False)
+    rs = np.random.RandomState(4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(200):
+            loc = (rs.uniform(-5, 5), rs.uniform(-5, 5), rs.uniform(-3.1, 3.1))
+            goal = (rs.uniform(-5, 5), rs.uniform(-5, 5), rs.uniform(-3.1, 3.1))
+            want = ref.utils.calc_errors(ref.utils.easy_Odom(loc[0], loc[1], loc[2]),
+                                         ref.utils.easy_Odom(goal[0], goal[1], goal[2]))
+            got = SlamAnalyzer.calc_errors(loc, goal)
+            assert np.allclose(got, want, rtol=0, atol=1e-12), (loc, goal, got, want)
+
+
+def test_spawn_restatement_matches_live_patched_reference():
+    """Spawn mode on a scenario that is not among the fixtures: the NumPy restatement against the reference run with
+    the three patches of SURVEY.md A.6 (ids incl. new negative ones, ancestors, next_id, orphaned readings)."""
+    from oracle import fastslam_np as onp, ref_driver
+    from parakeet_slam_b200.scenario import make_scenario
+    scn = make_scenario("c3", num_particles=10, num_landmarks=16, frames=25, obs_per_frame=6,
+                        world_seed=41, obs_seed=42, motion_seed=43, resample_seed=44)
+    ref = ref_shim.load_reference(with_ros_node=False)
+    ref_shim.apply_spawn_patches(ref)
+    tr = ref_driver.run_reference(scn, ref=ref, spawn=True, known_map=False, record_landmarks_at=(24,))
+    to = onp.run_scenario(scn, spawn=True, known_map=False, capacity=64, record_landmarks_at=(24,))
+    assert np.array_equal(tr["assoc"], to["assoc"]) and np.array_equal(tr["ancestors"], to["ancestors"])
+    assert np.array_equal(tr["next_id"], to["next_id"])
+    assert (tr["assoc"] < 0).any() and (tr["assoc"] > 0).any()
+    for i, ps in enumerate(tr["spawn_state"][24]):
+        ids = to["lm_ids"][24][i]
+        mine = {int(ids[j]): to["lm_mean"][24][i, j] for j in range(len(ids)) if ids[j] != 0}
+        assert set(mine) == set(ps["landmarks"])
+        for id_, (mean, cov, cnt) in ps["landmarks"].items():
+            assert np.max(np.abs(mean - mine[id_])) < 1e-9
+        assert [o[0] for o in to["orphans"][24][i]] == [o[0] for o in ps["orphans"]]
