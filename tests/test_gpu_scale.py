@@ -360,3 +360,56 @@ def test_config3_size_spawn_properties():
         assert np.isfinite(mean5[0, :int(nl[0])]).all()
     slot = fs.slot.cpu().numpy()
     assert len(np.unique(slot)) == M                               # blocks stay a permutation through the resamples
+
+
+@pytest.mark.parametrize("K", [3, 8, 40, 64])
+def test_blob_counts_f32_arithmetic(K):
+    """The fp32-algebra instantiation over the same blob counts (one and two items per lane, repeated blobs on one
+    landmark): frame 0 identical to the oracle, >= 90 % of all indices, weights of frame 0 to 1e-3, no flags."""
+    from oracle import fastslam_np as onp
+    from device_harness import make_features
+    from parakeet_slam_b200.core import FastSLAM
+    from parakeet_slam_b200.rosless import Time, messages
+    from parakeet_slam_b200.scenario import DT_NSEC, make_scenario
+    M, N, T = 1001, 24, 4
+    scn = make_scenario("c2", num_particles=M, num_landmarks=N, obs_per_frame=min(K, N), frames=T)
+    rs = np.random.RandomState(K)
+    obs = np.zeros((T, K, 4))
+    for t in range(T):
+        pick = np.concatenate([np.arange(min(K, N)), rs.randint(0, min(K, N), max(0, K - N))])
+        obs[t] = scn.observations[t][pick]
+        obs[t, :, 0] += rs.normal(0, 0.01, K)
+        obs[t, :, 1:] += rs.normal(0, 0.2, (K, 3))
+
+    class Clk(object):
+        ns = 0
+
+        def __call__(self):
+            return Time(0, self.ns)
+    clk = Clk()
+    blocks = [rs.standard_normal((M, 3)) for _ in range(T)]
+    it = iter(blocks)
+    fs = FastSLAM(make_features(scn), num_particles=M, dtype="f32", arithmetic="f32", noise=lambda m: next(it),
+                  uniform=random.Random(2).random, clock=clk)
+    fs.keep_trace = True
+    tw = messages.Twist()
+    tw.linear.x, tw.angular.z = scn.v, scn.w
+    fs.last_control = tw
+    st = onp.OracleState(M, scn.landmarks, preset_covar=scn.preset_covar)
+    urng = random.Random(2)
+    match = []
+    for t in range(T):
+        clk.ns += DT_NSEC
+        fs.motion_update(tw)
+        fs.measurement_update(obs[t])
+        assert fs.stats()["flags"] == 0
+        fs.low_variance_resample()
+        ids, wgt, anc, _ = onp.frame(st, obs[t], blocks[t], scn.v, scn.w, scn.dt, urng.random(), sequential_resample=False)
+        a, r = fs.last_assoc.cpu().numpy(), fs.last_ancestors.cpu().numpy()
+        match.append((float((a == ids).mean()), float((r == anc).mean())))
+        if t == 0:
+            assert np.array_equal(a, ids) and np.array_equal(r, anc)
+            w = fs.last_weight.cpu().numpy()
+            big = wgt > 1e-300
+            assert np.max(np.abs(w[big] - wgt[big]) / wgt[big]) < 1e-3
+    assert min(m for m, _ in match) >= 0.90 and min(r for _, r in match) >= 0.90, match
