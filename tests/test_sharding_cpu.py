@@ -210,3 +210,34 @@ def test_device_plan_flags_overflow():
         assert x[_lib.PK_XP_OVERFLOW] == 1 and x[_lib.PK_XP_N_SEND] == 0 and x[_lib.PK_XP_N_IN] == 0
         assert _xplan_host(E, Ml, g, need)[_lib.PK_XP_OVERFLOW] in (0, 1)
     assert all(_xplan_host(E, Ml, g, Ml)[_lib.PK_XP_OVERFLOW] == 0 for g in range(G))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_device_plan_random_offspring(seed):
+    """Random rank counts (incl. odd ones), random heavy-tailed offspring: the device plan's window split and send runs
+    add up on every rank and agree with the host plan."""
+    from parakeet_slam_b200 import _lib
+    rs = np.random.RandomState(100 + seed)
+    G = int(rs.choice([2, 3, 5, 7, 8, 16]))
+    Ml = int(rs.choice([32, 96, 256]))
+    M = G * Ml
+    w = rs.pareto(0.7, size=M) * (rs.uniform(size=M) < rs.uniform(0.05, 1.0))
+    if w.sum() == 0:
+        w[rs.randint(M)] = 1.0
+    C = np.cumsum(w)
+    anc = np.minimum(np.searchsorted(C, (rs.uniform() + np.arange(M)) * C[-1] / M, side="left"), M - 1)
+    off = np.bincount(anc, minlength=M)
+    E = _emitted(off, G)
+    total_send = total_in = 0
+    for g in range(G):
+        x, p = _xplan_host(E, Ml, g, Ml), plan_exchange(E, Ml, g)
+        assert x[_lib.PK_XP_OVERFLOW] == 0
+        assert x[_lib.PK_XP_N_LO] + x[_lib.PK_XP_N_LOC] + x[_lib.PK_XP_N_HI] == Ml
+        assert x[_lib.PK_XP_N_BELOW] + x[_lib.PK_XP_N_LOC] + x[_lib.PK_XP_N_ABOVE] == x[_lib.PK_XP_EMIT_N]
+        assert (x[_lib.PK_XP_N_LO], x[_lib.PK_XP_N_LOC]) == (p["n_lo"], p["n_loc"])
+        assert x[_lib.PK_XP_N_SEND] == sum(p["send"]) - p["send"][g]
+        if x[_lib.PK_XP_N_ABOVE]:
+            assert x[_lib.PK_XP_ABOVE_START] == max(E[g], (g + 1) * Ml)
+        total_send += int(x[_lib.PK_XP_N_SEND])
+        total_in += int(x[_lib.PK_XP_N_IN])
+    assert total_send == total_in          # every migrating particle is sent once and received once
