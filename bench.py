@@ -417,7 +417,8 @@ def run_ours(args):
                             "launch / K2 time is the HBM utilisation -- see profiles/r1_summary.md") if args.arith == "f32"
                            else ("not HBM: fp64 dependent-latency / issue (12 warps per SM at 168 registers; DRAM "
                                  "throughput ~27 % of peak under ncu) -- see profiles/r1_summary.md"),
-                "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_kernels_ncu.csv)",
+                "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_kernels_ncu.csv); captured one build "
+                                "before the full-sector record stores, see profiles/r1_summary.md",
                 "algorithmic_bytes_per_launch": bytes_particle * M_local,
                 "algorithmic_bytes_per_particle": bytes_particle,
                 "survey_aos_bytes_per_particle": survey_bytes,

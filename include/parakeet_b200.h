@@ -23,7 +23,7 @@
  *   aux2    int[M][2]       n_live landmarks, next_id            (travels with the particle)
  *   slot    int[M]          index of the particle's landmark block in the pool
  *   pool    bytes           n_slots blocks of pk_block_bytes(capacity, dtype); one block =
- *                           [hot region: capacity x 4 B, padded to 16 B][cold region: capacity x COLD]
+ *                           [hot region: capacity x 4 B, padded to 64 B][cold region: capacity x COLD]
  *                             hot  4 B  = colour KEY: r,g,b rounded and clamped to bytes (the only
  *                                         part streamed for every landmark by the fused kernel)
  *                             cold f32 64 B  = r,g,b, x,y, Sp lower triangle (3), Sc lower triangle (6)

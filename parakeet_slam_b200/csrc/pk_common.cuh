@@ -130,8 +130,10 @@ constexpr int kOrphanBytes = 64;        // double x, y, cos(ray), sin(ray), r, g
 
 __host__ __device__ inline size_t hot_bytes(int) { return 4; }
 __host__ __device__ inline size_t cold_bytes(int dtype) { return dtype_base(dtype) == PK_DTYPE_F64 ? sizeof(ColdD) : sizeof(ColdF); }
-// hot region padded to 16 B so the cold records and TMA bulk copies stay 16-byte aligned
-__host__ __device__ inline size_t hot_region_bytes(int capacity) { return ((size_t)capacity * 4 + 15) & ~(size_t)15; }
+// hot region padded to 64 B: every f32 cold record is then exactly one 64-byte DRAM granule and every f64 record
+// starts on a 32-byte sector, so records are written with full-sector (256-bit) stores -- a 16-byte store is a
+// partial-sector write whose miss in L2 costs a fill read from DRAM
+__host__ __device__ inline size_t hot_region_bytes(int capacity) { return ((size_t)capacity * 4 + 63) & ~(size_t)63; }
 __host__ __device__ inline size_t orphan_offset(int capacity, int dtype) {
     return hot_region_bytes(capacity) + (size_t)capacity * cold_bytes(dtype);
 }
@@ -150,6 +152,13 @@ __host__ __device__ inline size_t block_bytes(int capacity, int dtype) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const int4*>(p)); }
 __device__ __forceinline__ void stcg16(void* p, int4 v) { __stcg(reinterpret_cast<int4*>(p), v); }
+
+// one full 32-byte sector per request (STG.256); p must be 32-byte aligned
+__device__ __forceinline__ void stcg32(void* p, int4 a, int4 b) {
+    asm volatile("st.global.cg.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 
 __device__ __forceinline__ double i4lo(int4 v) { return __hiloint2double(v.y, v.x); }
 __device__ __forceinline__ double i4hi(int4 v) { return __hiloint2double(v.w, v.z); }
@@ -270,10 +279,10 @@ __device__ __forceinline__ void store_landmark<float>(unsigned char* block, int 
     // the key is derived from the STORED (rounded) colour so screen and exact test see one value
     const unsigned key = color_key((double)fr, (double)fg, (double)fb);
     if (key != old_key) __stcg(reinterpret_cast<unsigned*>(block) + j, key);
-    stcg16(cp, make_int4(__float_as_int(fr), __float_as_int(fg), __float_as_int(fb), PK_F(L.x)));
-    stcg16(cp + 16, make_int4(PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[2]), PK_F(L.sp[3])));
-    stcg16(cp + 32, make_int4(PK_F(L.sc[0]), PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[6])));
-    stcg16(cp + 48, make_int4(PK_F(L.sc[7]), PK_F(L.sc[8]), L.id, L.meta));
+    stcg32(cp, make_int4(__float_as_int(fr), __float_as_int(fg), __float_as_int(fb), PK_F(L.x)),
+           make_int4(PK_F(L.y), PK_F(L.sp[0]), PK_F(L.sp[2]), PK_F(L.sp[3])));
+    stcg32(cp + 32, make_int4(PK_F(L.sc[0]), PK_F(L.sc[3]), PK_F(L.sc[4]), PK_F(L.sc[6])),
+           make_int4(PK_F(L.sc[7]), PK_F(L.sc[8]), L.id, L.meta));
 #undef PK_F
 }
 
@@ -283,16 +292,11 @@ __device__ __forceinline__ void store_landmark<double>(unsigned char* block, int
     unsigned char* cp = const_cast<unsigned char*>(cold_ptr<double>(block, capacity, j));
     const unsigned key = color_key(L.r, L.g, L.b);
     if (key != old_key) __stcg(reinterpret_cast<unsigned*>(block) + j, key);
-    stcg16(cp, mk_i4(L.r, L.g));
-    stcg16(cp + 16, mk_i4(L.b, L.x));
-    stcg16(cp + 32, mk_i4(L.y, L.sp[0]));
-    stcg16(cp + 48, mk_i4(L.sp[1], L.sp[2]));
-    stcg16(cp + 64, mk_i4(L.sp[3], L.sc[0]));
-    stcg16(cp + 80, mk_i4(L.sc[1], L.sc[2]));
-    stcg16(cp + 96, mk_i4(L.sc[3], L.sc[4]));
-    stcg16(cp + 112, mk_i4(L.sc[5], L.sc[6]));
-    stcg16(cp + 128, mk_i4(L.sc[7], L.sc[8]));
-    stcg16(cp + 144, make_int4(L.id, L.meta, 0, 0));
+    stcg32(cp, mk_i4(L.r, L.g), mk_i4(L.b, L.x));
+    stcg32(cp + 32, mk_i4(L.y, L.sp[0]), mk_i4(L.sp[1], L.sp[2]));
+    stcg32(cp + 64, mk_i4(L.sp[3], L.sc[0]), mk_i4(L.sc[1], L.sc[2]));
+    stcg32(cp + 96, mk_i4(L.sc[3], L.sc[4]), mk_i4(L.sc[5], L.sc[6]));
+    stcg32(cp + 128, mk_i4(L.sc[7], L.sc[8]), make_int4(L.id, L.meta, 0, 0));
 }
 
 // ---- fp32 working copy <-> the 64-byte f32 record: plain bit moves, no conversions -----------------
@@ -337,10 +341,10 @@ __device__ __forceinline__ void store_landmark(unsigned char* block, int capacit
 #define PK_FI(v) __float_as_int(v)
     const unsigned key = color_key_f(L.r, L.g, L.b);
     if (key != old_key) __stcg(reinterpret_cast<unsigned*>(block) + j, key);
-    stcg16(cp, make_int4(PK_FI(L.r), PK_FI(L.g), PK_FI(L.b), PK_FI(L.x)));
-    stcg16(cp + 16, make_int4(PK_FI(L.y), PK_FI(L.sp[0]), PK_FI(L.sp[1]), PK_FI(L.sp[2])));
-    stcg16(cp + 32, make_int4(PK_FI(L.sc[0]), PK_FI(L.sc[1]), PK_FI(L.sc[2]), PK_FI(L.sc[3])));
-    stcg16(cp + 48, make_int4(PK_FI(L.sc[4]), PK_FI(L.sc[5]), L.id, L.meta));
+    stcg32(cp, make_int4(PK_FI(L.r), PK_FI(L.g), PK_FI(L.b), PK_FI(L.x)),
+           make_int4(PK_FI(L.y), PK_FI(L.sp[0]), PK_FI(L.sp[1]), PK_FI(L.sp[2])));
+    stcg32(cp + 32, make_int4(PK_FI(L.sc[0]), PK_FI(L.sc[1]), PK_FI(L.sc[2]), PK_FI(L.sc[3])),
+           make_int4(PK_FI(L.sc[4]), PK_FI(L.sc[5]), L.id, L.meta));
 #undef PK_FI
 }
 

@@ -433,7 +433,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     const unsigned* gkeys = reinterpret_cast<const unsigned*>(block);
                     const unsigned mykey = it_key[r];
                     for (int j4 = 0; j4 < nlive; j4 += 4) {
-                        const int4 kv = ldcg16(gkeys + j4);  // the key region is padded to 16 bytes
+                        const int4 kv = ldcg16(gkeys + j4);  // the key region is padded (to 64 bytes)
                         const unsigned kk[4] = {(unsigned)kv.x, (unsigned)kv.y, (unsigned)kv.z, (unsigned)kv.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {

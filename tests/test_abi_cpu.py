@@ -33,8 +33,9 @@ def test_layout_queries_and_error_convention():
     assert lib.pk_hot_bytes(_lib.PK_DTYPE_F32) == 4
     assert lib.pk_cold_bytes(_lib.PK_DTYPE_F32) == 64 and lib.pk_cold_bytes(_lib.PK_DTYPE_F64) == 160
     assert lib.pk_block_bytes(64, _lib.PK_DTYPE_F32) == 64 * 68
-    assert lib.pk_block_bytes(20, _lib.PK_DTYPE_F64) == 80 + 20 * 160
-    assert lib.pk_block_bytes(3, _lib.PK_DTYPE_F32) == 16 + 3 * 64       # key region padded to 16 B
+    assert lib.pk_block_bytes(20, _lib.PK_DTYPE_F64) == 128 + 20 * 160   # key region padded to 64 B
+    assert lib.pk_block_bytes(3, _lib.PK_DTYPE_F32) == 64 + 3 * 64
+    assert lib.pk_block_bytes(64, _lib.dtype_with_orphans(_lib.PK_DTYPE_F32, 32)) == 64 * 68 + 64 + 32 * 64
     assert lib.pk_num_scan_blocks(1) == 1 and lib.pk_num_scan_blocks(1025) == 2
     p = _lib.default_params()
     assert (p.bearing_gate, p.color_gate, p.no_match_weight, p.qt_diag, p.promote_count) == (0.5, 300.0, 0.1, 0.1, 5)
