@@ -58,3 +58,37 @@ def test_product_has_no_cpu_fallback_and_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_python_constants_match_the_header():
+    """Every PK_* constant the Python binding mirrors has the value include/parakeet_b200.h gives it."""
+    from parakeet_slam_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "parakeet_b200.h")).read()
+    defines = {}
+    for name, val in re.findall(r"^#define\s+(PK_[A-Z0-9_]+)\s+([^\s/]+)", text, flags=re.M):
+        v = val.rstrip("uUlL")
+        try:
+            defines[name] = int(v, 0)
+        except ValueError:
+            continue
+    checked = 0
+    for name, value in vars(_lib).items():
+        if name.startswith("PK_") and isinstance(value, int) and name in defines:
+            assert defines[name] == value, (name, defines[name], value)
+            checked += 1
+    assert checked >= 25
+    assert _lib.PK_XP_RANK_LOC == 16 + _lib.PK_MAX_RANKS and _lib.PK_XPLAN_LONGS >= 16 + 2 * _lib.PK_MAX_RANKS
+
+
+def test_layout_code_helpers():
+    from parakeet_slam_b200 import _lib
+    lib = _lib.load()
+    base = lib.pk_block_bytes(256, _lib.PK_DTYPE_F32)
+    assert base == 1024 + 256 * 64
+    assert lib.pk_block_bytes(256, _lib.PK_DTYPE_F32 | _lib.PK_DTYPE_ARITH_F32) == base       # arithmetic flag: no layout change
+    assert lib.pk_block_bytes(256, _lib.dtype_with_orphans(_lib.PK_DTYPE_F32, 16)) == base + 64 + 16 * 64
+    assert lib.pk_particle_record_bytes(256, _lib.PK_DTYPE_F32) == 64 + base
+    for cap in (1, 3, 20, 64, 100, 1024):            # records start on 64-byte (f32) / 32-byte (f64) boundaries
+        assert lib.pk_block_bytes(cap, _lib.PK_DTYPE_F32) % 64 == 0
+        assert lib.pk_block_bytes(cap, _lib.PK_DTYPE_F64) % 32 == 0
+    assert lib.pk_obs_table_bytes() >= 6 * 64 * 8 + 64 * 4
