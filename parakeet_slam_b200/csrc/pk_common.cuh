@@ -151,6 +151,15 @@ __host__ __device__ inline size_t block_bytes(int capacity, int dtype) {
 // lanes of a warp inside one kernel, so they must never be served from a stale L1 line.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const int4*>(p)); }
+// Same, with the L2 fetch size limited to 64 bytes.  On B200 an L2 read miss fetches the whole 128-byte line from
+// DRAM by default (measured with tools/dram_probe.cu: scattered 64-byte records cost 128 bytes of DRAM reads each,
+// whatever cudaLimitMaxL2FetchGranularity says); the .L2::64B qualifier halves that.  Used for every scattered
+// record access; streams that cover whole lines anyway keep the default.
+__device__ __forceinline__ int4 ldcg16_rec(const void* p) {
+    int4 v;
+    asm volatile("ld.global.cg.L2::64B.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void stcg16(void* p, int4 v) { __stcg(reinterpret_cast<int4*>(p), v); }
 
 // one full 32-byte sector per request (STG.256); p must be 32-byte aligned
@@ -183,7 +192,7 @@ template <typename T>
 __device__ __forceinline__ void load_colour(const unsigned char* block, int capacity, int j, double& r, double& g, double& b);
 template <>
 __device__ __forceinline__ void load_colour<float>(const unsigned char* block, int capacity, int j, double& r, double& g, double& b) {
-    const int4 c0 = ldcg16(cold_ptr<float>(block, capacity, j));
+    const int4 c0 = ldcg16_rec(cold_ptr<float>(block, capacity, j));
     r = (double)__int_as_float(c0.x);
     g = (double)__int_as_float(c0.y);
     b = (double)__int_as_float(c0.z);
@@ -191,7 +200,7 @@ __device__ __forceinline__ void load_colour<float>(const unsigned char* block, i
 template <>
 __device__ __forceinline__ void load_colour<double>(const unsigned char* block, int capacity, int j, double& r, double& g, double& b) {
     const unsigned char* cp = cold_ptr<double>(block, capacity, j);
-    const int4 c0 = ldcg16(cp), c1 = ldcg16(cp + 16);
+    const int4 c0 = ldcg16_rec(cp), c1 = ldcg16_rec(cp + 16);
     r = i4lo(c0);
     g = i4hi(c0);
     b = i4lo(c1);
@@ -253,7 +262,7 @@ __device__ __forceinline__ void load_landmark(const unsigned char* block, int ca
     const unsigned char* cp = cold_ptr<T>(block, capacity, j);
     int4 c[kWords];
 #pragma unroll
-    for (int i = 0; i < kWords; ++i) c[i] = ldcg16(cp + 16 * i);
+    for (int i = 0; i < kWords; ++i) c[i] = ldcg16_rec(cp + 16 * i);
     decode_cold<T>(c, L);
 }
 
@@ -324,7 +333,7 @@ __device__ __forceinline__ void load_landmark(const unsigned char* block, int ca
     const unsigned char* cp = cold_ptr<T>(block, capacity, j);
     int4 c[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = ldcg16(cp + 16 * i);
+    for (int i = 0; i < 4; ++i) c[i] = ldcg16_rec(cp + 16 * i);
     decode_cold_f(c, L);
 }
 __device__ __forceinline__ unsigned color_key_f(float r, float g, float b) {
@@ -415,7 +424,8 @@ __device__ __forceinline__ void tma_load_1d_a(uint32_t dst, const void* src_gmem
 // commit/wait groups.  Unlike cp.async.bulk (UBLKCP, uniform operands) every lane can use its own
 // addresses in one instruction, which is what a scattered per-lane record fetch needs.
 __device__ __forceinline__ void cp_async16_a(uint32_t dst, const void* src_gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_gmem) : "memory");
+    // .L2::64B: fetch only the record's 64-byte half of the 128-byte line on an L2 miss (see ldcg16_rec)
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(dst), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
