@@ -92,7 +92,19 @@ struct ObsTable {
     double beta[PK_MAX_OBS], cr[PK_MAX_OBS], cg[PK_MAX_OBS], cb[PK_MAX_OBS];
     double dirx[PK_MAX_OBS], diry[PK_MAX_OBS];  // unit((cos b, sin b, 0)) of closest_point :510
     unsigned okey[PK_MAX_OBS];                  // colour keys of the blobs
+    // != 0 when some pair of blobs has colours within twice the gate radius of each other: only then can two
+    // blobs of one frame pass the colour gate (:441) of the SAME landmark (triangle inequality), i.e. only then
+    // does the fused kernel have to order updates of one landmark (finding F2)
+    unsigned twins;
 };
+// squared colour distance below which two blobs count as twins (conservative: rounding of the fp32 gate, NaN gate)
+__host__ __device__ inline bool blobs_may_share_landmark(double r1, double g1, double b1, double r2, double g2, double b2,
+                                                          double gate) {
+    if (!(gate == gate)) return true;  // NaN gate: everything passes
+    if (gate < 0.0) return false;      // nothing passes
+    const double d2 = (r1 - r2) * (r1 - r2) + (g1 - g2) * (g1 - g2) + (b1 - b2) * (b1 - b2);
+    return !(d2 > 4.0 * gate * 1.001 + 1.0);
+}
 
 // fp64 working copy of one landmark
 struct Landmark {

@@ -64,8 +64,9 @@ struct MeasureArgs {
     unsigned char* pool;
     int* assoc;
     unsigned long long* stats;
-    long long M;
+    int M;            // particles of this launch (< 2^31: all group / particle indices are 32-bit)
     size_t block_bytes;
+    unsigned hot_bytes;  // hot_region_bytes(capacity): offset of the cold region inside a block
     int capacity;
     int K;
     int group;        // particles per warp group
@@ -79,18 +80,16 @@ struct MeasureArgs {
 };
 
 // fixed part of a warp's shared memory; the key ring [kStages][group][kKeyStride] and the record
-// staging area [2][32 * R] follow at keys_off / rec_off
+// staging area [2][kStaged][32 * R] follow at keys_off / rec_off
 template <int R>
 struct alignas(128) WarpSmemT {
     static constexpr int kItems = 32 * R;
     double pose[4][kMaxGroup][4];
     double factor[kItems];
-    int ids[kItems];
-    int bj[kItems];
     int slot_s[4][kMaxGroup];
     int nlive_s[4][kMaxGroup];
-    int nsteps_s[4];
-    int more_hits[2][kItems][kMaxHits - 2];  // third and later hits of an item (rare)
+    unsigned short more_hits[2][kItems][kMaxHits - 2];  // third and later hits of an item (rare)
+    int unseen_acc;  // R > 1: unseen blobs of the particle, summed over the rounds
     uint64_t key_bar[kStages];
 };
 static_assert(kMaxItems == 64, "R <= 2");
@@ -126,6 +125,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     using Pre_t = typename ArithOf<LM>::Pre;
     constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
     constexpr int kStaged = staged_candidates<T, LM>();  // candidates per item prefetched into shared memory
+    constexpr int kChunksPerRec = (int)(kRecBytes / 16u);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + (size_t)warp * A.warp_smem;
@@ -133,20 +133,24 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     WarpSmem& S = *reinterpret_cast<WarpSmem*>(wbase);
     const uint32_t s_base = smem_u32(wbase);
     const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
-    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [2][32 * R] Cold
+    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [2][kStaged][32 * R] Cold
     const uint32_t s_keybar = smem_u32(&S.key_bar[0]);
     const uint32_t s_pose = smem_u32(&S.pose[0][0][0]);
     const unsigned lt = lanemask_lt();
 
     const int K = A.K, GP = A.group, cap = A.capacity;
     const int key_thr = A.key_thr;
-    const long long M = A.M;
-    const long long n_groups = (M + GP - 1) / GP;
-    const long long total_warps = (long long)gridDim.x * kWarpsPerCta;
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
-    const long long my_groups = (gw < n_groups) ? (n_groups - gw + total_warps - 1) / total_warps : 0;
+    const int M = A.M;
+    const int n_groups = (M + GP - 1) / GP;
+    const int total_warps = (int)gridDim.x * kWarpsPerCta;
+    const int gw = (int)blockIdx.x * kWarpsPerCta + warp;
+    const int my_groups = (gw < n_groups) ? (n_groups - gw + total_warps - 1) / total_warps : 0;
+    const unsigned hot = A.hot_bytes;
 
     const ObsTable* OT = A.tab_dev ? A.tab_dev : &A.tab;
+    // two blobs of this frame may hit the same landmark only if their colours are close (ObsTable::twins); when no
+    // pair is, the same-landmark ordering of the update phase (finding F2) is skipped altogether
+    const bool twins = OT->twins != 0u;
     // this lane's items: item w = r * 32 + lane -> (particle pl, blob k) within a group
     int it_pl[R], it_k[R];
     unsigned it_key[R];
@@ -156,6 +160,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         it_pl[r] = w / K;
         it_k[r] = w - it_pl[r] * K;
         it_key[r] = (it_pl[r] < GP) ? OT->okey[it_k[r]] : 0u;
+        if (it_pl[r] >= GP) it_pl[r] = GP;  // inactive lane (GP * K < 32)
     }
 
     // the blob of this lane's item(s) never changes: keep its values in registers
@@ -178,92 +183,91 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     __syncwarp();
 
     // ---- key producer (warp-uniform state) -----------------------------------------------------
-    long long p_git = 0, s_git = 0;
-    unsigned p_cnt = 0, s_cnt = 0;  // stages produced / consumed
-    int p_step = 0, p_nsteps = 1;
-    int nx_slot = 0, nx_nlive = 0;  // lane pl holds slot / n_live of particle pl of the next group to open
-    auto fetch_info = [&](long long git) {
+    // A flat sequence of steps (group, 64-key chunk) goes through the ring of kStages key stages; produce_one()
+    // issues the next step and is called once per consumed step, so the producer stays kStages - 1 steps ahead.
+    // Group info buffers are indexed it & 3: group it is being evaluated, it + 1 screened, it + 2 may be open.
+    int p_it = 0, p_step = 0, p_ns = 1;
+    unsigned p_cnt = 0, s_cnt = 0;  // steps produced / consumed
+    int nx_slot = 0, nx_nlive = 0;  // lane pl: slot / n_live of particle pl of the next group to open
+    int op_slot = 0, op_nlive = 0;  // ... of the group that is open in the producer
+    auto fetch_info = [&](int it) {
         nx_slot = 0;
         nx_nlive = 0;
-        if (git < my_groups && lane < GP) {
-            const long long p = (gw + git * total_warps) * GP + lane;
-            if (p < M) {
-                nx_slot = A.slot[p];
-                nx_nlive = A.aux2[2 * p];
-            }
+        const int p = (gw + it * total_warps) * GP + lane;
+        if (it < my_groups && lane < GP && p < M) {
+            nx_slot = A.slot[p];
+            nx_nlive = A.aux2[2 * p];
         }
     };
     fetch_info(0);
-
-    // Group info buffers are indexed git & 3: group g is being evaluated, g+1 screened, g+2 may
-    // already be open in the producer.
-    auto produce = [&]() {
-        while (p_git < my_groups && p_git <= s_git + 1 && p_cnt - s_cnt < (unsigned)kStages) {
-            const int gi = (int)(p_git & 3);
-            const long long p0 = (gw + p_git * total_warps) * GP;
-            const int gpn = (int)min((long long)GP, M - p0);
-            if (p_step == 0) {  // open the group: publish slot / n_live, prefetch the next group's
-                if (lane < kMaxGroup) {
-                    S.slot_s[gi][lane] = nx_slot;
-                    S.nlive_s[gi][lane] = nx_nlive;
-                }
-                const int maxn = __reduce_max_sync(kFull, nx_nlive);
-                p_nsteps = max(1, (maxn + kChunk - 1) / kChunk);
-                if (lane == 0) S.nsteps_s[gi] = p_nsteps;
-                fetch_info(p_git + 1);
-                __syncwarp();
+    auto produce_one = [&]() {
+        if (p_it >= my_groups) return;
+        const int gi = p_it & 3;
+        const int p0 = (gw + p_it * total_warps) * GP;
+        const int gpn = min(GP, M - p0);
+        if (p_step == 0) {  // open the group: publish slot / n_live, prefetch the next group's
+            op_slot = nx_slot;
+            op_nlive = nx_nlive;
+            if (lane < kMaxGroup) {
+                S.slot_s[gi][lane] = op_slot;
+                S.nlive_s[gi][lane] = op_nlive;
             }
-            const unsigned stage = p_cnt % kStages;
-            unsigned bytes = 0;
-            if (lane < gpn) {
-                const int nl = max(0, min(kChunk, S.nlive_s[gi][lane] - p_step * kChunk));
-                bytes = ((unsigned)nl * 4u + 15u) & ~15u;
-            }
-            const unsigned total = __reduce_add_sync(kFull, bytes) + (p_step == 0 ? (unsigned)(gpn * 32) : 0u);
-            fence_proxy_async();
-            const uint32_t bar = s_keybar + stage * 8u;
-            if (lane == 0) {
-                mbar_arrive_expect_tx_a(bar, total);
-                if (p_step == 0) tma_load_1d_a(s_pose + (uint32_t)gi * (kMaxGroup * 32), A.pose4 + 4 * p0, (unsigned)(gpn * 32), bar);
-            }
-            __syncwarp();
-            // every lane moves its own particle's keys.  (cp.async.bulk takes warp-uniform operands, so this
-            // compiles to a short waterfall over the <= 8 issuing lanes; issuing all copies from lane 0 in a
-            // loop was measured slower.)
-            if (bytes)
-                tma_load_1d_a(s_keys + ((stage * (unsigned)GP + (unsigned)lane) * kKeyStride) * 4u,
-                              A.pool + (size_t)S.slot_s[gi][lane] * A.block_bytes + (size_t)p_step * kChunk * 4, bytes, bar);
-            ++p_cnt;
-            if (++p_step >= p_nsteps) {
-                p_step = 0;
-                ++p_git;
-            }
+            p_ns = max(1, (__reduce_max_sync(kFull, op_nlive) + kChunk - 1) / kChunk);
+            fetch_info(p_it + 1);
+        }
+        const unsigned stage = p_cnt % kStages;
+        const int nl = max(0, min(kChunk, op_nlive - p_step * kChunk));  // 0 on lanes >= gpn
+        const unsigned bytes = ((unsigned)nl * 4u + 15u) & ~15u;
+        const unsigned total = __reduce_add_sync(kFull, bytes) + (p_step == 0 ? (unsigned)(gpn * 32) : 0u);
+        fence_proxy_async();
+        const uint32_t bar = s_keybar + stage * 8u;
+        if (lane == 0) {
+            mbar_arrive_expect_tx_a(bar, total);
+            if (p_step == 0) tma_load_1d_a(s_pose + (uint32_t)gi * (kMaxGroup * 32), A.pose4 + 4 * (size_t)p0, (unsigned)(gpn * 32), bar);
+        }
+        __syncwarp();
+        // every lane moves its own particle's keys.  (cp.async.bulk takes warp-uniform operands, so this
+        // compiles to a short waterfall over the <= 8 issuing lanes; issuing all copies from lane 0 in a
+        // loop was measured slower.)
+        if (bytes)
+            tma_load_1d_a(s_keys + ((stage * (unsigned)GP + (unsigned)lane) * kKeyStride) * 4u,
+                          A.pool + (size_t)op_slot * A.block_bytes + (size_t)(p_step * kChunk * 4), bytes, bar);
+        ++p_cnt;
+        if (++p_step >= p_ns) {
+            p_step = 0;
+            ++p_it;
         }
     };
 
-    unsigned long long st_matched = 0, st_unmatched = 0, st_eval = 0, st_same = 0, st_promoted = 0;
+    // statistics: warp-uniform 32-bit counts (one warp sees < 2^31 items), folded into the 64-bit totals at the end
+    unsigned st_matched = 0, st_unmatched = 0, st_eval = 0, st_same = 0, st_promoted = 0;
     unsigned st_flags = 0;
 
-    // ---- screen(g): colour-key screen of group g + record prefetch --------------------------------
-    auto screen = [&](long long git, Hits (&H)[R]) {
-        s_git = git;
-        const int gi = (int)(git & 3), par = (int)(git & 1);
-        const long long p0 = (gw + git * total_warps) * GP;
-        const int gpn = (int)min((long long)GP, M - p0);
-        const int nitems = gpn * K;
-        produce();  // opens this group if it is not open yet
+    // ---- screen(it): colour-key screen of group it + record prefetch -------------------------------
+    auto screen = [&](int it, Hits (&H)[R]) {
+        const int gi = it & 3, par = it & 1;
+        const int p0 = (gw + it * total_warps) * GP;
+        const int nitems = min(GP, M - p0) * K;
 #pragma unroll
         for (int r = 0; r < R; ++r) H[r] = Hits{0, -1, -1};
-        const int nsteps = S.nsteps_s[gi];
+        int my_nl[R], my_slot[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool act = (r * 32 + lane) < nitems;
+            my_nl[r] = act ? S.nlive_s[gi][it_pl[r]] : 0;
+            my_slot[r] = act ? S.slot_s[gi][it_pl[r]] : 0;
+        }
+        int maxnl = my_nl[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) maxnl = max(maxnl, my_nl[r]);
+        const int nsteps = max(1, (__reduce_max_sync(kFull, maxnl) + kChunk - 1) / kChunk);
         for (int step = 0; step < nsteps; ++step) {
-            produce();
             const unsigned stage = s_cnt % kStages;
             mbar_wait_a(s_keybar + stage * 8u, (s_cnt / kStages) & 1u);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const bool act = (r * 32 + lane) < nitems;
-                const int pl = act ? it_pl[r] : 0;
-                const int nl = act ? max(0, min(kChunk, S.nlive_s[gi][pl] - step * kChunk)) : 0;
+                const int pl = min(it_pl[r], GP - 1);
+                const int nl = my_nl[r] - step * kChunk;  // keys of this chunk that are live (<= 0: none)
                 const uint32_t kp = s_keys + ((stage * (unsigned)GP + (unsigned)pl) * kKeyStride) * 4u;
                 const unsigned mykey = it_key[r];
                 // three integer instructions per key: |difference| per byte, dot product accumulated onto
@@ -282,68 +286,78 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                         if (4 * q + e < 32) lo = __funnelshift_l(sgn, lo, 1); else hi = __funnelshift_l(sgn, hi, 1);
                     }
                 }
-                unsigned long long m = ((unsigned long long)__brev(hi) << 32) | __brev(lo);
-                m &= (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);  // keys beyond n_live are stale
-                while (m) {  // about one hit per item
-                    const int j = step * kChunk + __ffsll((long long)m) - 1;
-                    m &= m - 1ull;
-                    if (H[r].cnt == 0) H[r].c0 = j;
-                    else if (H[r].cnt == 1) H[r].c1 = j;
-                    else if (H[r].cnt < kMaxHits) S.more_hits[par][r * 32 + lane][H[r].cnt - 2] = j;
-                    H[r].cnt += 1;
+                // keys beyond n_live are stale: mask them (nl <= 0 clears everything)
+                const unsigned vlo = nl >= 32 ? 0xffffffffu : (nl > 0 ? (1u << nl) - 1u : 0u);
+                const unsigned vhi = nl >= 64 ? 0xffffffffu : (nl > 32 ? (1u << (nl - 32)) - 1u : 0u);
+                unsigned mh[2] = {__brev(lo) & vlo, __brev(hi) & vhi};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    unsigned m = mh[h];
+                    while (m) {  // about one hit per item in the whole chunk
+                        const int j = step * kChunk + 32 * h + __ffs((int)m) - 1;
+                        m &= m - 1u;
+                        if (H[r].cnt == 0) H[r].c0 = j;
+                        else if (H[r].cnt == 1) H[r].c1 = j;
+                        else if (H[r].cnt < kMaxHits) S.more_hits[par][r * 32 + lane][H[r].cnt - 2] = (unsigned short)j;
+                        H[r].cnt += 1;
+                    }
                 }
             }
             __syncwarp();  // every lane is done with this key stage before it is refilled
             ++s_cnt;
+            produce_one();
         }
-        // request the cold record of each item's first hit(s) into the lane's staging slot.  The 32 slots of a
-        // round are consecutive in shared memory, so the warp fetches them TOGETHER: instruction i moves 16-byte
-        // chunk i*32+lane of that 32-record strip, i.e. the lanes of one instruction cover whole records and every
-        // 32-byte sector is requested once.  (Each lane copying its own record 16 bytes at a time asks L2 for every
-        // sector twice, from different instructions; the second request missed as well and DRAM read the records
-        // twice -- 1.53 GB instead of ~1 GB per launch under ncu.)
-        constexpr int kChunksPerRec = (int)(kRecBytes / 16u);
+        // Request the cold record of each item's first hit into the lane's staging slot.  The 32 slots of a round
+        // are consecutive in shared memory, so the warp fetches them TOGETHER: instruction i moves 16-byte chunk
+        // i*32+lane of that 32-record strip, i.e. the lanes of one instruction cover whole records (each 32-byte
+        // sector is requested once and an instruction touches 8 lines instead of 32).  The record's position
+        // travels between lanes as ONE 32-bit word: its offset inside the pool in units of 32 bytes.
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-#pragma unroll
-            for (int c = 0; c < kStaged; ++c) {
-                const bool have = H[r].cnt > c;
-                unsigned long long src = 0ull;
-                if (have)
-                    src = (unsigned long long)cold_ptr<T>(A.pool + (size_t)S.slot_s[gi][it_pl[r]] * A.block_bytes, cap,
-                                                          c == 0 ? H[r].c0 : H[r].c1);
-                if (!__any_sync(kFull, have)) continue;
-                const uint32_t strip = s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)(r * 32)) * kRecBytes;
+            const size_t rec0 = (size_t)my_slot[r] * A.block_bytes + hot;
+            {
+                const bool have = H[r].cnt > 0;
+                const unsigned off32 = have ? (unsigned)((rec0 + (size_t)H[r].c0 * kRecBytes) >> 5) : 0xffffffffu;
+                const uint32_t strip = s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)(r * 32)) * kRecBytes;
 #pragma unroll
                 for (int i = 0; i < kChunksPerRec; ++i) {
                     const int chunk = i * 32 + lane;
                     const int rec = chunk / kChunksPerRec, part = chunk - rec * kChunksPerRec;
-                    const unsigned long long sp = __shfl_sync(kFull, src, rec);
-                    if (sp) cp_async16_a(strip + 16u * (unsigned)chunk, reinterpret_cast<const unsigned char*>(sp) + 16 * part);
+                    const unsigned so = __shfl_sync(kFull, off32, rec);
+                    if (so != 0xffffffffu) cp_async16_a(strip + 16u * (unsigned)chunk, A.pool + ((size_t)so << 5) + 16 * part);
                 }
+            }
+            // second hit (one item in ten): fetched by its own lane
+            if (kStaged > 1 && H[r].cnt > 1) {
+                const unsigned char* src = A.pool + rec0 + (size_t)H[r].c1 * kRecBytes;
+                const uint32_t dst = s_rec + (((unsigned)par * kStaged + 1u) * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
+#pragma unroll
+                for (int i = 0; i < kChunksPerRec; ++i) cp_async16_a(dst + 16u * i, src + 16 * i);
             }
         }
         cp_async_commit();
     };
 
-    // ---- evaluate(g): association arg-max + sequential EKF updates + weight ----------------------
-    auto evaluate = [&](long long git, const Hits (&H)[R], bool more_in_flight) {
-        const int gi = (int)(git & 3), par = (int)(git & 1);
-        const long long p0 = (gw + git * total_warps) * GP;
-        const int gpn = (int)min((long long)GP, M - p0);
+    // ---- evaluate(it): association arg-max + sequential EKF updates + weight ----------------------
+    auto evaluate = [&](int it, const Hits (&H)[R], bool more_in_flight) {
+        const int gi = it & 3, par = it & 1;
+        const int p0 = (gw + it * total_warps) * GP;
+        const int gpn = min(GP, M - p0);
         const int nitems = gpn * K;
         // this group's records were committed one group ago; the next group's may still be in flight
         if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
-        // per-lane association result of the (last) evaluated round, kept in registers
-        S_t best_pse = 0;
-        int bestj = -1, lastj = -1;
+        __syncwarp();  // the first-hit strip was filled cooperatively: other lanes' copies must have landed too
+        // association result per item: winner slot, its bearing, and which staging slot holds its record
+        S_t best_pse[R];
+        int bestj[R], win_c[R];
         LM L;
+        int L_j = -1;  // landmark slot whose PRE-update record is in L (R == 1 only)
         // ---- association (:84, match_features_to_scan): every blob against the PRE-update map ----
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int w = r * 32 + lane;
             const bool act = w < nitems;
-            const int pl = act ? it_pl[r] : 0, k = act ? it_k[r] : 0;
+            const int pl = act ? it_pl[r] : 0;
             const unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
             const int cnt = act ? H[r].cnt : 0;
@@ -352,197 +366,199 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             S_t pse = 0;
             Pre_t pre;
             pre.sure = false;
-            best_pse = 0;
-            bestj = -1;
-            lastj = -1;
+            best_pse[r] = 0;
+            bestj[r] = -1;
+            win_c[r] = -1;
             if (cnt > 0) {
                 load_staged<T>(s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)w) * kRecBytes, L);
-                lastj = H[r].c0;
+                L_j = H[r].c0;
                 pre = match_prepare(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r], ob_dy[r], A.prm,
                                     st_flags);
                 pse = pre.pse;
-                st_eval += 1;
             }
+            st_eval += __popc(__ballot_sync(kFull, cnt > 0));
             // An item with a single colour-compatible landmark only needs the reference's decision
             // `probability > 0.0` (:369-381), and match_prepare can usually PROVE it without the two logs
             // and two exps of the pdf tails (MatchPre::sure).  The value itself is needed only to rank
             // several candidates, or when the product may underflow (finding F3) -- a warp-uniform branch.
 #if PK_MATCH_SKIP == 0
-            if (cnt > 0) {
-                const double Lk = match_finish(pre);
-                if (Lk > 0.0) {
-                    best = Lk;
-                    bestj = lastj;
-                    best_pse = pse;
-                }
-            }
+            const bool need_any = true;
 #else
-            const bool need_value = cnt > 1 || (cnt == 1 && !pre.sure);
-            if (__any_sync(kFull, need_value)) {
+            const bool need_any = __any_sync(kFull, cnt > 1 || (cnt == 1 && !pre.sure));
+#endif
+            if (need_any) {
                 if (cnt > 0) {
                     const double Lk = match_finish(pre);
                     if (Lk > 0.0) {
                         best = Lk;
-                        bestj = lastj;
-                        best_pse = pse;
+                        bestj[r] = H[r].c0;
+                        win_c[r] = 0;
+                        best_pse[r] = pse;
                     }
                 }
             } else if (cnt > 0) {
                 best = 1.0;  // some positive value: never compared against anything
-                bestj = lastj;
-                best_pse = pse;
+                bestj[r] = H[r].c0;
+                win_c[r] = 0;
+                best_pse[r] = pse;
             }
-#endif
-            if (__any_sync(kFull, cnt > 1)) {
-                if (cnt <= kMaxHits) {  // further colour-compatible landmarks, in slot order
-                    const int maxcnt = __reduce_max_sync(kFull, cnt <= kMaxHits ? cnt : 0);
-                    for (int c = 1; c < maxcnt; ++c) {
-                        // Most extra hits are false positives of the byte-key screen: apply the exact colour
-                        // gate (:441) first and run the full likelihood only if some lane still needs it.
-                        bool need = false;
-                        if (c < cnt) {
-                            const int j = (c == 1) ? H[r].c1 : S.more_hits[par][w][c - 2];
-                            if (c < kStaged)
-                                load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)w) * kRecBytes, L);
-                            else
-                                load_landmark<T>(block, cap, j, L);
-                            lastj = j;
-                            const S_t dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
-                            need = !(fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate);
-                        }
-                        if (!__any_sync(kFull, need)) continue;
-                        if (need) {
-                            const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
-                                                               ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
-                            st_eval += 1;
-                            if (Lk > best) {
-                                best = Lk;
-                                bestj = lastj;
-                                best_pse = pse;
-                            }
-                        }
+            // further colour-compatible landmarks, in slot order.  All warp collectives sit outside the per-lane
+            // conditions; lanes with more hits than the hit list holds re-walk their keys afterwards, on their own.
+            const int ncand = cnt <= kMaxHits ? cnt : 0;
+            const int maxcnt = __reduce_max_sync(kFull, ncand);
+            for (int c = 1; c < maxcnt; ++c) {
+                // Most extra hits are false positives of the byte-key screen: apply the exact colour
+                // gate (:441) first and run the full likelihood only if some lane still needs it.
+                bool need = false;
+                int j = -1;
+                if (c < ncand) {
+                    j = (c == 1) ? H[r].c1 : (int)S.more_hits[par][w][c - 2];
+                    if (c < kStaged)
+                        load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)w) * kRecBytes, L);
+                    else
+                        load_landmark<T>(block, cap, j, L);
+                    L_j = j;
+                    const S_t dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
+                    need = !(fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate);
+                }
+                if (!__any_sync(kFull, need)) continue;
+                st_eval += __popc(__ballot_sync(kFull, need));
+                if (need) {
+                    const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                       ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
+                    if (Lk > best) {
+                        best = Lk;
+                        bestj[r] = j;
+                        win_c[r] = c < kStaged ? c : -1;
+                        best_pse[r] = pse;
                     }
-                } else if (cnt > kMaxHits) {
-                    // More colour-compatible landmarks than hit registers: walk the particle's keys again
-                    // (from global memory this time) and evaluate every landmark that passes the key screen
-                    // and the exact colour gate, in slot order.
-                    best = 0.0;
-                    bestj = -1;
-                    lastj = -1;
-                    const int nlive = S.nlive_s[gi][pl];
-                    const unsigned* gkeys = reinterpret_cast<const unsigned*>(block);
-                    const unsigned mykey = it_key[r];
-                    for (int j4 = 0; j4 < nlive; j4 += 4) {
-                        const int4 kv = ldcg16(gkeys + j4);  // the key region is padded (to 64 bytes)
-                        const unsigned kk[4] = {(unsigned)kv.x, (unsigned)kv.y, (unsigned)kv.z, (unsigned)kv.w};
+                }
+            }
+            unsigned extra_evals = 0;
+            if (cnt > kMaxHits) {
+                // More colour-compatible landmarks than hit registers: walk the particle's keys again
+                // (from global memory this time) and evaluate every landmark that passes the key screen
+                // and the exact colour gate, in slot order.
+                best = 0.0;
+                bestj[r] = -1;
+                win_c[r] = -1;
+                const int nlive = S.nlive_s[gi][pl];
+                const unsigned* gkeys = reinterpret_cast<const unsigned*>(block);
+                const unsigned mykey = it_key[r];
+                for (int j4 = 0; j4 < nlive; j4 += 4) {
+                    const int4 kv = ldcg16(gkeys + j4);  // the key region is padded (to 64 bytes)
+                    const unsigned kk[4] = {(unsigned)kv.x, (unsigned)kv.y, (unsigned)kv.z, (unsigned)kv.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = j4 + e;
-                            const unsigned dk = __vabsdiffu4(kk[e], mykey);
-                            if (j >= nlive || (int)__dp4a(dk, dk, 0u) > key_thr) continue;
-                            double cr_, cg_, cb_;
-                            load_colour<T>(block, cap, j, cr_, cg_, cb_);
-                            const S_t dr = ob_r[r] - (S_t)cr_, dg = ob_g[r] - (S_t)cg_, db = ob_b[r] - (S_t)cb_;
-                            if (fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate) continue;
-                            load_landmark<T>(block, cap, j, L);
-                            lastj = j;
-                            const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
-                                                               ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
-                            st_eval += 1;
-                            if (Lk > best) {
-                                best = Lk;
-                                bestj = j;
-                                best_pse = pse;
-                            }
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = j4 + e;
+                        const unsigned dk = __vabsdiffu4(kk[e], mykey);
+                        if (j >= nlive || (int)__dp4a(dk, dk, 0u) > key_thr) continue;
+                        double cr_, cg_, cb_;
+                        load_colour<T>(block, cap, j, cr_, cg_, cb_);
+                        const S_t dr = ob_r[r] - (S_t)cr_, dg = ob_g[r] - (S_t)cg_, db = ob_b[r] - (S_t)cb_;
+                        if (fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate) continue;
+                        load_landmark<T>(block, cap, j, L);
+                        L_j = j;
+                        const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                           ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
+                        extra_evals += 1;
+                        if (Lk > best) {
+                            best = Lk;
+                            bestj[r] = j;
+                            best_pse[r] = pse;
                         }
                     }
                 }
             }
-            if (R > 1 && act) {
-                S.bj[w] = bestj;
-                S.factor[w] = (double)best_pse;
-            }
+            if (__any_sync(kFull, cnt > kMaxHits)) st_eval += __reduce_add_sync(kFull, extra_evals);
         }
-        if (R > 1) __syncwarp();
         // ---- sequential updates (:88-124) in scan order -------------------------------------------
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int w = r * 32 + lane;
             const bool act = w < nitems;
-            const int pl = act ? it_pl[r] : 0, k = act ? it_k[r] : 0;
+            const int pl = act ? it_pl[r] : 0;
             unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1];
-            if (R > 1) {
-                bestj = act ? S.bj[w] : -1;
-                best_pse = act ? (S_t)S.factor[w] : (S_t)0;
-                lastj = -1;  // records are re-read: an earlier round may have rewritten them
+            const bool matched = act && bestj[r] >= 0;
+            // items on the same landmark of the same particle go one after the other (finding F2); that can
+            // only happen when two blobs of the frame have close colours
+            int rank = 0, maxrank = 0;
+            if (twins) {
+                const int key = matched ? (pl * cap + bestj[r]) : (-1 - lane);
+                const unsigned peers = __match_any_sync(kFull, key);
+                rank = __popc(peers & lt);
+                maxrank = __reduce_max_sync(kFull, matched ? rank : 0);
             }
-            const bool matched = act && bestj >= 0;
-            // items on the same landmark of the same particle go one after the other
-            const int key = matched ? (pl * cap + bestj) : (-1 - lane);
-            const unsigned peers = __match_any_sync(kFull, key);
-            const int rank = __popc(peers & lt);
-            const int maxrank = __reduce_max_sync(kFull, matched ? rank : 0);
             double factor = A.prm.no_match_weight;  // :95 / :851-857
             int id_out = 0;
+            int promoted = 0;
             for (int q = 0; q <= maxrank; ++q) {
                 if (matched && rank == q) {
-                    // the winner's record is in registers unless another candidate was evaluated after
-                    // it, or an earlier blob of this frame has just rewritten the landmark
-                    const bool fresh = (q > 0 || lastj != bestj);
-                    if (fresh) load_landmark<T>(block, cap, bestj, L);
-                    int promoted = 0;
+                    // The winner's PRE-update record is in registers, or still in its staging slot; after an
+                    // earlier blob of this frame rewrote the landmark (q > 0) it is read back from global memory.
+                    // (with two rounds of items, a blob of the first round may have done so as well)
+                    const bool stale = q > 0 || (R > 1 && r > 0 && twins);
+                    if (stale)
+                        load_landmark<T>(block, cap, bestj[r], L);
+                    else if (R > 1 || L_j != bestj[r]) {
+                        if (win_c[r] >= 0)
+                            load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)win_c[r]) * 32u * R + (unsigned)w) * kRecBytes, L);
+                        else
+                            load_landmark<T>(block, cap, bestj[r], L);
+                    }
                     bool changed = false;
-                    // the bearing computed during association is that of the PRE-update landmark: it can be
-                    // re-used only if no earlier blob of this frame has moved the landmark since
-                    // L holds the stored colours here, so its key is the one in the hot region: the fp32 instantiation is
-                    // memory-latency bound and skips the key store when the update leaves the key alone (-8 % K2 time,
-                    // ~0.5 GB less DRAM traffic per launch); the fp64 one is issue bound, where the extra key costs 2 %
+                    // L holds the stored colours here, so its key is the one in the hot region: the fp32 instantiation
+                    // skips the key store when the update leaves the key alone (a 4-byte store dirties a 32-byte sector)
                     const unsigned key_before = (sizeof(LM) == sizeof(LandmarkF)) ? stored_key(L, Rec<T>::kDtype) : kNoKey;
+                    // the bearing computed during association is that of the PRE-update landmark: it is re-used
+                    // unless an earlier blob of this frame has moved the landmark since
                     factor = ekf_update_lm(L, px, py, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], A.prm, id_out, st_flags,
-                                           promoted, changed, !fresh, best_pse);
-                    if (changed) store_landmark<T>(block, cap, bestj, L, key_before);
-                    st_promoted += promoted;
-                    if (q > 0) st_same += 1;
+                                           promoted, changed, !stale, best_pse[r]);
+                    if (changed) store_landmark<T>(block, cap, bestj[r], L, key_before);
                 }
                 if (maxrank > 0) __syncwarp();
             }
-            if (act) {
-                A.assoc[(p0 + pl) * K + k] = id_out;
-                if (R > 1) {
-                    S.factor[w] = factor;
-                    S.ids[w] = id_out;
-                }
-                if (matched) st_matched += 1; else st_unmatched += 1;
+            if (maxrank > 0) st_same += __popc(__ballot_sync(kFull, matched && rank > 0));
+            if (act) (A.assoc + (size_t)p0 * K)[w] = id_out;
+            {
+                const unsigned bm = __ballot_sync(kFull, matched), ba = __ballot_sync(kFull, act);
+                st_matched += __popc(bm);
+                st_unmatched += __popc(ba & ~bm);
+                const unsigned bp = __ballot_sync(kFull, promoted != 0);
+                if (bp) st_promoted += __popc(bp);
             }
+            if (act) S.factor[w] = factor;
+            // add_orphaned_reading bumps next_id once per unseen blob (:745-746)
+            const unsigned unseen = __ballot_sync(kFull, act && id_out == 0);
             if (R == 1) {
-                // particles[i].weight = 1 (:73); weight *= factor in scan order (:95, :124): every lane folds the K
-                // factors of its own particle (lanes pl*K .. pl*K+K-1), the particle's first lane stores
-                const int base = pl * K;
-                double wgt = 1.0;
-                for (int k2 = 0; k2 < K; ++k2) wgt *= __shfl_sync(kFull, factor, base + k2);
-                const unsigned unseen = __ballot_sync(kFull, act && id_out == 0);
-                if (act && k == 0) {
+                __syncwarp();
+                // particles[i].weight = 1 (:73); weight *= factor in scan order (:95, :124): the first lane of a
+                // particle folds its K factors left to right
+                if (act && it_k[0] == 0) {
+                    const int base = pl * K;
+                    double wgt = 1.0;
+                    for (int k2 = 0; k2 < K; ++k2) wgt *= S.factor[base + k2];
                     if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
-                    A.pose4[4 * (p0 + pl) + 3] = wgt;
-                    // add_orphaned_reading bumps next_id once per unseen blob (:745-746)
+                    A.pose4[4 * (size_t)(p0 + pl) + 3] = wgt;
                     const int orphans = __popc((unseen >> base) & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)));
-                    if (orphans) A.aux2[2 * (p0 + pl) + 1] += orphans;
+                    if (orphans) A.aux2[2 * (size_t)(p0 + pl) + 1] += orphans;
                 }
+            } else {
+                // one particle per group: count the unseen blobs of both rounds in lane 0
+                if (lane == 0) S.unseen_acc = (r == 0 ? 0 : S.unseen_acc) + __popc(unseen);
+                __syncwarp();  // also orders this round's record stores before the next round's loads
             }
         }
         if (R > 1) {
             __syncwarp();
-            if (lane < gpn) {
+            if (lane == 0 && gpn > 0) {
                 double wgt = 1.0;
-                int orphans = 0;
-                for (int k = 0; k < K; ++k) {
-                    wgt *= S.factor[lane * K + k];
-                    orphans += (S.ids[lane * K + k] == 0);
-                }
+                for (int k = 0; k < K; ++k) wgt *= S.factor[k];
                 if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
-                A.pose4[4 * (p0 + lane) + 3] = wgt;
-                if (orphans) A.aux2[2 * (p0 + lane) + 1] += orphans;
+                A.pose4[4 * (size_t)p0 + 3] = wgt;
+                const int orphans = S.unseen_acc;
+                if (orphans) A.aux2[2 * (size_t)p0 + 1] += orphans;
             }
         }
         __syncwarp();
@@ -552,28 +568,22 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     Hits Hcur[R], Hnext[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
-    for (long long git = -1; git < my_groups; ++git) {
-        if (git + 1 < my_groups) screen(git + 1, Hnext);
-        if (git >= 0) evaluate(git, Hcur, git + 1 < my_groups);
+    for (int s = 0; s < kStages - 1; ++s) produce_one();
+    for (int it = -1; it < my_groups; ++it) {
+        if (it + 1 < my_groups) screen(it + 1, Hnext);
+        if (it >= 0) evaluate(it, Hcur, it + 1 < my_groups);
 #pragma unroll
         for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r];
     }
 
     // ---- statistics: one atomic per warp per counter ------------------------------------------------
-    for (int o = 16; o > 0; o >>= 1) {
-        st_matched += __shfl_xor_sync(kFull, st_matched, o);
-        st_unmatched += __shfl_xor_sync(kFull, st_unmatched, o);
-        st_eval += __shfl_xor_sync(kFull, st_eval, o);
-        st_same += __shfl_xor_sync(kFull, st_same, o);
-        st_promoted += __shfl_xor_sync(kFull, st_promoted, o);
-        st_flags |= __shfl_xor_sync(kFull, st_flags, o);
-    }
+    st_flags = __reduce_or_sync(kFull, st_flags);
     if (lane == 0 && A.stats != nullptr) {
-        if (st_matched) atomicAdd(&A.stats[PK_STAT_MATCHED], st_matched);
-        if (st_unmatched) atomicAdd(&A.stats[PK_STAT_UNMATCHED], st_unmatched);
-        if (st_eval) atomicAdd(&A.stats[PK_STAT_EVALUATED], st_eval);
-        if (st_same) atomicAdd(&A.stats[PK_STAT_SAME_LANDMARK], st_same);
-        if (st_promoted) atomicAdd(&A.stats[PK_STAT_PROMOTED], st_promoted);
+        if (st_matched) atomicAdd(&A.stats[PK_STAT_MATCHED], (unsigned long long)st_matched);
+        if (st_unmatched) atomicAdd(&A.stats[PK_STAT_UNMATCHED], (unsigned long long)st_unmatched);
+        if (st_eval) atomicAdd(&A.stats[PK_STAT_EVALUATED], (unsigned long long)st_eval);
+        if (st_same) atomicAdd(&A.stats[PK_STAT_SAME_LANDMARK], (unsigned long long)st_same);
+        if (st_promoted) atomicAdd(&A.stats[PK_STAT_PROMOTED], (unsigned long long)st_promoted);
         if (st_flags) atomicOr(&A.stats[PK_STAT_FLAGS], (unsigned long long)st_flags);
     }
 }
@@ -585,20 +595,18 @@ __global__ void reset_weight_kernel(double* __restrict__ pose4, long long M) {
 
 template <typename T, int R, typename LM>
 static int launch_measure(MeasureArgs& args, cudaStream_t st) {
-    static int configured_smem = -1;
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     args.keys_off = (int)align128(sizeof(WarpSmemT<R>));
     args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
     args.warp_smem = (int)align128(args.rec_off + (size_t)2 * staged_candidates<T, LM>() * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
-    if ((int)smem > configured_smem) {
+    // the attribute is per device (a process may run filters on several): set it on every launch, it is cheap
+    if (smem > 48 * 1024)
         PK_CUDA(cudaFuncSetAttribute(measure_kernel<T, R, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_smem = (int)smem;
-    }
     int ctas_per_sm = 0;
     PK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, measure_kernel<T, R, LM>, kWarpsPerCta * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const long long n_groups = (args.M + args.group - 1) / args.group;
+    const long long n_groups = ((long long)args.M + args.group - 1) / args.group;
     long long grid = (long long)num_sms() * ctas_per_sm;
     const long long need = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
@@ -620,9 +628,18 @@ using namespace pk;
 
 // blob table from a device-resident scan: one thread per blob, the arithmetic of the host path
 // (closest_point :510 / utils.py:69-76 with separate roundings; cos/sin are CUDA's, <= 2 ulp from libm)
-__global__ void obs_table_kernel(const double* __restrict__ obs, int K, pk::ObsTable* __restrict__ tab) {
+__global__ void obs_table_kernel(const double* __restrict__ obs, int K, double color_gate, pk::ObsTable* __restrict__ tab) {
     const int k = threadIdx.x;
     if (k >= PK_MAX_OBS) return;
+    // does any other blob have a colour close enough to share a landmark with blob k?  (ObsTable::twins)
+    bool tw = false;
+    if (k < K)
+        for (int k2 = 0; k2 < K; ++k2)
+            if (k2 != k && pk::blobs_may_share_landmark(obs[4 * k + 1], obs[4 * k + 2], obs[4 * k + 3], obs[4 * k2 + 1],
+                                                        obs[4 * k2 + 2], obs[4 * k2 + 3], color_gate))
+                tw = true;
+    const int any_tw = __syncthreads_or(tw ? 1 : 0);
+    if (k == 0) tab->twins = any_tw ? 1u : 0u;
     if (k >= K) {
         tab->okey[k] = 0u;
         return;
@@ -646,9 +663,11 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
                               const pk_params* params, int* assoc, unsigned long long* stats, void* stream) {
     PK_CHECK_ARG(pose4 && aux2 && slot && pool, "null state pointer");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    PK_CHECK_ARG(M >= 0, "M < 0");
+    PK_CHECK_ARG(M >= 0 && M < (1ll << 31) - 64, "M must be in [0, 2^31 - 64)");
     PK_CHECK_ARG(K >= 0 && K <= PK_MAX_OBS, "K must be in [0, PK_MAX_OBS]");
-    PK_CHECK_ARG(capacity >= 0 && capacity < (1 << 20), "capacity must be < 2^20");
+    PK_CHECK_ARG(capacity >= 0 && capacity < (1 << 16), "capacity must be < 2^16");
+    // record positions travel between lanes as 32-bit offsets in units of 32 bytes
+    PK_CHECK_ARG((double)M * (double)block_bytes(capacity, dtype) < 137438953472.0, "landmark pool must be < 2^37 bytes");
     PK_CHECK_ARG(params != nullptr, "params is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 0) return PK_OK;
@@ -668,8 +687,9 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     args.pool = (unsigned char*)pool;
     args.assoc = assoc;
     args.stats = stats;
-    args.M = M;
+    args.M = (int)M;
     args.block_bytes = block_bytes(capacity, dtype);
+    args.hot_bytes = (unsigned)hot_region_bytes(capacity);
     args.capacity = capacity;
     args.K = K;
     int group = 32 / K;
@@ -680,7 +700,7 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     args.tab_dev = nullptr;
     if (obs_dev != nullptr) {
         PK_CHECK_ARG(table_ws != nullptr, "table workspace is NULL");
-        obs_table_kernel<<<1, PK_MAX_OBS, 0, st>>>(obs_dev, K, (ObsTable*)table_ws);
+        obs_table_kernel<<<1, PK_MAX_OBS, 0, st>>>(obs_dev, K, params->color_gate, (ObsTable*)table_ws);
         PK_LAUNCH_CHECK("obs_table_kernel");
         args.tab_dev = (const ObsTable*)table_ws;
     } else {
@@ -705,6 +725,11 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
             T.diry[k] = s * inv;
             T.okey[k] = key_of(T.cr[k]) | (key_of(T.cg[k]) << 8) | (key_of(T.cb[k]) << 16);
         }
+        T.twins = 0u;
+        for (int k = 0; k < K; ++k)
+            for (int k2 = k + 1; k2 < K; ++k2)
+                if (blobs_may_share_landmark(T.cr[k], T.cg[k], T.cb[k], T.cr[k2], T.cg[k2], T.cb[k2], params->color_gate))
+                    T.twins = 1u;
     }
     // Colour screen bound (DESIGN.md "colour keys").  Keys are the colours clamped to [0,255] and
     // rounded, so per channel |key difference| <= |true difference| + 1.  If the exact gate accepts
