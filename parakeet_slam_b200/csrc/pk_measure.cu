@@ -80,7 +80,7 @@ struct MeasureArgs {
 };
 
 // fixed part of a warp's shared memory; the key ring [kStages][group][kKeyStride] and the record
-// staging area [2][kStaged][32 * R] follow at keys_off / rec_off
+// staging area [kStaged][32 * R] follow at keys_off / rec_off
 template <int R>
 struct alignas(128) WarpSmemT {
     static constexpr int kItems = 32 * R;
@@ -133,7 +133,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     WarpSmem& S = *reinterpret_cast<WarpSmem*>(wbase);
     const uint32_t s_base = smem_u32(wbase);
     const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
-    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [2][kStaged][32 * R] Cold
+    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [kStaged][32 * R] Cold
     const uint32_t s_keybar = smem_u32(&S.key_bar[0]);
     const uint32_t s_pose = smem_u32(&S.pose[0][0][0]);
     const unsigned lt = lanemask_lt();
@@ -190,14 +190,12 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     unsigned p_cnt = 0, s_cnt = 0;  // steps produced / consumed
     int nx_slot = 0, nx_nlive = 0;  // lane pl: slot / n_live of particle pl of the next group to open
     int op_slot = 0, op_nlive = 0;  // ... of the group that is open in the producer
+    // (loaded unconditionally from a clamped index so that the values land in their registers without a
+    // select that would wait for them; lanes that own no particle are zeroed when the group is opened)
     auto fetch_info = [&](int it) {
-        nx_slot = 0;
-        nx_nlive = 0;
-        const int p = (gw + it * total_warps) * GP + lane;
-        if (it < my_groups && lane < GP && p < M) {
-            nx_slot = A.slot[p];
-            nx_nlive = A.aux2[2 * p];
-        }
+        const int p = min((gw + min(it, max(my_groups - 1, 0)) * total_warps) * GP + lane, M - 1);
+        nx_slot = A.slot[p];
+        nx_nlive = A.aux2[2 * p];
     };
     fetch_info(0);
     auto produce_one = [&]() {
@@ -206,8 +204,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         const int p0 = (gw + p_it * total_warps) * GP;
         const int gpn = min(GP, M - p0);
         if (p_step == 0) {  // open the group: publish slot / n_live, prefetch the next group's
-            op_slot = nx_slot;
-            op_nlive = nx_nlive;
+            op_slot = lane < gpn ? nx_slot : 0;
+            op_nlive = lane < gpn ? nx_nlive : 0;
             if (lane < kMaxGroup) {
                 S.slot_s[gi][lane] = op_slot;
                 S.nlive_s[gi][lane] = op_nlive;
@@ -243,19 +241,18 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     unsigned st_matched = 0, st_unmatched = 0, st_eval = 0, st_same = 0, st_promoted = 0;
     unsigned st_flags = 0;
 
-    // ---- screen(it): colour-key screen of group it + record prefetch -------------------------------
-    auto screen = [&](int it, Hits (&H)[R]) {
+    // ---- scan(it): colour-key screen of group it ---------------------------------------------------
+    auto scan = [&](int it, Hits (&H)[R]) {
         const int gi = it & 3, par = it & 1;
         const int p0 = (gw + it * total_warps) * GP;
         const int nitems = min(GP, M - p0) * K;
 #pragma unroll
         for (int r = 0; r < R; ++r) H[r] = Hits{0, -1, -1};
-        int my_nl[R], my_slot[R];
+        int my_nl[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool act = (r * 32 + lane) < nitems;
             my_nl[r] = act ? S.nlive_s[gi][it_pl[r]] : 0;
-            my_slot[r] = act ? S.slot_s[gi][it_pl[r]] : 0;
         }
         int maxnl = my_nl[0];
 #pragma unroll
@@ -307,6 +304,20 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             ++s_cnt;
             produce_one();
         }
+    };
+
+    // ---- prefetch(it): request the cold records of group it's first hits ------------------------------
+    // The staging area is single-buffered: this runs after the association phase of the previous group has
+    // consumed its records (evaluate calls it between its two phases), a whole update phase and key scan
+    // before the records are needed.
+    auto prefetch = [&](int it, const Hits (&H)[R]) {
+        const int gi = it & 3;
+        const int p0 = (gw + it * total_warps) * GP;
+        const int nitems = min(GP, M - p0) * K;
+        int my_slot[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) my_slot[r] = ((r * 32 + lane) < nitems) ? S.slot_s[gi][it_pl[r]] : 0;
+        __syncwarp();  // every lane has read its records of the previous group out of the staging area
         // Request the cold record of each item's first hit into the lane's staging slot.  The 32 slots of a round
         // are consecutive in shared memory, so the warp fetches them TOGETHER: instruction i moves 16-byte chunk
         // i*32+lane of that 32-record strip, i.e. the lanes of one instruction cover whole records (each 32-byte
@@ -318,7 +329,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             {
                 const bool have = H[r].cnt > 0;
                 const unsigned off32 = have ? (unsigned)((rec0 + (size_t)H[r].c0 * kRecBytes) >> 5) : 0xffffffffu;
-                const uint32_t strip = s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)(r * 32)) * kRecBytes;
+                const uint32_t strip = s_rec + (unsigned)(r * 32) * kRecBytes;
 #pragma unroll
                 for (int i = 0; i < kChunksPerRec; ++i) {
                     const int chunk = i * 32 + lane;
@@ -330,7 +341,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             // second hit (one item in ten): fetched by its own lane
             if (kStaged > 1 && H[r].cnt > 1) {
                 const unsigned char* src = A.pool + rec0 + (size_t)H[r].c1 * kRecBytes;
-                const uint32_t dst = s_rec + (((unsigned)par * kStaged + 1u) * 32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
+                const uint32_t dst = s_rec + (32u * R + (unsigned)(r * 32 + lane)) * kRecBytes;
 #pragma unroll
                 for (int i = 0; i < kChunksPerRec; ++i) cp_async16_a(dst + 16u * i, src + 16 * i);
             }
@@ -339,19 +350,21 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     };
 
     // ---- evaluate(it): association arg-max + sequential EKF updates + weight ----------------------
-    auto evaluate = [&](int it, const Hits (&H)[R], bool more_in_flight) {
+    // `Hn` are the hits of the next group (already scanned): its records are requested between the two phases.
+    auto evaluate = [&](int it, const Hits (&H)[R], const Hits (&Hn)[R], bool have_next) {
         const int gi = it & 3, par = it & 1;
         const int p0 = (gw + it * total_warps) * GP;
         const int gpn = min(GP, M - p0);
         const int nitems = gpn * K;
-        // this group's records were committed one group ago; the next group's may still be in flight
-        if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
+        cp_async_wait<0>();
         __syncwarp();  // the first-hit strip was filled cooperatively: other lanes' copies must have landed too
-        // association result per item: winner slot, its bearing, and which staging slot holds its record
+        // association result per item: winner slot and its bearing.  With one item per lane (R == 1) and fp32 algebra
+        // L ends up holding the winner's PRE-update record; otherwise L_j says which record L holds.
+        constexpr bool kKeepWinner = (R == 1) && (sizeof(LM) == sizeof(LandmarkF));
         S_t best_pse[R];
-        int bestj[R], win_c[R];
+        int bestj[R];
         LM L;
-        int L_j = -1;  // landmark slot whose PRE-update record is in L (R == 1 only)
+        int L_j = -1;
         // ---- association (:84, match_features_to_scan): every blob against the PRE-update map ----
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -368,9 +381,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             pre.sure = false;
             best_pse[r] = 0;
             bestj[r] = -1;
-            win_c[r] = -1;
             if (cnt > 0) {
-                load_staged<T>(s_rec + (((unsigned)par * kStaged) * 32u * R + (unsigned)w) * kRecBytes, L);
+                load_staged<T>(s_rec + (unsigned)w * kRecBytes, L);
                 L_j = H[r].c0;
                 pre = match_prepare(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], ob_dx[r], ob_dy[r], A.prm,
                                     st_flags);
@@ -392,20 +404,21 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     if (Lk > 0.0) {
                         best = Lk;
                         bestj[r] = H[r].c0;
-                        win_c[r] = 0;
                         best_pse[r] = pse;
                     }
                 }
             } else if (cnt > 0) {
                 best = 1.0;  // some positive value: never compared against anything
                 bestj[r] = H[r].c0;
-                win_c[r] = 0;
                 best_pse[r] = pse;
             }
             // further colour-compatible landmarks, in slot order.  All warp collectives sit outside the per-lane
             // conditions; lanes with more hits than the hit list holds re-walk their keys afterwards, on their own.
             const int ncand = cnt <= kMaxHits ? cnt : 0;
             const int maxcnt = __reduce_max_sync(kFull, ncand);
+            // candidate record: its own registers when L must keep the best one so far (kKeepWinner), else L itself
+            LM Lc_own;
+            LM& Lc = kKeepWinner ? Lc_own : L;
             for (int c = 1; c < maxcnt; ++c) {
                 // Most extra hits are false positives of the byte-key screen: apply the exact colour
                 // gate (:441) first and run the full likelihood only if some lane still needs it.
@@ -414,23 +427,26 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 if (c < ncand) {
                     j = (c == 1) ? H[r].c1 : (int)S.more_hits[par][w][c - 2];
                     if (c < kStaged)
-                        load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)c) * 32u * R + (unsigned)w) * kRecBytes, L);
+                        load_staged<T>(s_rec + ((unsigned)c * 32u * R + (unsigned)w) * kRecBytes, Lc);
                     else
-                        load_landmark<T>(block, cap, j, L);
-                    L_j = j;
-                    const S_t dr = ob_r[r] - L.r, dg = ob_g[r] - L.g, db = ob_b[r] - L.b;
+                        load_landmark<T>(block, cap, j, Lc);
+                    if (!kKeepWinner) L_j = j;
+                    const S_t dr = ob_r[r] - Lc.r, dg = ob_g[r] - Lc.g, db = ob_b[r] - Lc.b;
                     need = !(fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate);
                 }
                 if (!__any_sync(kFull, need)) continue;
                 st_eval += __popc(__ballot_sync(kFull, need));
                 if (need) {
-                    const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                    const double Lk = match_likelihood(Lc, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
                                                        ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
                     if (Lk > best) {
                         best = Lk;
                         bestj[r] = j;
-                        win_c[r] = c < kStaged ? c : -1;
                         best_pse[r] = pse;
+                        if (kKeepWinner) {
+                            L = Lc;
+                            L_j = j;
+                        }
                     }
                 }
             }
@@ -441,7 +457,6 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 // and the exact colour gate, in slot order.
                 best = 0.0;
                 bestj[r] = -1;
-                win_c[r] = -1;
                 const int nlive = S.nlive_s[gi][pl];
                 const unsigned* gkeys = reinterpret_cast<const unsigned*>(block);
                 const unsigned mykey = it_key[r];
@@ -457,21 +472,27 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                         load_colour<T>(block, cap, j, cr_, cg_, cb_);
                         const S_t dr = ob_r[r] - (S_t)cr_, dg = ob_g[r] - (S_t)cg_, db = ob_b[r] - (S_t)cb_;
                         if (fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate) continue;
-                        load_landmark<T>(block, cap, j, L);
-                        L_j = j;
-                        const double Lk = match_likelihood(L, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                        load_landmark<T>(block, cap, j, Lc);
+                        if (!kKeepWinner) L_j = j;
+                        const double Lk = match_likelihood(Lc, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
                                                            ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
                         extra_evals += 1;
                         if (Lk > best) {
                             best = Lk;
                             bestj[r] = j;
                             best_pse[r] = pse;
+                            if (kKeepWinner) {
+                                L = Lc;
+                                L_j = j;
+                            }
                         }
                     }
                 }
             }
             if (__any_sync(kFull, cnt > kMaxHits)) st_eval += __reduce_add_sync(kFull, extra_evals);
         }
+        // the staged records are consumed: request the next group's into the same staging area
+        if (have_next) prefetch(it + 1, Hn);
         // ---- sequential updates (:88-124) in scan order -------------------------------------------
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -495,18 +516,11 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             int promoted = 0;
             for (int q = 0; q <= maxrank; ++q) {
                 if (matched && rank == q) {
-                    // The winner's PRE-update record is in registers, or still in its staging slot; after an
-                    // earlier blob of this frame rewrote the landmark (q > 0) it is read back from global memory.
-                    // (with two rounds of items, a blob of the first round may have done so as well)
+                    // The winner's PRE-update record is normally still in registers; after an earlier blob of this
+                    // frame rewrote the landmark (q > 0; with two rounds of items, a blob of the first round may have
+                    // done so as well) it is read back from global memory.
                     const bool stale = q > 0 || (R > 1 && r > 0 && twins);
-                    if (stale)
-                        load_landmark<T>(block, cap, bestj[r], L);
-                    else if (R > 1 || L_j != bestj[r]) {
-                        if (win_c[r] >= 0)
-                            load_staged<T>(s_rec + (((unsigned)par * kStaged + (unsigned)win_c[r]) * 32u * R + (unsigned)w) * kRecBytes, L);
-                        else
-                            load_landmark<T>(block, cap, bestj[r], L);
-                    }
+                    if (stale || R > 1 || L_j != bestj[r]) load_landmark<T>(block, cap, bestj[r], L);
                     bool changed = false;
                     // L holds the stored colours here, so its key is the one in the hot region: the fp32 instantiation
                     // skips the key store when the update leaves the key alone (a 4-byte store dirties a 32-byte sector)
@@ -565,13 +579,20 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     };
 
     // ---- software pipeline over this warp's groups -----------------------------------------------
+    // scan(it + 1) -> association(it) -> record prefetch(it + 1) -> updates(it): keys run one group ahead through
+    // the key ring, records one phase ahead through the (single) staging area.
     Hits Hcur[R], Hnext[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
     for (int s = 0; s < kStages - 1; ++s) produce_one();
-    for (int it = -1; it < my_groups; ++it) {
-        if (it + 1 < my_groups) screen(it + 1, Hnext);
-        if (it >= 0) evaluate(it, Hcur, it + 1 < my_groups);
+    if (my_groups > 0) {
+        scan(0, Hcur);
+        prefetch(0, Hcur);
+    }
+    for (int it = 0; it < my_groups; ++it) {
+        const bool have_next = it + 1 < my_groups;
+        if (have_next) scan(it + 1, Hnext);
+        evaluate(it, Hcur, Hnext, have_next);
 #pragma unroll
         for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r];
     }
@@ -598,7 +619,7 @@ static int launch_measure(MeasureArgs& args, cudaStream_t st) {
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     args.keys_off = (int)align128(sizeof(WarpSmemT<R>));
     args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
-    args.warp_smem = (int)align128(args.rec_off + (size_t)2 * staged_candidates<T, LM>() * 32 * R * sizeof(typename Rec<T>::Cold));
+    args.warp_smem = (int)align128(args.rec_off + (size_t)staged_candidates<T, LM>() * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
     // the attribute is per device (a process may run filters on several): set it on every launch, it is cheap
     if (smem > 48 * 1024)
