@@ -439,6 +439,10 @@ __device__ __forceinline__ void cp_async16_a(uint32_t dst, const void* src_gmem)
     // .L2::64B: fetch only the record's 64-byte half of the 128-byte line on an L2 miss (see ldcg16_rec)
     asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(dst), "l"(src_gmem) : "memory");
 }
+// same for streams that cover whole 128-byte lines anyway (keys, poses): default L2 fetch size
+__device__ __forceinline__ void cp_async16_line(uint32_t dst, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -323,6 +323,24 @@ __device__ __forceinline__ float pk_atan2f(float y, float x) {
     return copysignf(r, y);
 }
 
+// exp(x) for an fp32 argument with an fp64 RESULT (the importance factor spans hundreds of decades, finding F3, but
+// its argument -maha/2 comes out of fp32 algebra): n = rint(x log2 e), 2^f by the hardware ex2 on the compensated
+// remainder f = x log2 e - n (|f| <= 1/2, abs. error ~3e-8), scaled by 2^n in two exact steps so that the last
+// multiply rounds once into the subnormal range (or to 0).  Relative error ~3e-7, fifteen instructions instead of
+// the fifty of the fp64 polynomial.
+__device__ __forceinline__ double pk_exp_f2d(float x) {
+    const float t = x * 1.44269502162933349609375f;
+    const float n = rintf(t);
+    float f = fmaf(x, 1.44269502162933349609375f, -n);
+    f = fmaf(x, 1.925963033500011e-8f, f);
+    const float m = exp2f(f);
+    int ni = (int)fminf(fmaxf(n, -1100.0f), 1100.0f);
+    const int n1 = ni >> 1, n2 = ni - n1;
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0);
+    const double s2 = __hiloint2double((n2 + 1023) << 20, 0);
+    return ((double)m * s1) * s2;
+}
+
 struct MatchPreF {
     float a2, a3, pse;
     bool gated;
@@ -367,11 +385,11 @@ __device__ __forceinline__ MatchPreF match_prepare(const LandmarkF& L, double px
 }
 
 // rank value: 0 = no match, otherwise increasing with the likelihood (log domain, shifted positive)
-__device__ __forceinline__ double match_finish(const MatchPreF& m) {
-    return m.sure ? (double)(m.a2 + m.a3) + 2048.0 : 0.0;
+__device__ __forceinline__ float match_finish(const MatchPreF& m) {
+    return m.sure ? (m.a2 + m.a3) + 2048.0f : 0.0f;
 }
 
-__device__ __forceinline__ double match_likelihood(const LandmarkF& L, double px, double py, double pth, float beta, float orr,
+__device__ __forceinline__ float match_likelihood(const LandmarkF& L, double px, double py, double pth, float beta, float orr,
                                                    float og, float ob, float dirx, float diry, const pk_params& prm,
                                                    unsigned& flags, float& pse_out) {
     const MatchPreF m = match_prepare(L, px, py, pth, beta, orr, og, ob, dirx, diry, prm, flags);
@@ -410,34 +428,36 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
     const float y3 = d1 * I20 + d2 * I21 + d3 * I22;
     const float maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
     // importance_factor :844-849: the exp and the product that follows stay fp64 (weights span hundreds of decades)
-    double factor = (double)rsqrtf(2.0f * 3.14159265358979f * fro) * pk_exp(-0.5 * (double)maha);
+    double factor = (double)rsqrtf(2.0f * 3.14159265358979f * fro) * pk_exp_f2d(-0.5f * maha);
 
     bool changed = false;
     if (!(L.meta & PK_META_IMMUTABLE)) {
-        const float kp0 = (a * hx + b * hy) * inv_s, kp1 = (b * hx + d * hy) * inv_s;  // :833
+        // kalman_gain :833  K = Sigma H^T Qinv.  Position block: kp = Sigma_p h / s.  Colour block: Kc = Sigma_c Sc^-1,
+        // symmetric because Sc = Sigma_c + qt I commutes with Sigma_c -- six entries instead of nine.
+        const float kp0 = t0 * inv_s, kp1 = t1 * inv_s;
         const float c00 = L.sc[0], c10 = L.sc[1], c11 = L.sc[2], c20 = L.sc[3], c21 = L.sc[4], c22 = L.sc[5];
-        const float K00 = c00 * I00 + c10 * I10 + c20 * I20, K01 = c00 * I10 + c10 * I11 + c20 * I21,
-                    K02 = c00 * I20 + c10 * I21 + c20 * I22;
-        const float K10 = c10 * I00 + c11 * I10 + c21 * I20, K11 = c10 * I10 + c11 * I11 + c21 * I21,
-                    K12 = c10 * I20 + c11 * I21 + c21 * I22;
-        const float K20 = c20 * I00 + c21 * I10 + c22 * I20, K21 = c20 * I10 + c21 * I11 + c22 * I21,
-                    K22 = c20 * I20 + c21 * I21 + c22 * I22;
+        const float K00 = c00 * I00 + c10 * I10 + c20 * I20;
+        const float K10 = c10 * I00 + c11 * I10 + c21 * I20;
+        const float K11 = c10 * I10 + c11 * I11 + c21 * I21;
+        const float K20 = c20 * I00 + c21 * I10 + c22 * I20;
+        const float K21 = c20 * I10 + c21 * I11 + c22 * I21;
+        const float K22 = c20 * I20 + c21 * I21 + c22 * I22;
         L.x += kp0 * d0;                                                                  // :909-914
         L.y += kp1 * d0;
-        L.r += K00 * d1 + K01 * d2 + K02 * d3;
-        L.g += K10 * d1 + K11 * d2 + K12 * d3;
+        L.r += K00 * d1 + K10 * d2 + K20 * d3;
+        L.g += K10 * d1 + K11 * d2 + K21 * d3;
         L.b += K20 * d1 + K21 * d2 + K22 * d3;
-        const float m00 = 1.0f - kp0 * hx, m01 = -(kp0 * hy), m10 = -(kp1 * hx), m11 = 1.0f - kp1 * hy;   // :926-930
-        L.sp[0] = m00 * a + m01 * b;
-        L.sp[1] = m10 * a + m11 * b;
-        L.sp[2] = m10 * b + m11 * d;
-        const float A00 = 1.0f - K00, A10 = -K10, A11 = 1.0f - K11, A20 = -K20, A21 = -K21, A22 = 1.0f - K22;
-        L.sc[0] = A00 * c00 - K01 * c10 - K02 * c20;
-        L.sc[1] = A10 * c00 + A11 * c10 - K12 * c20;
-        L.sc[2] = A10 * c10 + A11 * c11 - K12 * c21;
-        L.sc[3] = A20 * c00 + A21 * c10 + A22 * c20;
-        L.sc[4] = A20 * c10 + A21 * c11 + A22 * c21;
-        L.sc[5] = A20 * c20 + A21 * c21 + A22 * c22;
+        // update_covar :926-930  Sigma <- (I - K H) Sigma, as algebra on the stored (lower-triangle) blocks:
+        // position  (I - kp h^T) Sigma_p = Sigma_p - kp (Sigma_p h)^T;  colour  (I - Kc) Sigma_c = qt Sc^-1 Sigma_c = qt Kc
+        L.sp[0] = a - kp0 * t0;
+        L.sp[1] = b - kp1 * t0;
+        L.sp[2] = d - kp1 * t1;
+        L.sc[0] = qt * K00;
+        L.sc[1] = qt * K10;
+        L.sc[2] = qt * K11;
+        L.sc[3] = qt * K20;
+        L.sc[4] = qt * K21;
+        L.sc[5] = qt * K22;
         int cnt = (L.meta & PK_META_COUNT_MASK) + 2;
         if (cnt > PK_META_COUNT_MASK) cnt = PK_META_COUNT_MASK;
         L.meta = (L.meta & ~PK_META_COUNT_MASK) | cnt;

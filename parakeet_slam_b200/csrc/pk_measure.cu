@@ -90,7 +90,6 @@ struct alignas(128) WarpSmemT {
     int nlive_s[4][kMaxGroup];
     unsigned short more_hits[2][kItems][kMaxHits - 2];  // third and later hits of an item (rare)
     int unseen_acc;  // R > 1: unseen blobs of the particle, summed over the rounds
-    uint64_t key_bar[kStages];
 };
 static_assert(kMaxItems == 64, "R <= 2");
 
@@ -134,7 +133,6 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     const uint32_t s_base = smem_u32(wbase);
     const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
     const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [kStaged][32 * R] Cold
-    const uint32_t s_keybar = smem_u32(&S.key_bar[0]);
     const uint32_t s_pose = smem_u32(&S.pose[0][0][0]);
     const unsigned lt = lanemask_lt();
 
@@ -176,15 +174,14 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         ob_dy[r] = (S_t)OT->diry[k];
     }
 
-    if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&S.key_bar[s], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
     // ---- key producer (warp-uniform state) -----------------------------------------------------
     // A flat sequence of steps (group, 64-key chunk) goes through the ring of kStages key stages; produce_one()
     // issues the next step and is called once per consumed step, so the producer stays kStages - 1 steps ahead.
+    // Keys and poses move with per-thread 16-byte cp.async copies (LDGSTS): a lane owns one 16-byte piece, 16 lanes
+    // cover a particle's 64 keys, so one instruction requests whole 128-byte lines -- no mbarrier, no proxy fence,
+    // no per-lane waterfall over uniform bulk-copy operands (this replaced 1-D cp.async.bulk copies; a warp-private
+    // stream of 1 KB per step gains nothing from the bulk engine).  Every call commits exactly ONE cp.async group
+    // (empty when there is nothing left), and so does prefetch(): the wait_group counts below rely on that.
     // Group info buffers are indexed it & 3: group it is being evaluated, it + 1 screened, it + 2 may be open.
     int p_it = 0, p_step = 0, p_ns = 1;
     unsigned p_cnt = 0, s_cnt = 0;  // steps produced / consumed
@@ -199,42 +196,40 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     };
     fetch_info(0);
     auto produce_one = [&]() {
-        if (p_it >= my_groups) return;
-        const int gi = p_it & 3;
-        const int p0 = (gw + p_it * total_warps) * GP;
-        const int gpn = min(GP, M - p0);
-        if (p_step == 0) {  // open the group: publish slot / n_live, prefetch the next group's
-            op_slot = lane < gpn ? nx_slot : 0;
-            op_nlive = lane < gpn ? nx_nlive : 0;
-            if (lane < kMaxGroup) {
-                S.slot_s[gi][lane] = op_slot;
-                S.nlive_s[gi][lane] = op_nlive;
+        if (p_it < my_groups) {
+            const int gi = p_it & 3;
+            const int p0 = (gw + p_it * total_warps) * GP;
+            const int gpn = min(GP, M - p0);
+            if (p_step == 0) {  // open the group: publish slot / n_live, fetch its poses, prefetch the next group's info
+                op_slot = lane < gpn ? nx_slot : 0;
+                op_nlive = lane < gpn ? nx_nlive : 0;
+                if (lane < kMaxGroup) {
+                    S.slot_s[gi][lane] = op_slot;
+                    S.nlive_s[gi][lane] = op_nlive;
+                }
+                p_ns = max(1, (__reduce_max_sync(kFull, op_nlive) + kChunk - 1) / kChunk);
+                fetch_info(p_it + 1);
+                if (lane < 2 * gpn)
+                    cp_async16_line(s_pose + (uint32_t)gi * (kMaxGroup * 32) + 16u * (unsigned)lane,
+                                    reinterpret_cast<const unsigned char*>(A.pose4 + 4 * (size_t)p0) + 16 * lane);
             }
-            p_ns = max(1, (__reduce_max_sync(kFull, op_nlive) + kChunk - 1) / kChunk);
-            fetch_info(p_it + 1);
+            const unsigned stage = p_cnt % kStages;
+            for (int c0 = 0; c0 < GP * (kChunk / 4); c0 += 32) {
+                const int c = c0 + lane;
+                const int pl = min(c >> 4, GP - 1), ch = c & 15;
+                const int nl = __shfl_sync(kFull, op_nlive, pl) - p_step * kChunk;  // live keys of this chunk
+                const int sl = __shfl_sync(kFull, op_slot, pl);
+                if (c < GP * (kChunk / 4) && ch * 4 < nl)
+                    cp_async16_line(s_keys + ((stage * (unsigned)GP + (unsigned)pl) * kKeyStride) * 4u + 16u * (unsigned)ch,
+                                    A.pool + (size_t)sl * A.block_bytes + (size_t)(p_step * kChunk * 4 + 16 * ch));
+            }
+            ++p_cnt;
+            if (++p_step >= p_ns) {
+                p_step = 0;
+                ++p_it;
+            }
         }
-        const unsigned stage = p_cnt % kStages;
-        const int nl = max(0, min(kChunk, op_nlive - p_step * kChunk));  // 0 on lanes >= gpn
-        const unsigned bytes = ((unsigned)nl * 4u + 15u) & ~15u;
-        const unsigned total = __reduce_add_sync(kFull, bytes) + (p_step == 0 ? (unsigned)(gpn * 32) : 0u);
-        fence_proxy_async();
-        const uint32_t bar = s_keybar + stage * 8u;
-        if (lane == 0) {
-            mbar_arrive_expect_tx_a(bar, total);
-            if (p_step == 0) tma_load_1d_a(s_pose + (uint32_t)gi * (kMaxGroup * 32), A.pose4 + 4 * (size_t)p0, (unsigned)(gpn * 32), bar);
-        }
-        __syncwarp();
-        // every lane moves its own particle's keys.  (cp.async.bulk takes warp-uniform operands, so this
-        // compiles to a short waterfall over the <= 8 issuing lanes; issuing all copies from lane 0 in a
-        // loop was measured slower.)
-        if (bytes)
-            tma_load_1d_a(s_keys + ((stage * (unsigned)GP + (unsigned)lane) * kKeyStride) * 4u,
-                          A.pool + (size_t)op_slot * A.block_bytes + (size_t)(p_step * kChunk * 4), bytes, bar);
-        ++p_cnt;
-        if (++p_step >= p_ns) {
-            p_step = 0;
-            ++p_it;
-        }
+        cp_async_commit();
     };
 
     // statistics: warp-uniform 32-bit counts (one warp sees < 2^31 items), folded into the 64-bit totals at the end
@@ -260,7 +255,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         const int nsteps = max(1, (__reduce_max_sync(kFull, maxnl) + kChunk - 1) / kChunk);
         for (int step = 0; step < nsteps; ++step) {
             const unsigned stage = s_cnt % kStages;
-            mbar_wait_a(s_keybar + stage * 8u, (s_cnt / kStages) & 1u);
+            // this step's keys: one newer group (the previous group's records) is in flight at step 0, none later
+            if (step == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int pl = min(it_pl[r], GP - 1);
@@ -286,17 +283,29 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 // keys beyond n_live are stale: mask them (nl <= 0 clears everything)
                 const unsigned vlo = nl >= 32 ? 0xffffffffu : (nl > 0 ? (1u << nl) - 1u : 0u);
                 const unsigned vhi = nl >= 64 ? 0xffffffffu : (nl > 32 ? (1u << (nl - 32)) - 1u : 0u);
-                unsigned mh[2] = {__brev(lo) & vlo, __brev(hi) & vhi};
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    unsigned m = mh[h];
-                    while (m) {  // about one hit per item in the whole chunk
-                        const int j = step * kChunk + 32 * h + __ffs((int)m) - 1;
-                        m &= m - 1u;
-                        if (H[r].cnt == 0) H[r].c0 = j;
-                        else if (H[r].cnt == 1) H[r].c1 = j;
-                        else if (H[r].cnt < kMaxHits) S.more_hits[par][r * 32 + lane][H[r].cnt - 2] = (unsigned short)j;
-                        H[r].cnt += 1;
+                const unsigned mlo = __brev(lo) & vlo, mhi = __brev(hi) & vhi;
+                // about one hit per item: the first two are extracted without branches, the rest in a rare loop
+                const int n = __popc(mlo) + __popc(mhi);
+                const int base = step * kChunk;
+                const int j0 = base + (mlo ? __ffs((int)mlo) - 1 : 31 + __ffs((int)mhi));
+                const unsigned mlo2 = mlo & (mlo - 1u), mhi2 = mlo ? mhi : (mhi & (mhi - 1u));
+                const int j1 = base + (mlo2 ? __ffs((int)mlo2) - 1 : 31 + __ffs((int)mhi2));
+                const int c_before = H[r].cnt;
+                if (c_before == 0) {
+                    if (n > 0) H[r].c0 = j0;
+                    if (n > 1) H[r].c1 = j1;
+                } else if (c_before == 1) {
+                    if (n > 0) H[r].c1 = j0;
+                }
+                H[r].cnt = c_before + n;
+                if (__any_sync(kFull, c_before + n > 2)) {
+                    unsigned ma = mlo, mb = mhi;
+                    int idx = c_before;
+                    while (ma | mb) {
+                        const int j = base + (ma ? __ffs((int)ma) - 1 : 31 + __ffs((int)mb));
+                        if (ma) ma &= ma - 1u; else mb &= mb - 1u;
+                        if (idx >= 2 && idx < kMaxHits) S.more_hits[par][r * 32 + lane][idx - 2] = (unsigned short)j;
+                        ++idx;
                     }
                 }
             }
@@ -356,7 +365,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         const int p0 = (gw + it * total_warps) * GP;
         const int gpn = min(GP, M - p0);
         const int nitems = gpn * K;
-        cp_async_wait<0>();
+        cp_async_wait<1>();  // all but the newest group (the keys requested at the end of the last scan)
         __syncwarp();  // the first-hit strip was filled cooperatively: other lanes' copies must have landed too
         // association result per item: winner slot and its bearing.  With one item per lane (R == 1) and fp32 algebra
         // L ends up holding the winner's PRE-update record; otherwise L_j says which record L holds.
@@ -375,10 +384,11 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
             const int cnt = act ? H[r].cnt : 0;
             // match_one :353-381: arg-max, strict '>' from 0.0, first (lowest slot) maximum wins
-            double best = 0.0;
-            S_t pse = 0;
             Pre_t pre;
             pre.sure = false;
+            // likelihood (fp64 algebra) or log-domain rank (fp32 algebra) of the best landmark so far
+            auto best = decltype(match_finish(pre))(0);
+            S_t pse = 0;
             best_pse[r] = 0;
             bestj[r] = -1;
             if (cnt > 0) {
@@ -400,15 +410,15 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
 #endif
             if (need_any) {
                 if (cnt > 0) {
-                    const double Lk = match_finish(pre);
-                    if (Lk > 0.0) {
+                    const auto Lk = match_finish(pre);
+                    if (Lk > 0) {
                         best = Lk;
                         bestj[r] = H[r].c0;
                         best_pse[r] = pse;
                     }
                 }
             } else if (cnt > 0) {
-                best = 1.0;  // some positive value: never compared against anything
+                best = 1;  // some positive value: never compared against anything
                 bestj[r] = H[r].c0;
                 best_pse[r] = pse;
             }
@@ -437,8 +447,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 if (!__any_sync(kFull, need)) continue;
                 st_eval += __popc(__ballot_sync(kFull, need));
                 if (need) {
-                    const double Lk = match_likelihood(Lc, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
-                                                       ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
+                    const auto Lk = match_likelihood(Lc, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                     ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
                     if (Lk > best) {
                         best = Lk;
                         bestj[r] = j;
@@ -455,7 +465,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 // More colour-compatible landmarks than hit registers: walk the particle's keys again
                 // (from global memory this time) and evaluate every landmark that passes the key screen
                 // and the exact colour gate, in slot order.
-                best = 0.0;
+                best = 0;
                 bestj[r] = -1;
                 const int nlive = S.nlive_s[gi][pl];
                 const unsigned* gkeys = reinterpret_cast<const unsigned*>(block);
@@ -474,8 +484,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                         if (fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate) continue;
                         load_landmark<T>(block, cap, j, Lc);
                         if (!kKeepWinner) L_j = j;
-                        const double Lk = match_likelihood(Lc, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
-                                                           ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
+                        const auto Lk = match_likelihood(Lc, px, py, pth, ob_beta[r], ob_r[r], ob_g[r], ob_b[r],
+                                                         ob_dx[r], ob_dy[r], A.prm, st_flags, pse);
                         extra_evals += 1;
                         if (Lk > best) {
                             best = Lk;
@@ -552,6 +562,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 if (act && it_k[0] == 0) {
                     const int base = pl * K;
                     double wgt = 1.0;
+#pragma unroll 4
                     for (int k2 = 0; k2 < K; ++k2) wgt *= S.factor[base + k2];
                     if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
                     A.pose4[4 * (size_t)(p0 + pl) + 3] = wgt;
@@ -585,13 +596,14 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
 #pragma unroll
     for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r] = Hits{0, -1, -1};
     for (int s = 0; s < kStages - 1; ++s) produce_one();
+    cp_async_commit();  // stands for the records of a previous group: scan() waits for all but the newest group
     if (my_groups > 0) {
         scan(0, Hcur);
         prefetch(0, Hcur);
     }
     for (int it = 0; it < my_groups; ++it) {
         const bool have_next = it + 1 < my_groups;
-        if (have_next) scan(it + 1, Hnext);
+        if (have_next) scan(it + 1, Hnext); else cp_async_commit();  // (keeps the group count evaluate() waits on)
         evaluate(it, Hcur, Hnext, have_next);
 #pragma unroll
         for (int r = 0; r < R; ++r) Hcur[r] = Hnext[r];
