@@ -4,17 +4,18 @@ try:  # pragma: no cover - depends on the host having ROS
     import rospy
     from geometry_msgs.msg import Quaternion, Twist
     from nav_msgs.msg import Odometry
+    from viz_feature_sim.msg import Blob
 
     def now():
         return rospy.Time.now()
 
     HAVE_ROS = not getattr(rospy, "__rosless__", False)
 except ImportError:
-    from .rosless import Odometry, Quaternion, Time, Twist
+    from .rosless import Blob, Odometry, Quaternion, Time, Twist
 
     def now():
         return Time.now()
 
     HAVE_ROS = False
 
-__all__ = ["Odometry", "Quaternion", "Twist", "now", "HAVE_ROS"]
+__all__ = ["Blob", "Odometry", "Quaternion", "Twist", "now", "HAVE_ROS"]

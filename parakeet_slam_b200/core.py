@@ -26,6 +26,7 @@ import numpy as np
 
 from . import _lib
 from ._ros import Odometry, Quaternion, Twist, now as _ros_now
+from .particle_math import ParticleMathMixin
 
 __all__ = ["FastSLAM", "FilterParticle", "Feature", "ParticleList", "Matrix"]
 
@@ -142,11 +143,13 @@ def _feature_from_arrays(mean5, covp, covc, meta):
 # --------------------------------------------------------------------------------------------
 # FilterParticle  (prkt_core_v2.py:278-879) -- host-side view / container
 # --------------------------------------------------------------------------------------------
-class FilterParticle(object):
+class FilterParticle(ParticleMathMixin):
     """One particle as the reference exposes it: ``state`` (Odometry), ``weight``,
     ``feature_set`` {id>0: Feature}, ``potential_features`` {id<0: Feature},
     ``hypothesis_set``, ``next_id`` (``:279-292``).  Objects returned by
-    ``FastSLAM.particles[i]`` are snapshots copied from the device."""
+    ``FastSLAM.particles[i]`` are snapshots copied from the device.  The scalar helper methods
+    of ``:457-877`` (``prob_position_match`` ... ``generate_measurement``) come from
+    ``particle_math.ParticleMathMixin``; ``probability_of_match`` / ``match_one`` run on the device."""
 
     def __init__(self, state=None):
         if state is None:
@@ -471,6 +474,10 @@ class FastSLAM(object):
                 self.last_pose_pre = self.pose[:, :3].clone()
 
     cam_observation_update = measurement_update       # v1 lineage name (prkt_core.py:205)
+
+    def odom_motion_update(self, odom):
+        """``:140-146`` -- "***Alpha feature***": the reference's body is ``pass``; kept for interface parity."""
+        return None
 
     # -- motion: motion_update / motion_model (:148-208) -------------------------------------------
     def motion_update(self, new_twist):

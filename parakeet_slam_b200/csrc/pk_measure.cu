@@ -195,6 +195,10 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         nx_nlive = A.aux2[2 * p];
     };
     fetch_info(0);
+    // key copies: this lane's piece of a particle's 64-key chunk
+    const int kc_ch = lane & 15, kc_pl = lane >> 4;
+    const uint32_t kc_dst = s_keys + (unsigned)kc_pl * (kKeyStride * 4u) + 16u * (unsigned)kc_ch;
+    const unsigned char* kc_src = A.pool + 16 * kc_ch;
     auto produce_one = [&]() {
         if (p_it < my_groups) {
             const int gi = p_it & 3;
@@ -214,14 +218,16 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                                     reinterpret_cast<const unsigned char*>(A.pose4 + 4 * (size_t)p0) + 16 * lane);
             }
             const unsigned stage = p_cnt % kStages;
-            for (int c0 = 0; c0 < GP * (kChunk / 4); c0 += 32) {
-                const int c = c0 + lane;
-                const int pl = min(c >> 4, GP - 1), ch = c & 15;
-                const int nl = __shfl_sync(kFull, op_nlive, pl) - p_step * kChunk;  // live keys of this chunk
+            // lane -> 16-byte piece kc_ch of particle kc_pl (+2 per round): two shuffles, one 64-bit multiply-add
+            // and one copy per round
+            const uint32_t dst0 = kc_dst + stage * (unsigned)GP * (kKeyStride * 4u);
+            const int first_key = p_step * kChunk + 4 * kc_ch;  // first key of this lane's piece
+            for (int pl0 = 0; pl0 < GP; pl0 += 2) {
+                const int pl = min(pl0 + kc_pl, GP - 1);
+                const int nl = __shfl_sync(kFull, op_nlive, pl);
                 const int sl = __shfl_sync(kFull, op_slot, pl);
-                if (c < GP * (kChunk / 4) && ch * 4 < nl)
-                    cp_async16_line(s_keys + ((stage * (unsigned)GP + (unsigned)pl) * kKeyStride) * 4u + 16u * (unsigned)ch,
-                                    A.pool + (size_t)sl * A.block_bytes + (size_t)(p_step * kChunk * 4 + 16 * ch));
+                if (pl0 + kc_pl < GP && first_key < nl)
+                    cp_async16_line(dst0 + (unsigned)pl0 * (kKeyStride * 4u), kc_src + (size_t)sl * A.block_bytes + (size_t)(p_step * kChunk * 4));
             }
             ++p_cnt;
             if (++p_step >= p_ns) {
@@ -524,7 +530,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             double factor = A.prm.no_match_weight;  // :95 / :851-857
             int id_out = 0;
             int promoted = 0;
-            for (int q = 0; q <= maxrank; ++q) {
+            for (int q = 0;; ++q) {
                 if (matched && rank == q) {
                     // The winner's PRE-update record is normally still in registers; after an earlier blob of this
                     // frame rewrote the landmark (q > 0; with two rounds of items, a blob of the first round may have
@@ -541,7 +547,8 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                                            promoted, changed, !stale, best_pse[r]);
                     if (changed) store_landmark<T>(block, cap, bestj[r], L, key_before);
                 }
-                if (maxrank > 0) __syncwarp();
+                if (q >= maxrank) break;
+                __syncwarp();
             }
             if (maxrank > 0) st_same += __popc(__ballot_sync(kFull, matched && rank > 0));
             if (act) (A.assoc + (size_t)p0 * K)[w] = id_out;
@@ -562,8 +569,17 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 if (act && it_k[0] == 0) {
                     const int base = pl * K;
                     double wgt = 1.0;
-#pragma unroll 4
-                    for (int k2 = 0; k2 < K; ++k2) wgt *= S.factor[base + k2];
+                    if (K == 8) {  // the usual scan size: four 16-byte loads, eight multiplications
+                        const double2* f2 = reinterpret_cast<const double2*>(&S.factor[base]);
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            const double2 v = f2[k2];
+                            wgt *= v.x;
+                            wgt *= v.y;
+                        }
+                    } else {
+                        for (int k2 = 0; k2 < K; ++k2) wgt *= S.factor[base + k2];
+                    }
                     if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
                     A.pose4[4 * (size_t)(p0 + pl) + 3] = wgt;
                     const int orphans = __popc((unseen >> base) & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)));
