@@ -226,15 +226,34 @@ int pk_resample_thresholds(const double* all_block_sums, long long nb_total, lon
 /* K4: for the local particles (global index particle_offset + i, scan blocks starting at
  * block_offset) compute each one's run of output slots [out_lo[i], out_lo[i]+offspring[i]) and
  * write ancestors[k - out_offset] = particle_offset + i for every output k of the local output
- * window [out_offset, out_offset + n_out).  big_runs: workspace of >= 4 + 3*M_local int64. */
+ * window [out_offset, out_offset + n_out).  big_runs: workspace of 4 + 3*R int64, R = the most runs of MORE than 16
+ * equal ancestors the window can hold = min(M_local, n_out / 17 + 2) (a counter and R triples: ancestor, first and
+ * one-past-last slot; such runs are written by a second kernel). */
 int pk_resample_ancestors(const double* cumsum, long long M_local, long long particle_offset,
                           long long block_offset, const double* plan, const double* block_prefix,
                           const long long* block_count, long long M_total, long long out_offset,
                           long long n_out, long long* out_lo, int* offspring, long long* ancestors,
                           long long* big_runs, void* stream);
 
+/* K4 and the first step of K5 in ONE kernel (what the filters call every frame): pk_resample_ancestors' outputs for the
+ * window [out_offset, out_offset + n_out) -- runs of any length, no big_runs list -- plus, into gather_workspace
+ * (pk_gather_workspace_bytes(M_local)), each local particle's offspring count INSIDE the window and the per-scan-block
+ * exclusive count of particles that have none (their landmark block is free).  Follow with
+ * pk_resample_gather_planned (single GPU: window = [0, M)) or pk_resample_gather_peer (window = this rank's slots). */
+int pk_resample_plan(const double* cumsum, long long M_local, long long particle_offset,
+                     long long block_offset, const double* plan, const double* block_prefix,
+                     const long long* block_count, long long M_total, long long out_offset,
+                     long long n_out, long long* out_lo, int* offspring, long long* ancestors,
+                     void* gather_workspace, void* stream);
+
 /* ---- K5 copy-on-resample: the deepcopy(particle) of prkt_core_v2.py:243 ---------------------- */
 long long pk_gather_workspace_bytes(long long M);
+/* pk_resample_gather after pk_resample_plan(window [0, M)) has filled `workspace`: free-block list (each scan block
+ * adds up the dead counts before it), pose / aux / slot permutation, block copies -- three launches. */
+int pk_resample_gather_planned(const long long* ancestors, long long M, const double* pose4_in,
+                               double* pose4_out, const int* aux2_in, int* aux2_out,
+                               const int* slot_in, int* slot_out, void* pool, int capacity, int dtype,
+                               void* workspace, long long* n_copied_out, void* stream);
 /* Single-GPU form.  ancestors[M] ascending (int64, local indices).  Survivors keep their landmark
  * block; every extra copy of a particle is written into the block of a particle that died
  * (#copies == #dead).  pose/aux are permuted out of place.  n_copied_out (device int64) receives
@@ -313,7 +332,7 @@ int pk_push_particles(const long long* xplan, const long long* out_lo, long long
                       int capacity, int dtype, const unsigned long long* peer_recv_tab,
                       long long send_capacity, int* workspace, void* stream);
 /* pk_resample_gather_sharded with the window split read from xplan; anc_window[Ml] = global ancestor
- * of each local output slot (as written by pk_resample_ancestors with out_offset = rank * Ml). */
+ * of each local output slot and `workspace` as left by pk_resample_plan with out_offset = rank * Ml, n_out = Ml. */
 int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const long long* out_lo, const int* offspring, long long Ml,
                             long long particle_offset, const double* pose4_in, double* pose4_out,

@@ -204,3 +204,103 @@ def run_reference(scn: Scenario, frames=None, num_particles=None, record_landmar
     trace.setdefault("frames_run", T)
     trace["filter"] = fs
     return trace
+
+
+class ReferenceStepper(object):
+    """The unmodified reference advanced ONE ``cam_cb`` frame at a time (for timing: ``bench.py``'s reference arm
+    and ``cpu_baseline`` leg).  Nothing is recorded; ``step()`` returns the wall-clock seconds of the frame."""
+
+    def __init__(self, scn: Scenario, ref=None, seed=None):
+        if ref is None:
+            ref = ref_shim.load_reference(with_ros_node=False)
+        self.ref = ref
+        self.scn = scn
+        self.fs = build_reference_filter(ref, scn)
+        twist = ref.msgs.Twist()
+        twist.linear.x = scn.v
+        twist.angular.z = scn.w
+        self.fs.last_control = twist
+        np.random.seed(scn.motion_seed if seed is None else seed)
+        _pyrandom.seed(scn.meta.get("resample_seed", 12345) if seed is None else seed)
+        self.view = _View()
+        self.t = 0
+
+    def step(self) -> float:
+        import time
+        scn = self.scn
+        clock.advance_nsec(int(round(scn.dt * 1e9)))
+        self.view.last_sensor_reading = scan_from_observations(scn.observations[self.t % scn.frames], self.ref.msgs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            self.fs.cam_cb(self.view)
+            dt = time.perf_counter() - t0
+        self.t += 1
+        return dt
+
+    @property
+    def updates_per_frame(self) -> int:
+        return len(self.fs.particles) * self.scn.obs_per_frame
+
+
+def _replica_main(conn, scenario_kwargs, seed):
+    """Worker process of ``ReplicaPool``: one reference filter, stepped on request."""
+    try:
+        from parakeet_slam_b200.scenario import make_scenario
+        stepper = ReferenceStepper(make_scenario(**scenario_kwargs), seed=seed)
+        conn.send(("ready", stepper.updates_per_frame))
+        while True:
+            msg = conn.recv()
+            if msg == "stop":
+                break
+            conn.send(("done", stepper.step()))
+    except Exception as exc:  # pragma: no cover - reported to the parent
+        conn.send(("error", repr(exc)))
+    finally:
+        conn.close()
+
+
+class ReplicaPool(object):
+    """``n`` independent replicas of the (single-threaded) reference, one process per host core, advanced in
+    lock-step: how the reference would use a whole host (SURVEY.md 8(d) "CPU reference timing")."""
+
+    def __init__(self, n, scenario_kwargs, first_seed=1000):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.conns, self.procs = [], []
+        for i in range(n):
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_replica_main, args=(child, scenario_kwargs, first_seed + i), daemon=True)
+            p.start()
+            self.conns.append(parent)
+            self.procs.append(p)
+        self.updates_per_frame = 0
+        for c in self.conns:
+            kind, val = c.recv()
+            if kind != "ready":
+                self.close()
+                raise RuntimeError("reference replica failed to start: %s" % (val,))
+            self.updates_per_frame += val
+
+    def step(self) -> float:
+        """One frame on every replica; returns the wall-clock seconds until the slowest has finished."""
+        import time
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send("step")
+        for c in self.conns:
+            kind, val = c.recv()
+            if kind != "done":
+                raise RuntimeError("reference replica failed: %s" % (val,))
+        return time.perf_counter() - t0
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send("stop")
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()

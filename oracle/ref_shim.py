@@ -12,8 +12,10 @@ top of the fake ROS modules of ``parakeet_slam_b200.rosless``.  The resulting
 classes ARE the reference implementation; golden vectors under ``tests/golden``
 are produced from them by ``oracle/make_golden.py``.
 
-``/root/reference`` exists only in the development container, so everything here
-degrades to ``available() == False`` on the GPU box.
+``/root/reference`` exists only in the development container.  ``oracle/build_ref.py`` byte-compiles the same
+(substituted) module texts into ``oracle/_ref/*.pyc`` -- build outputs, git-ignored, shipped with a ``gpurun``
+snapshot -- and the loader falls back to those code objects when the sources are absent, so the GPU box can
+still execute the unmodified reference (``available()`` says which, ``origin()`` says from where).
 """
 from __future__ import annotations
 
@@ -28,7 +30,16 @@ _REF_MODULE_NAMES = ("matrix", "utils", "prkt_core_v2", "prkt_ros")
 
 
 def available(src_dir: str = REFERENCE_SRC) -> bool:
-    return os.path.isfile(os.path.join(src_dir, "prkt_core_v2.py"))
+    """Can the reference be executed here (from its sources, or from the compiled ``oracle/_ref``)?"""
+    from . import build_ref
+    return os.path.isfile(os.path.join(src_dir, "prkt_core_v2.py")) or build_ref.built()
+
+
+def origin(src_dir: str = REFERENCE_SRC) -> str:
+    from . import build_ref
+    if os.path.isfile(os.path.join(src_dir, "prkt_core_v2.py")):
+        return "source:" + src_dir
+    return "bytecode:" + build_ref.OUT_DIR if build_ref.built() else "absent"
 
 
 class ReferenceModules(object):
@@ -44,22 +55,34 @@ class ReferenceModules(object):
 
 
 def _exec_source(name: str, path: str, extra_globals=None) -> types.ModuleType:
-    with open(path, "r") as fh:
-        text = fh.read()
-    for old, new in _PY2_SUBSTITUTIONS:
-        text = text.replace(old, new)
+    if os.path.isfile(path):
+        with open(path, "r") as fh:
+            text = fh.read()
+        for old, new in _PY2_SUBSTITUTIONS:
+            text = text.replace(old, new)
+        code = compile(text, path, "exec")
+    else:
+        from . import build_ref
+        code = build_ref.load_code(os.path.splitext(os.path.basename(path))[0])
+        if code is None:
+            raise RuntimeError("reference module %r: neither %s nor its compiled form under oracle/_ref exists"
+                               % (name, path))
     mod = types.ModuleType(name)
     mod.__file__ = path
     if extra_globals:
         mod.__dict__.update(extra_globals)
     sys.modules[name] = mod
-    code = compile(text, path, "exec")
     exec(code, mod.__dict__)
     return mod
 
 
-def load_reference(src_dir: str = REFERENCE_SRC, with_ros_node: bool = True) -> ReferenceModules:
+def load_reference(src_dir: str = REFERENCE_SRC, with_ros_node: bool = True, core_module=None) -> ReferenceModules:
     """Load matrix/utils/prkt_core_v2 (and prkt_ros) from ``src_dir``.
+
+    ``core_module``: a module to stand in for ``prkt_core_v2`` -- the DROP-IN (``parakeet_slam_b200.dropin.
+    prkt_core_v2``).  The reference's ``prkt_ros.py`` (and, through ``load_reference_tests``, its unit tests) then
+    run unmodified on top of the device core: ``from prkt_core_v2 import FastSLAM, Feature`` (``prkt_ros.py:13``)
+    resolves to it, exactly as putting ``dropin/`` ahead on ``sys.path`` would.
 
     The fake ROS modules are installed into ``sys.modules`` only while the
     reference files execute their imports; the reference module names
@@ -81,7 +104,11 @@ def load_reference(src_dir: str = REFERENCE_SRC, with_ros_node: bool = True) -> 
     try:
         out.matrix = _exec_source("matrix", os.path.join(src_dir, "matrix.py"))
         out.utils = _exec_source("utils", os.path.join(src_dir, "utils.py"))
-        out.core = _exec_source("prkt_core_v2", os.path.join(src_dir, "prkt_core_v2.py"))
+        if core_module is not None:
+            out.core = core_module
+            sys.modules["prkt_core_v2"] = core_module
+        else:
+            out.core = _exec_source("prkt_core_v2", os.path.join(src_dir, "prkt_core_v2.py"))
         if with_ros_node:
             out.ros = _exec_source("prkt_ros", os.path.join(src_dir, "prkt_ros.py"))
     finally:

@@ -9,13 +9,16 @@ try:  # pragma: no cover - depends on the host having ROS
     def now():
         return rospy.Time.now()
 
+    Publisher = rospy.Publisher
     HAVE_ROS = not getattr(rospy, "__rosless__", False)
 except ImportError:
     from .rosless import Blob, Odometry, Quaternion, Time, Twist
+
+    from .rosless.fake_rospy import Publisher
 
     def now():
         return Time.now()
 
     HAVE_ROS = False
 
-__all__ = ["Blob", "Odometry", "Quaternion", "Twist", "now", "HAVE_ROS"]
+__all__ = ["Blob", "Odometry", "Publisher", "Quaternion", "Twist", "now", "HAVE_ROS"]

@@ -25,7 +25,7 @@ import threading
 import numpy as np
 
 from . import _lib
-from ._ros import Odometry, Quaternion, Twist, now as _ros_now
+from ._ros import Odometry, Publisher, Quaternion, Twist, now as _ros_now
 from .particle_math import ParticleMathMixin
 
 __all__ = ["FastSLAM", "FilterParticle", "Feature", "ParticleList", "Matrix"]
@@ -219,13 +219,21 @@ class FilterParticle(ParticleMathMixin):
         self.next_id += 1
 
 
-class ParticleList(object):
+class ParticleList(list):
     """``FastSLAM.particles``: a read-only sequence whose items are fetched from the device on
     access (copying a million Python objects per frame is what the reference spends 76 % of its
-    time on; the device keeps particles as structure-of-arrays instead)."""
+    time on; the device keeps particles as structure-of-arrays instead).  A ``list`` subclass because
+    the reference's attribute is one (``test_prkt_ros2.py:43``); the list storage itself stays empty."""
 
     def __init__(self, owner):
+        super(ParticleList, self).__init__()
         self._owner = owner
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __repr__(self):
+        return "<ParticleList of %d particles on %s>" % (len(self), self._owner._device)
 
     def __len__(self):
         return self._owner.num_particles
@@ -264,6 +272,10 @@ class FastSLAM(object):
     within ``pair_gate`` (default ``sqrt(300)``), the pair is triangulated into a potential landmark
     (id < 0) that is promoted after three updates.  ``orphan_capacity`` readings are kept per particle
     (a ring; the reference keeps them for ever).  Needs ``capacity`` > number of preset landmarks.
+    ``publish_particles=n`` (> 0): publish the pose of a bounded, evenly strided sub-sample of at most ``n`` particles per
+    frame on the reference's three debugging topics ``/particle_track``, ``/aged_particles`` and ``/resampled_particles``
+    (``:55-57, 127, 237, 242``; the reference publishes EVERY particle, which at 10^6 particles would be the whole
+    frame time).  Default 0: nothing is published and no pose leaves the device.
     ``arithmetic="f32"`` (with ``dtype="f32"`` only): the landmark algebra of the fused kernel -- gates, Mahalanobis
     forms, EKF gain and covariance update -- runs in fp32 on the fp32 records; poses, the importance weights and the
     whole resampling stay fp64 (``PK_DTYPE_ARITH_F32``).  The throughput mode: >= 90 % of the reference's indices.
@@ -271,7 +283,7 @@ class FastSLAM(object):
 
     def __init__(self, preset_features=[], *, num_particles=50, capacity=None, dtype="f64",
                  device=None, noise="numpy", seed=0, uniform=None, clock=None, params=None,
-                 spawn=False, orphan_capacity=32, pair_gate=300.0 ** 0.5, arithmetic="f64"):
+                 spawn=False, orphan_capacity=32, pair_gate=300.0 ** 0.5, arithmetic="f64", publish_particles=0):
         import torch
 
         _lib.require_device()
@@ -322,6 +334,12 @@ class FastSLAM(object):
         self._alloc()
         self._load_presets(preset_features)
         self.particles = ParticleList(self)           # :42-49
+        self.publish_particles = int(publish_particles)
+        self.aged_particles_pub = self.resampled_particles_pub = self.particle_track_pub = None
+        if self.publish_particles > 0:                # :55-57
+            self.aged_particles_pub = Publisher('/aged_particles', Odometry, queue_size=1)
+            self.resampled_particles_pub = Publisher('/resampled_particles', Odometry, queue_size=1)
+            self.particle_track_pub = Publisher('/particle_track', Odometry, queue_size=1)
         self.last_stats = {}
         self.last_assoc = None
         self.last_ancestors = None
@@ -408,7 +426,30 @@ class FastSLAM(object):
             scan = ros_view.last_sensor_reading
             obs = self._scan_to_array(scan)
             self.measurement_update(obs)
+            if self.particle_track_pub is not None:
+                self._publish_sample(self.particle_track_pub)          # :126-127
+            if self.aged_particles_pub is not None:
+                self._publish_sample(self.aged_particles_pub)          # :241-242
             self.low_variance_resample()
+            if self.resampled_particles_pub is not None:
+                self._publish_sample(self.resampled_particles_pub)     # :236-237 (the copies that were emitted)
+
+    def _publish_sample(self, pub):
+        """Publish the current pose of at most ``publish_particles`` evenly strided particles as Odometry messages
+        with ``frame_id = 'odom'`` (``:126, 236, 241``): one small device-to-host copy."""
+        torch, M = self._torch, self.num_particles
+        n = min(self.publish_particles, M)
+        if n <= 0:
+            return
+        idx = torch.linspace(0, M - 1, n, device=self._device).round().to(torch.int64)
+        rows = self.pose.index_select(0, idx).cpu().numpy()
+        for x, y, heading, _w in rows:
+            msg = Odometry()
+            msg.header.frame_id = 'odom'
+            msg.pose.pose.position.x = float(x)
+            msg.pose.pose.position.y = float(y)
+            msg.pose.pose.orientation = heading_to_quaternion(float(heading))
+            pub.publish(msg)
 
     @staticmethod
     def _scan_to_array(scan):
@@ -562,18 +603,19 @@ class FastSLAM(object):
             _lib.check(lib.pk_resample_thresholds(_lib.ptr(self._block_sums), self._nb, M, u01,
                                                   _lib.ptr(self._plan), _lib.ptr(self._block_prefix),
                                                   _lib.ptr(self._block_count), st), "pk_resample_thresholds")
-            _lib.check(lib.pk_resample_ancestors(_lib.ptr(self._cumsum), M, 0, 0, _lib.ptr(self._plan),
-                                                 _lib.ptr(self._block_prefix), _lib.ptr(self._block_count), M, 0, M,
-                                                 _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
-                                                 _lib.ptr(self._ancestors), _lib.ptr(self._big_runs), st),
-                       "pk_resample_ancestors")
-            _lib.check(lib.pk_resample_gather(_lib.ptr(self._ancestors), _lib.ptr(self._offspring), M,
-                                              _lib.ptr(self._pose[cur]), _lib.ptr(self._pose[nxt]),
-                                              _lib.ptr(self._aux[cur]), _lib.ptr(self._aux[nxt]),
-                                              _lib.ptr(self._slot[cur]), _lib.ptr(self._slot[nxt]),
-                                              _lib.ptr(self._pool), self.capacity, self._dt,
-                                              _lib.ptr(self._gather_ws), _lib.ptr(self._n_copied), st),
-                       "pk_resample_gather")
+            # K4 + dead-particle scan in one kernel, then free list / permutation / block copies (6 launches in all)
+            _lib.check(lib.pk_resample_plan(_lib.ptr(self._cumsum), M, 0, 0, _lib.ptr(self._plan),
+                                            _lib.ptr(self._block_prefix), _lib.ptr(self._block_count), M, 0, M,
+                                            _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
+                                            _lib.ptr(self._ancestors), _lib.ptr(self._gather_ws), st),
+                       "pk_resample_plan")
+            _lib.check(lib.pk_resample_gather_planned(_lib.ptr(self._ancestors), M,
+                                                      _lib.ptr(self._pose[cur]), _lib.ptr(self._pose[nxt]),
+                                                      _lib.ptr(self._aux[cur]), _lib.ptr(self._aux[nxt]),
+                                                      _lib.ptr(self._slot[cur]), _lib.ptr(self._slot[nxt]),
+                                                      _lib.ptr(self._pool), self.capacity, self._dt,
+                                                      _lib.ptr(self._gather_ws), _lib.ptr(self._n_copied), st),
+                       "pk_resample_gather_planned")
             self._cur = nxt
             if self.keep_trace:
                 self.last_ancestors = self._ancestors.clone()

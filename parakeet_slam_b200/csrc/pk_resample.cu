@@ -357,6 +357,111 @@ free_list_kernel(const int* __restrict__ offspring, const int* __restrict__ slot
     if (offspring[i] == 0) free_list[g] = slot_in[i];
 }
 
+// K4 + G1 in one kernel (one CTA of 1024 threads per scan block): every particle's run of output slots, the
+// ancestors of the output window (runs of any length: long ones are filled by the whole CTA), and the exclusive count
+// of DEAD particles -- particles without an output inside the window, whose landmark block is therefore free -- inside
+// the block.  Replaces ancestors_kernel + fill_runs_kernel + (offspring_window_kernel +) dead_scan_kernel and the
+// big-run list in global memory.
+__global__ void __launch_bounds__(PK_SCAN_BLOCK)
+resample_plan_kernel(const double* __restrict__ cumsum, long long M_local, long long particle_offset, long long block_offset,
+                     const double* __restrict__ plan, const double* __restrict__ block_prefix,
+                     const long long* __restrict__ block_count, long long M_total, long long out_offset, long long n_out,
+                     long long* __restrict__ out_lo, int* __restrict__ offspring, long long* __restrict__ ancestors,
+                     int* __restrict__ offspring_window, int* __restrict__ dead_excl, int* __restrict__ block_dead) {
+    __shared__ long long s_klo[PK_SCAN_BLOCK], s_khi[PK_SCAN_BLOCK];
+    __shared__ int s_who[PK_SCAN_BLOCK];
+    __shared__ int s_nbig;
+    __shared__ int s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long blk = blockIdx.x;
+    const long long i = blk * PK_SCAN_BLOCK + t;
+    if (t == 0) s_nbig = 0;
+    __syncthreads();
+    const bool in = i < M_local;
+    long long klo = 0, khi = 0;
+    if (in) {
+        const double r = plan[1], u0 = plan[2];
+        const long long b = block_offset + blk;
+        const dd P{block_prefix[2 * b], block_prefix[2 * b + 1]};
+        const long long c_lo = block_count[b], c_hi = block_count[b + 1];
+        const long long gi = particle_offset + i;
+        const bool last = (t == PK_SCAN_BLOCK - 1) || (gi == M_total - 1);
+        long long hi = last ? c_hi : min(max(count_le(P, cumsum[i], u0, r, M_total), c_lo), c_hi);
+        long long lo = (t == 0) ? c_lo : min(max(count_le(P, cumsum[i - 1], u0, r, M_total), c_lo), c_hi);
+        if (hi < lo) hi = lo;
+        out_lo[i] = lo;
+        offspring[i] = (int)(hi - lo);
+        klo = max(lo, out_offset);
+        khi = min(hi, out_offset + n_out);
+        if (khi < klo) khi = klo;
+        offspring_window[i] = (int)(khi - klo);
+        if (khi - klo <= kInlineRun) {
+            for (long long k = klo; k < khi; ++k) ancestors[k - out_offset] = gi;
+        } else {
+            const int idx = atomicAdd(&s_nbig, 1);
+            s_who[idx] = t;
+            s_klo[idx] = klo - out_offset;
+            s_khi[idx] = khi - out_offset;
+        }
+    }
+    // dead particles of this block: exclusive count
+    const bool dead = in && (khi == klo);
+    const unsigned bal = __ballot_sync(kFullMask, dead);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        const int v = s_warp[lane];
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += u;
+        }
+        s_warp[lane] = incl - v;
+        if (lane == 31) block_dead[blk] = incl;
+    }
+    __syncthreads();
+    if (in) dead_excl[i] = s_warp[warp] + __popc(bal & lanemask_lt());
+    // long runs (a particle with more than kInlineRun offspring in the window): the whole CTA writes them
+    const int nbig = s_nbig;
+    for (int q = 0; q < nbig; ++q) {
+        const long long gi = particle_offset + blk * PK_SCAN_BLOCK + s_who[q];
+        const long long a = s_klo[q], e = s_khi[q];
+        for (long long k = a + t; k < e; k += PK_SCAN_BLOCK) ancestors[k] = gi;
+    }
+}
+
+// G2 + G3 in one kernel (one CTA per scan block): the block's offset among the dead is the sum of the block totals
+// before it (every CTA adds them up itself: nb ints out of L2, instead of a single-CTA scan kernel in between), and
+// dead particle i donates its block: free_list[rank of i among the dead] = slot[i].
+__global__ void __launch_bounds__(PK_SCAN_BLOCK)
+free_list_fused_kernel(const int* __restrict__ offspring_window, const int* __restrict__ slot_in, long long M,
+                       int* __restrict__ dead_excl, const int* __restrict__ block_dead, long long nb,
+                       int* __restrict__ free_list, long long* __restrict__ total_out) {
+    __shared__ int s_part[32];
+    __shared__ int s_off;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long blk = blockIdx.x;
+    int s = 0;
+    for (long long b = t; b < blk; b += PK_SCAN_BLOCK) s += block_dead[b];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+    if (lane == 0) s_part[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_part[lane];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+        if (lane == 0) {
+            s_off = v;
+            if (blk == nb - 1 && total_out) *total_out = (long long)v + block_dead[blk];
+        }
+    }
+    __syncthreads();
+    const long long i = blk * PK_SCAN_BLOCK + t;
+    if (i >= M) return;
+    const int g = dead_excl[i] + s_off;
+    dead_excl[i] = g;  // now global
+    if (offspring_window[i] == 0) free_list[g] = slot_in[i];
+}
+
 // G4: per output slot k: permute pose/aux, keep or allocate a landmark block
 __global__ void __launch_bounds__(256)
 assign_kernel(const long long* __restrict__ ancestors, long long M, const double* __restrict__ pose_in,
@@ -968,6 +1073,48 @@ int pk_resample_gather(const long long* ancestors, const int* offspring, long lo
     return PK_OK;
 }
 
+int pk_resample_plan(const double* cumsum, long long M_local, long long particle_offset, long long block_offset,
+                     const double* plan, const double* block_prefix, const long long* block_count, long long M_total,
+                     long long out_offset, long long n_out, long long* out_lo, int* offspring, long long* ancestors,
+                     void* gather_workspace, void* stream) {
+    PK_CHECK_ARG(cumsum && plan && block_prefix && block_count && out_lo && offspring && ancestors && gather_workspace,
+                 "null pointer");
+    PK_CHECK_ARG(M_local > 0 && M_local < (1ll << 31) && M_total >= M_local, "sizes");
+    PK_CHECK_ARG(particle_offset % PK_SCAN_BLOCK == 0, "particle_offset must be a multiple of PK_SCAN_BLOCK");
+    GatherWs g = carve(gather_workspace, M_local);
+    const long long nb = num_blocks(M_local);
+    resample_plan_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, (cudaStream_t)stream>>>(
+        cumsum, M_local, particle_offset, block_offset, plan, block_prefix, block_count, M_total, out_offset, n_out, out_lo,
+        offspring, ancestors, g.offspring_local, g.dead_excl, g.block_dead);
+    PK_LAUNCH_CHECK("resample_plan_kernel");
+    return PK_OK;
+}
+
+int pk_resample_gather_planned(const long long* ancestors, long long M, const double* pose4_in, double* pose4_out,
+                               const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out, void* pool,
+                               int capacity, int dtype, void* workspace, long long* n_copied_out, void* stream) {
+    PK_CHECK_ARG(ancestors && pose4_in && pose4_out && aux2_in && aux2_out && slot_in && slot_out && pool && workspace &&
+                     n_copied_out,
+                 "null pointer");
+    PK_CHECK_ARG(M > 0 && M < (1ll << 31), "M");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
+    PK_CHECK_ARG(pose4_in != pose4_out && slot_in != slot_out && aux2_in != aux2_out, "gather is out of place");
+    cudaStream_t st = (cudaStream_t)stream;
+    GatherWs g = carve(workspace, M);
+    const long long nb = num_blocks(M);
+    free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, M, g.dead_excl, g.block_dead, nb,
+                                                                  g.free_list, n_copied_out);
+    PK_LAUNCH_CHECK("free_list_fused_kernel");
+    const int threads = 256;
+    assign_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
+        ancestors, M, pose4_in, pose4_out, aux2_in, aux2_out, slot_in, slot_out, g.dead_excl, g.free_list, g.copy_src,
+        g.copy_dst, g.copy_nlive);
+    PK_LAUNCH_CHECK("assign_kernel");
+    if (capacity > 0)
+        return copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, M, n_copied_out, st);
+    return PK_OK;
+}
+
 long long pk_particle_record_bytes(int capacity, int dtype) {
     return (long long)kHeaderBytes + (long long)block_bytes(capacity, dtype);
 }
@@ -993,7 +1140,7 @@ int pk_pack_particles(const long long* emit_run, long long n, long long particle
     return PK_OK;
 }
 
-static int gather_sharded_impl(const long long* local_run, const long long* xplan, long long recv_capacity,
+static int gather_sharded_impl(bool planned, const long long* local_run, const long long* xplan, long long recv_capacity,
                                const long long* out_lo, const int* offspring, long long Ml, long long particle_offset,
                                long long n_lo, long long n_loc, const double* pose4_in, double* pose4_out,
                                const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out, const void* recv,
@@ -1004,15 +1151,16 @@ static int gather_sharded_impl(const long long* local_run, const long long* xpla
     const long long stride = pk_particle_record_bytes(capacity, dtype);
     const int threads = 256;
     const unsigned grid = (unsigned)((Ml + threads - 1) / threads);
-    offspring_window_kernel<<<grid, threads, 0, st>>>(out_lo, offspring, Ml, particle_offset, g.offspring_local);
-    PK_LAUNCH_CHECK("offspring_window_kernel");
-    dead_scan_kernel<<<(unsigned)((nb + kScanWarps - 1) / kScanWarps), kScanWarps * 32, 0, st>>>(g.offspring_local, Ml,
-                                                                                                 g.dead_excl, g.block_dead, nb);
-    PK_LAUNCH_CHECK("dead_scan_kernel");
-    block_offsets_kernel<<<1, 1024, 0, st>>>(g.block_dead, nb, g.block_off, total_dead_out);
-    PK_LAUNCH_CHECK("block_offsets_kernel");
-    free_list_kernel<<<grid, threads, 0, st>>>(g.offspring_local, slot_in, Ml, g.dead_excl, g.block_off, g.free_list);
-    PK_LAUNCH_CHECK("free_list_kernel");
+    if (!planned) {  // pk_resample_plan has not run for this window: windowed offspring and the dead scan, separately
+        offspring_window_kernel<<<grid, threads, 0, st>>>(out_lo, offspring, Ml, particle_offset, g.offspring_local);
+        PK_LAUNCH_CHECK("offspring_window_kernel");
+        dead_scan_kernel<<<(unsigned)((nb + kScanWarps - 1) / kScanWarps), kScanWarps * 32, 0, st>>>(
+            g.offspring_local, Ml, g.dead_excl, g.block_dead, nb);
+        PK_LAUNCH_CHECK("dead_scan_kernel");
+    }
+    free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, Ml, g.dead_excl, g.block_dead,
+                                                                  nb, g.free_list, total_dead_out);
+    PK_LAUNCH_CHECK("free_list_fused_kernel");
     assign_sharded_kernel<<<grid, threads, 0, st>>>(local_run, Ml, particle_offset, n_lo, n_loc, xplan, pose4_in, pose4_out,
                                                     aux2_in, aux2_out, slot_in, slot_out, (const unsigned char*)recv, stride,
                                                     g.dead_excl, g.free_list, total_dead_out, g.copy_src, g.copy_dst,
@@ -1054,7 +1202,7 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
     PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
     PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    return gather_sharded_impl(local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
+    return gather_sharded_impl(false, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
 }
@@ -1177,7 +1325,7 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                  "null pointer");
     PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31) && recv_capacity >= 0, "sizes");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    return gather_sharded_impl(anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
+    return gather_sharded_impl(true, anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
 }

@@ -80,7 +80,7 @@ def wrap_pi(a):
 
 
 def make_world(num_landmarks: int, layout: str, frames: int, v: float, w: float,
-               seed: int = 2024) -> np.ndarray:
+               seed: int = 2024, num_colors: int | None = None) -> np.ndarray:
     rs = np.random.RandomState(seed)
     lm = np.empty((num_landmarks, 5), dtype=np.float64)
     if layout == "polar":
@@ -95,6 +95,11 @@ def make_world(num_landmarks: int, layout: str, frames: int, v: float, w: float,
     else:
         raise ValueError("unknown layout %r" % (layout,))
     lm[:, 2:5] = rs.uniform(0.0, 255.0, (num_landmarks, 3))
+    if num_colors:
+        # colour-ambiguous world: landmark j wears palette colour j % num_colors, so every blob is colour-compatible
+        # with num_landmarks / num_colors landmarks and the association is decided by the position likelihood
+        palette = np.random.RandomState(seed + 1).uniform(20.0, 235.0, (num_colors, 3))
+        lm[:, 2:5] = palette[np.arange(num_landmarks) % num_colors]
     return lm
 
 
@@ -104,7 +109,7 @@ def make_scenario(name: str = "c1", *, num_particles: int | None = None,
                   layout: str | None = None, sigma_bearing: float = 0.02,
                   sigma_color: float = 0.3, immutable: bool = False,
                   world_seed: int = 2024, obs_seed: int = 7, motion_seed: int = 12345,
-                  resample_seed: int = 12345) -> Scenario:
+                  resample_seed: int = 12345, num_colors: int | None = None) -> Scenario:
     """Build one of the BASELINE.json configurations (or a scaled variant).
 
     ``name``: "c1" (100 x 20, 500 frames, T-circle), "c2" (2^20 x 64, T-corridor),
@@ -129,7 +134,7 @@ def make_scenario(name: str = "c1", *, num_particles: int | None = None,
     w = 0.1 if traj == "circle" else 0.0
     dt = DT
 
-    lm = make_world(N, lay, T, v, 0.1, seed=world_seed)
+    lm = make_world(N, lay, T, v, 0.1, seed=world_seed, num_colors=num_colors)
 
     poses = np.empty((T, 3), dtype=np.float64)
     x = y = th = 0.0
@@ -163,7 +168,7 @@ def make_scenario(name: str = "c1", *, num_particles: int | None = None,
                     immutable=immutable,
                     meta=dict(trajectory=traj, layout=lay, sigma_bearing=sigma_bearing,
                               sigma_color=sigma_color, world_seed=world_seed, obs_seed=obs_seed,
-                              resample_seed=resample_seed))
+                              resample_seed=resample_seed, num_colors=num_colors))
 
 
 def scan_from_observations(obs_frame: np.ndarray, msgs=None):

@@ -97,6 +97,10 @@ class ShardedFastSLAM(FastSLAM):
         super().__init__(preset_features, num_particles=M_total // self.world_size, **kw)
         self.particle_offset = self.rank * self.num_particles
         torch = self._torch
+        # runs of more than 16 equal ancestors are listed for the fill kernel: a window of n_out output slots holds
+        # at most n_out / 17 of them, and here n_out goes up to the GLOBAL particle count (include/parakeet_b200.h)
+        self._big_runs = torch.zeros((4 + 3 * min(self.num_particles, M_total // 17 + 2),), dtype=torch.int64,
+                                     device=self._device)
         G, nb = self.world_size, self._nb
         dev = self._device
         self._all_sums = torch.zeros((G * nb,), dtype=torch.float64, device=dev)
@@ -244,13 +248,14 @@ class ShardedFastSLAM(FastSLAM):
                        "pk_resample_thresholds")
             _lib.check(lib.pk_exchange_plan(_lib.ptr(self._all_count), nb, G, me, Ml, self.exchange_capacity,
                                             _lib.ptr(self._xplan), status, st), "pk_exchange_plan")
-            # ancestors of my own output window (entries owned by other ranks' particles stay untouched)
-            _lib.check(lib.pk_resample_ancestors(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
-                                                 _lib.ptr(self._plan), _lib.ptr(self._all_prefix),
-                                                 _lib.ptr(self._all_count), Mt, me * Ml, Ml,
-                                                 _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
-                                                 _lib.ptr(self._anc_window), _lib.ptr(self._big_runs), st),
-                       "pk_resample_ancestors")
+            # ancestors of my own output window (entries owned by other ranks' particles stay untouched), each local
+            # particle's offspring inside the window and the dead-particle scan, in one kernel
+            _lib.check(lib.pk_resample_plan(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
+                                            _lib.ptr(self._plan), _lib.ptr(self._all_prefix),
+                                            _lib.ptr(self._all_count), Mt, me * Ml, Ml,
+                                            _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
+                                            _lib.ptr(self._anc_window), _lib.ptr(self._gather_ws), st),
+                       "pk_resample_plan")
             # offspring that live on other ranks: header + landmark block straight into their receive buffers
             _lib.check(lib.pk_push_particles(_lib.ptr(self._xplan), _lib.ptr(self._out_lo), Ml, me, _lib.ptr(pose_in),
                                              _lib.ptr(aux_in), _lib.ptr(slot_in), _lib.ptr(self._pool), self.capacity,
