@@ -124,8 +124,21 @@ typedef struct pk_params {
     double no_match_weight;  /* 0.1          prkt_core_v2.py:857 */
     double qt_diag;          /* 0.1          prkt_core_v2.py:50-53 (Qt = qt_diag * I4) */
     int promote_count;       /* 5            prkt_core_v2.py:114 (promote when update_count > 5) */
-    int reserved;
+    int model;               /* 0 = the reference's measurement model, as written (default); PK_MODEL_TEXTBOOK */
 } pk_params;
+/* PK_MODEL_TEXTBOOK: the EKF update with the textbook bearing model instead of the reference's (SURVEY.md finding F4,
+ * section 8(f) row 3): predicted bearing in the ROBOT frame, atan2(dy, dx) - heading (the reference predicts the
+ * world-frame bearing, prkt_core_v2.py:871); Jacobian row [-dy/q, +dx/q] (the reference writes [+dy/q, +dx/q],
+ * :785-797); bearing innovation wrapped to (-pi, pi] (the reference does not wrap, :846, :911).  Association
+ * (probability_of_match) is unchanged.  Not reference behaviour: no reference fixture exists for it; pinned against
+ * the NumPy restatement run with the same switch. */
+#define PK_MODEL_TEXTBOOK 1
+/* PK_MODEL_LOG_WEIGHTS: the importance factors and the particle weight are carried as LOGARITHMS (pose4[.][3] = sum of
+ * the log factors; an unseen blob adds log(no_match_weight)), so a frame of very unlikely observations cannot
+ * underflow every weight to zero as the reference's fp64 product can (finding F3 applies to the association only).
+ * pk_log_weights_max / pk_log_weights_normalise turn them into linear weights exp(lw - max) (largest weight 1)
+ * before the resampling scan; across shards the max and the sums are all-reduced (NCCL) in between. */
+#define PK_MODEL_LOG_WEIGHTS 2
 
 int pk_version(void);
 const char* pk_last_error(void);
@@ -339,6 +352,16 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
                             const void* recv, long long recv_capacity, void* pool, int capacity,
                             int dtype, void* workspace, long long* total_dead_out, void* stream);
+
+/* ---- log-domain weight normaliser (PK_MODEL_LOG_WEIGHTS; north_star "log-sum-exp normalisation") ----------------
+ * pk_log_weights_max: max_out[0] = max_i pose4[i][3] (warp-shuffle + block reduction, fixed order).
+ * pk_log_weights_normalise: pose4[i][3] <- exp(pose4[i][3] - max_in[0]) in place (max_in: this rank's maximum, or the
+ * all-reduced one of a sharded filter), out3 = sum w, sum w^2 of the LOCAL particles and max_in[0]; the caller
+ * all-reduces the sums when sharded: log-sum-exp = max + log(sum w), N_eff = (sum w)^2 / sum w^2.
+ * workspace: 2 * 1024 doubles. */
+int pk_log_weights_max(const double* pose4, long long M, double* max_out, double* workspace, void* stream);
+int pk_log_weights_normalise(double* pose4, long long M, const double* max_in, double* out3, double* workspace,
+                             void* stream);
 
 /* ---- K6 queries: FastSLAM.summary (prkt_core_v2.py:254-276); best particle is additive ------- */
 /* out5[0..3] = sum x, sum y, sum sin(theta), sum cos(theta); out5[4] = M.  The caller finishes

@@ -334,10 +334,24 @@ def add_hypothesis(state: OracleState, i, blob, gate=PAIR_GATE, orphan_capacity=
     return "orphaned"
 
 
-def measurement_update(state: OracleState, obs, ids=None, spawn=False, gate=PAIR_GATE, orphan_capacity=None):
+def wrap_pi(a):
+    """Angle difference wrapped to (-pi, pi] (textbook model only; the reference never wraps, finding F4e)."""
+    a = a - 2.0 * math.pi * np.rint(a / (2.0 * math.pi))
+    return np.where(a <= -math.pi, a + 2.0 * math.pi, a)
+
+
+def measurement_update(state: OracleState, obs, ids=None, spawn=False, gate=PAIR_GATE, orphan_capacity=None,
+                       model="reference"):
     """One frame of ``cam_cb``'s per-particle body after the motion update: weights <- 1
     (``:73``), association of all blobs against the pre-update map (``:84``), then the K
-    sequential updates in scan order (``:88-124``).  Mutates ``state``; returns ids [M,K]."""
+    sequential updates in scan order (``:88-124``).  Mutates ``state``; returns ids [M,K].
+
+    ``model="textbook"`` is NOT reference behaviour: the documented deviation ``PK_MODEL_TEXTBOOK`` of the device
+    library -- robot-frame predicted bearing, Jacobian row ``[-dy/q, +dx/q]``, wrapped bearing
+    innovation -- restated here so that the device build of it has something to be checked against."""
+    textbook = model == "textbook"
+    if model not in ("reference", "textbook"):
+        raise ValueError("model must be 'reference' or 'textbook'")
     M = state.num_particles
     K = obs.shape[0]
     slots = None
@@ -373,6 +387,9 @@ def measurement_update(state: OracleState, obs, ids=None, spawn=False, gate=PAIR
             with np.errstate(divide="ignore", invalid="ignore"):
                 hx = np.where(q == 0, 0.0, dy / q)      # :788-791
                 hy = np.where(q == 0, 0.0, dx / q)      # :794-797
+            if textbook:
+                zhat[:, 0] = zhat[:, 0] - state.pose[r, 2]
+                hx = -hx
             H = np.zeros((len(r), 4, 5))                # :799-802
             H[:, 0, 0] = hx
             H[:, 0, 1] = hy
@@ -385,6 +402,8 @@ def measurement_update(state: OracleState, obs, ids=None, spawn=False, gate=PAIR
             Kg = Sg @ Ht @ Qinv                         # :833
             z = np.broadcast_to(obs[k], (len(r), 4))
             delz = z - zhat                             # :911, :846 (no wrapping)
+            if textbook:
+                delz[:, 0] = wrap_pi(delz[:, 0])
             mut = ~state.immutable[r, j]                # :909, :926
             new_mu = mu + np.einsum("mij,mj->mi", Kg, delz)          # :912-913
             new_Sg = (I5 - Kg @ H) @ Sg                              # :928-929
@@ -468,12 +487,13 @@ def summary(pose):
 # --------------------------------------------------------------------------------------
 # One full frame  (cam_cb :59-137)
 # --------------------------------------------------------------------------------------
-def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=None, spawn=False, orphan_capacity=None):
+def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=None, spawn=False, orphan_capacity=None,
+          model="reference"):
     """motion (``:75-77``) -> association + updates (``:84-124``) -> resample (``:137``).
     Returns (ids [M,K], pre-resample weights [M], ancestors [M], pose_pre [M,3])."""
     state.pose = motion_update(state.pose, noise, v, w, dt)
     pose_pre = state.pose.copy()
-    ids = measurement_update(state, obs, spawn=spawn, orphan_capacity=orphan_capacity)
+    ids = measurement_update(state, obs, spawn=spawn, orphan_capacity=orphan_capacity, model=model)
     wgt = state.weight.copy()
     if sequential_resample is None:
         sequential_resample = state.num_particles <= 4096
@@ -485,7 +505,7 @@ def frame(state: OracleState, obs, noise, v, w, dt, u01, sequential_resample=Non
 
 
 def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), chunk=None, potential_slots=(),
-                 spawn=False, known_map=True, capacity=None, orphan_capacity=None):
+                 spawn=False, known_map=True, capacity=None, orphan_capacity=None, model="reference"):
     """Run the restatement over a ``Scenario`` (same trace layout as
     ``oracle.ref_driver.run_reference``)."""
     T = scn.frames if frames is None else frames
@@ -503,7 +523,7 @@ def run_scenario(scn, frames=None, num_particles=None, record_landmarks_at=(), c
     for t in range(T):
         noise = next(stream)
         ids, wgt, anc, pose_pre = frame(st, scn.observations[t], noise, scn.v, scn.w, scn.dt,
-                                        float(scn.u01[t]), spawn=spawn, orphan_capacity=orphan_capacity)
+                                        float(scn.u01[t]), spawn=spawn, orphan_capacity=orphan_capacity, model=model)
         trace["assoc"][t] = ids
         trace["weight"][t] = wgt
         trace["ancestors"][t] = anc

@@ -43,6 +43,8 @@ PK_FLAG_SINGULAR_COV, PK_FLAG_NONFINITE_WEIGHT, PK_FLAG_REPROMOTED = 1, 2, 4
 PK_FLAG_MAP_FULL, PK_FLAG_ORPHAN_EXPIRED, PK_FLAG_SPAWN_DEGENERATE = 8, 16, 32
 PK_MAX_ORPHANS = 1024
 PK_DTYPE_ARITH_F32 = 0x1000000
+PK_MODEL_TEXTBOOK = 1
+PK_MODEL_LOG_WEIGHTS = 2
 
 
 def dtype_with_orphans(base: int, slots: int) -> int:
@@ -63,7 +65,7 @@ class PkParams(ctypes.Structure):
     _fields_ = [("bearing_gate", ctypes.c_double), ("position_gate", ctypes.c_double),
                 ("color_gate", ctypes.c_double), ("no_match_weight", ctypes.c_double),
                 ("qt_diag", ctypes.c_double), ("promote_count", ctypes.c_int),
-                ("reserved", ctypes.c_int)]
+                ("model", ctypes.c_int)]
 
 
 class ParakeetLibraryError(RuntimeError):
@@ -163,6 +165,8 @@ SIGNATURES = {
     "pk_push_particles": (_I, [_P, _P, _LL, _I, _P, _P, _P, _P, _I, _I, _P, _LL, _P, _P]),
     "pk_resample_gather_peer": (_I, [_P, _P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _P, _I, _I,
                                      _P, _P, _P]),
+    "pk_log_weights_max": (_I, [_P, _LL, _P, _P, _P]),
+    "pk_log_weights_normalise": (_I, [_P, _LL, _P, _P, _P, _P]),
     "pk_summary_partial": (_I, [_P, _LL, _P, _P, _P]),
     "pk_best_particle": (_I, [_P, _LL, _P, _P, _P]),
     "pk_probe_likelihood": (_I, [_P, _P, _P, _P, _P, _P, _LL, ctypes.POINTER(PkParams), _P, _P]),

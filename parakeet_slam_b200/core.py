@@ -272,6 +272,13 @@ class FastSLAM(object):
     within ``pair_gate`` (default ``sqrt(300)``), the pair is triangulated into a potential landmark
     (id < 0) that is promoted after three updates.  ``orphan_capacity`` readings are kept per particle
     (a ring; the reference keeps them for ever).  Needs ``capacity`` > number of preset landmarks.
+    ``measurement_model="textbook"``: the EKF update with the textbook bearing model (robot-frame predicted bearing,
+    Jacobian row ``[-dy/q, +dx/q]``, wrapped innovation) instead of the reference's as-written one (``:785-797, 871``,
+    SURVEY.md finding F4 a/b/e) -- ``PK_MODEL_TEXTBOOK``; a documented deviation, default ``"reference"``.
+    ``weights="log"``: importance factors and particle weights are carried as logarithms (``PK_MODEL_LOG_WEIGHTS``) and
+    turned into linear weights ``exp(lw - max)`` by a log-sum-exp normaliser (warp-shuffle reductions; across shards the
+    maximum and the sums are NCCL all-reduces) right before the resampling scan.  Unlike the reference's fp64 product
+    (``:124``) a frame of very unlikely observations cannot zero every weight.  Default ``"linear"`` = the reference.
     ``publish_particles=n`` (> 0): publish the pose of a bounded, evenly strided sub-sample of at most ``n`` particles per
     frame on the reference's three debugging topics ``/particle_track``, ``/aged_particles`` and ``/resampled_particles``
     (``:55-57, 127, 237, 242``; the reference publishes EVERY particle, which at 10^6 particles would be the whole
@@ -283,7 +290,8 @@ class FastSLAM(object):
 
     def __init__(self, preset_features=[], *, num_particles=50, capacity=None, dtype="f64",
                  device=None, noise="numpy", seed=0, uniform=None, clock=None, params=None,
-                 spawn=False, orphan_capacity=32, pair_gate=300.0 ** 0.5, arithmetic="f64", publish_particles=0):
+                 spawn=False, orphan_capacity=32, pair_gate=300.0 ** 0.5, arithmetic="f64", publish_particles=0,
+                 measurement_model="reference", weights="linear"):
         import torch
 
         _lib.require_device()
@@ -298,6 +306,16 @@ class FastSLAM(object):
         self.num_particles = int(num_particles)        # :41
         self.Qt = Matrix([[.1, 0, 0, 0], [0, .1, 0, 0], [0, 0, .1, 0], [0, 0, 0, .1]])  # :50-53
         self.params = params if params is not None else _lib.default_params()
+        if measurement_model not in ("reference", "textbook"):
+            raise ValueError("measurement_model must be 'reference' or 'textbook'")
+        self.measurement_model = measurement_model
+        if measurement_model == "textbook":
+            self.params.model |= _lib.PK_MODEL_TEXTBOOK
+        if weights not in ("linear", "log"):
+            raise ValueError("weights must be 'linear' or 'log'")
+        self.weights = weights
+        if weights == "log":
+            self.params.model |= _lib.PK_MODEL_LOG_WEIGHTS
 
         if dtype not in ("f32", "f64"):
             raise ValueError("dtype must be 'f32' or 'f64'")
@@ -374,6 +392,8 @@ class FastSLAM(object):
         self._red_ws = torch.zeros((5 * 1024,), dtype=f64, device=dev)
         self._out5 = torch.zeros((5,), dtype=f64, device=dev)
         self._best2 = torch.zeros((2,), dtype=f64, device=dev)
+        self._wmax = torch.zeros((1,), dtype=f64, device=dev)     # log-weight normaliser: maximum log weight
+        self._wstats = torch.zeros((3,), dtype=f64, device=dev)   # ... sum w, sum w^2, max (after normalisation)
         self._assoc = None
         self._obs_table = None
         self._noise_pinned = None
@@ -485,7 +505,7 @@ class FastSLAM(object):
         if K > _lib.PK_MAX_OBS:
             raise ValueError("at most %d blobs per frame (got %d)" % (_lib.PK_MAX_OBS, K))
         with self._lock, self._on_device():
-            if self._assoc is None or self._assoc.shape[1] != K:
+            if self._assoc is None or self._assoc.shape[1] != max(K, 1):
                 self._assoc = torch.zeros((M, max(K, 1)), dtype=torch.int32, device=self._device)
             if on_device:
                 if self._obs_table is None:
@@ -598,6 +618,8 @@ class FastSLAM(object):
             u01 = float(self._uniform())
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
+            if self.weights == "log":
+                self._normalise_log_weights()
             _lib.check(lib.pk_weight_scan(_lib.ptr(self._pose[cur]), M, _lib.ptr(self._cumsum),
                                           _lib.ptr(self._block_sums), st), "pk_weight_scan")
             _lib.check(lib.pk_resample_thresholds(_lib.ptr(self._block_sums), self._nb, M, u01,
@@ -619,6 +641,37 @@ class FastSLAM(object):
             self._cur = nxt
             if self.keep_trace:
                 self.last_ancestors = self._ancestors.clone()
+
+    # -- log-domain weights (weights="log") ----------------------------------------------------------------
+    def _all_reduce_weight_stat(self, tensor, op):
+        """Cross-shard reduction hook of the weight normaliser (no-op on one GPU; NCCL all-reduce when sharded)."""
+        return None
+
+    def _normalise_log_weights(self):
+        """log weights -> linear weights exp(lw - max) in place, with sum w and sum w^2 on the side (log-sum-exp
+        normaliser: max reduction, all-reduce(max), exp + sums, all-reduce(sum))."""
+        lib, M, st = self._lib, self.num_particles, self._stream()
+        _lib.check(lib.pk_log_weights_max(_lib.ptr(self.pose), M, _lib.ptr(self._wmax), _lib.ptr(self._red_ws), st),
+                   "pk_log_weights_max")
+        self._all_reduce_weight_stat(self._wmax, "max")
+        _lib.check(lib.pk_log_weights_normalise(_lib.ptr(self.pose), M, _lib.ptr(self._wmax), _lib.ptr(self._wstats),
+                                                _lib.ptr(self._red_ws), st), "pk_log_weights_normalise")
+        self._all_reduce_weight_stat(self._wstats[:2], "sum")
+
+    def effective_sample_size(self):
+        """N_eff = (sum w)^2 / sum w^2 of the weights of the last measurement update.  ``weights="log"``: from the
+        normaliser of the last resample (also returns the log-sum-exp of the log weights); linear weights: reduced on
+        demand from the current weights (call it before ``low_variance_resample`` permutes them)."""
+        torch, lib, M = self._torch, self._lib, self.num_particles
+        with self._lock, self._on_device():
+            if self.weights == "log":
+                s = self._wstats.cpu().numpy()
+                return float(s[0] * s[0] / s[1]), float(s[2] + math.log(s[0]))
+            w = self.pose[:, 3]
+            t = torch.stack([w.sum(), (w * w).sum()])
+            self._all_reduce_weight_stat(t, "sum")
+            s = t.cpu().numpy()
+        return float(s[0] * s[0] / s[1]) if s[1] > 0 else 0.0, float(math.log(s[0])) if s[0] > 0 else float("-inf")
 
     # -- queries -------------------------------------------------------------------------------------
     def summary(self):
@@ -704,6 +757,17 @@ class FastSLAM(object):
         torch, lib = self._torch, self._lib
         count = len(mean5)
         dev = self._device
+        N = self.capacity
+        if not (0 <= lo and lo + count <= self.num_particles):
+            raise ValueError("import_maps: particles [%d, %d) are outside the filter" % (lo, lo + count))
+        shapes = (np.shape(mean5), np.shape(np.reshape(covp, (count, -1, 4))), np.shape(np.reshape(covc, (count, -1, 9))),
+                  np.shape(meta), np.shape(ids))
+        if shapes != ((count, N, 5), (count, N, 4), (count, N, 9), (count, N), (count, N)):
+            raise ValueError("import_maps: arrays must be shaped [count, capacity=%d, ...] like export_maps' (got %s)"
+                             % (N, shapes,))
+        if n_live is not None and (np.shape(n_live) != (count,) or np.min(n_live, initial=0) < 0
+                                   or np.max(n_live, initial=0) > N):
+            raise ValueError("import_maps: n_live must hold count values in [0, capacity]")
         with self._lock, self._on_device():
             t = [torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev) for a, dt in
                  ((mean5, np.float64), (np.reshape(covp, (count, -1, 4)), np.float64),
@@ -754,15 +818,46 @@ class FastSLAM(object):
         return p
 
     def state_dict(self):
-        """Checkpoint of the device state (host tensors)."""
-        return dict(pose=self.pose.cpu(), aux=self.aux.cpu(), slot=self.slot.cpu(), pool=self._pool.cpu(),
-                    frame=self._frame, capacity=self.capacity, dtype=self.dtype)
+        """Checkpoint of the device state (host tensors) plus what the next frame needs from the host side: the control
+        and time of the last motion update (``:162-166``), the Philox frame counter and the layout it was saved with."""
+        with self._lock, self._on_device():
+            self._torch.cuda.current_stream(self._device).synchronize()
+            lu = self.last_update
+            return dict(pose=self.pose.cpu(), aux=self.aux.cpu(), slot=self.slot.cpu(), pool=self._pool.cpu(),
+                        frame=self._frame, capacity=self.capacity, dtype=self.dtype, layout=int(self._dt),
+                        arithmetic=self.arithmetic, num_particles=self.num_particles, block_bytes=self.block_bytes,
+                        spawn=self.spawn, orphan_capacity=self.orphan_capacity, pair_gate=self.pair_gate,
+                        particle_offset=self.particle_offset,
+                        last_control=(float(self.last_control.linear.x), float(self.last_control.angular.z)),
+                        last_update=(int(getattr(lu, "secs", 0)), int(getattr(lu, "nsecs", 0))))
 
     def load_state_dict(self, sd):
+        """Restore ``state_dict()``.  The filter must have been built with the same layout (particles, capacity,
+        storage type, arithmetic, spawn mode / orphan slots): anything else is refused, not reinterpreted."""
+        mine = dict(capacity=self.capacity, dtype=self.dtype, layout=int(self._dt), arithmetic=self.arithmetic,
+                    num_particles=self.num_particles, block_bytes=self.block_bytes, spawn=self.spawn,
+                    orphan_capacity=self.orphan_capacity)
+        for k, v in mine.items():
+            if k in sd and sd[k] != v:
+                raise ValueError("checkpoint layout mismatch: %s is %r here, %r in the checkpoint" % (k, v, sd[k]))
         if sd["capacity"] != self.capacity or sd["dtype"] != self.dtype:
             raise ValueError("checkpoint layout mismatch")
-        self.pose.copy_(sd["pose"])
-        self.aux.copy_(sd["aux"])
-        self.slot.copy_(sd["slot"])
-        self._pool.copy_(sd["pool"])
-        self._frame = int(sd["frame"])
+        for name, t in (("pose", self.pose), ("aux", self.aux), ("slot", self.slot), ("pool", self._pool)):
+            if tuple(sd[name].shape) != tuple(t.shape) or sd[name].dtype != t.dtype:
+                raise ValueError("checkpoint tensor %r has shape %s / %s, expected %s / %s"
+                                 % (name, tuple(sd[name].shape), sd[name].dtype, tuple(t.shape), t.dtype))
+        with self._lock, self._on_device():
+            self.pose.copy_(sd["pose"])
+            self.aux.copy_(sd["aux"])
+            self.slot.copy_(sd["slot"])
+            self._pool.copy_(sd["pool"])
+            self._frame = int(sd["frame"])
+            self.particle_offset = int(sd.get("particle_offset", self.particle_offset))
+            if "last_control" in sd:
+                tw = Twist()
+                tw.linear.x, tw.angular.z = sd["last_control"]
+                self.last_control = tw
+            if "last_update" in sd and hasattr(self.last_update, "secs"):
+                self.last_update = type(self.last_update)(*sd["last_update"])
+            # the host tensors may be reused or freed by the caller as soon as this returns
+            self._torch.cuda.current_stream(self._device).synchronize()

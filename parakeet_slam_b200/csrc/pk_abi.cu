@@ -23,14 +23,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    // per device (a process may drive filters on several GPUs) and cheap enough to ask every time it matters
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        cached = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+        cached_dev = dev;
     }
     return cached;
 }
@@ -130,7 +130,7 @@ int pk_default_params(pk_params* out) {
     out->no_match_weight = 0.1;                    // prkt_core_v2.py:857
     out->qt_diag = 0.1;                            // prkt_core_v2.py:50-53
     out->promote_count = 5;                        // prkt_core_v2.py:114
-    out->reserved = 0;
+    out->model = 0;                                // the reference's measurement model, as written
     return PK_OK;
 }
 

@@ -198,10 +198,23 @@ __device__ __forceinline__ double match_likelihood(const Landmark& L, double px,
 // One EKF update of landmark j with blob k, block form of reference :98-124.
 // Returns the weight factor; writes the landmark back unless it is immutable.
 // ---------------------------------------------------------------------------------------------
+// wrap an angle difference to (-pi, pi] (PK_MODEL_TEXTBOOK only; the reference never wraps, finding F4e)
+__device__ __forceinline__ double pk_wrap_pi(double a) {
+    const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+    a = a - two_pi * rint(a / two_pi);
+    return (a <= -pi) ? a + two_pi : a;
+}
+__device__ __forceinline__ float pk_wrap_pi(float a) {
+    const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+    a = a - two_pi * rintf(a * 0.15915494309189535f);
+    return (a <= -pi) ? a + two_pi : a;
+}
+
+// `pth`: the particle's heading, used by PK_MODEL_TEXTBOOK only.
 __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double py, double beta, double orr, double og,
                                                 double ob, const pk_params& prm, int& id_out, unsigned& flags,
                                                 int& promoted, bool& changed_out, bool have_zb = false,
-                                                double zb_in = 0.0) {
+                                                double zb_in = 0.0, double pth = 0.0) {
     id_out = L.id;
     const double qt = prm.qt_diag;
     // measurement_jacobian :785-797 (sign and order as written, finding F4b)
@@ -212,6 +225,11 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     // generate_measurement :871 -- world-frame bearing, no heading subtraction (finding F4a)
     // (the association step evaluates the same atan2(fy - sy, fx - sx), :408/:473; reuse it)
     double zb = have_zb ? zb_in : pk_atan2(dy, dx);
+    const bool textbook = (prm.model & PK_MODEL_TEXTBOOK) != 0;
+    if (textbook) {  // d bearing / d(landmark x) = -dy/q, and the robot-frame prediction
+        hx = -hx;
+        zb = zb - pth;
+    }
     double a = L.sp[0], b = L.sp[1], c = L.sp[2], d = L.sp[3];
     // measurement_covariance :817-819   Q = H Sigma H^T + Qt = diag(s) (+) Sc
     double t0 = hx * a + hy * c, t1 = hx * b + hy * d;
@@ -230,6 +248,7 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     double I20 = C02 * idet, I21 = (S01 * S20 - S00 * S21) * idet, I22 = (S00 * S11 - S01 * S10) * idet;
     // innovation :911 / :846 -- no angle wrapping (finding F4e)
     double d0 = beta - zb, d1 = orr - L.r, d2 = og - L.g, d3 = ob - L.b;
+    if (textbook) d0 = pk_wrap_pi(d0);
     // importance_factor :844-849 with the PRE-update Q and z-hat; Frobenius norm of Q (F4d)
     double fro = sqrt(s * s + S00 * S00 + S01 * S01 + S02 * S02 + S10 * S10 + S11 * S11 + S12 * S12 + S20 * S20 +
                       S21 * S21 + S22 * S22);
@@ -237,7 +256,9 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     double y2 = d1 * I01 + d2 * I11 + d3 * I21;
     double y3 = d1 * I02 + d2 * I12 + d3 * I22;
     double maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
-    double factor = (1.0 / sqrt(2.0 * 3.141592653589793 * fro)) * pk_exp(-0.5 * maha);
+    const bool log_w = (prm.model & PK_MODEL_LOG_WEIGHTS) != 0;
+    double factor = log_w ? -0.5 * (log(2.0 * 3.141592653589793 * fro) + maha)
+                          : (1.0 / sqrt(2.0 * 3.141592653589793 * fro)) * pk_exp(-0.5 * maha);
 
     bool changed = false;
     if (!(L.meta & PK_META_IMMUTABLE)) {
@@ -281,7 +302,7 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     }
     if (id_out < 0) {
         // potential feature :109-118: weight as if unseen; promote when update_count > 5
-        factor = prm.no_match_weight;
+        factor = log_w ? log(prm.no_match_weight) : prm.no_match_weight;
         if (L.meta & PK_META_POTENTIAL) {
             if ((L.meta & PK_META_COUNT_MASK) > prm.promote_count) {
                 L.meta &= ~PK_META_POTENTIAL;
@@ -399,16 +420,21 @@ __device__ __forceinline__ float match_likelihood(const LandmarkF& L, double px,
 
 __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double py, float beta, float orr, float og, float ob,
                                                 const pk_params& prm, int& id_out, unsigned& flags, int& promoted,
-                                                bool& changed_out, bool have_zb = false, float zb_in = 0.0f) {
+                                                bool& changed_out, bool have_zb = false, float zb_in = 0.0f, double pth = 0.0) {
     id_out = L.id;
     const float qt = (float)prm.qt_diag;
     const float dx = (float)((double)L.x - px), dy = (float)((double)L.y - py);
     const float q = dx * dx + dy * dy;                                                   // :785
     const float inv_q = __fdividef(1.0f, q);
-    const float hx = (q == 0.0f) ? 0.0f : dy * inv_q;                                    // :788-797 (as written, F4b)
+    float hx = (q == 0.0f) ? 0.0f : dy * inv_q;                                          // :788-797 (as written, F4b)
     const float hy = (q == 0.0f) ? 0.0f : dx * inv_q;
     float zb = zb_in;                                                                    // :871 (world frame, F4a)
     if (!have_zb) zb = pk_atan2f(dy, dx);
+    const bool textbook = (prm.model & PK_MODEL_TEXTBOOK) != 0;
+    if (textbook) {
+        hx = -hx;
+        zb = zb - (float)pth;
+    }
     const float a = L.sp[0], b = L.sp[1], d = L.sp[2];                                   // S00, S10 (= S01), S11
     const float t0 = hx * a + hy * b, t1 = hx * b + hy * d;
     const float s = t0 * hx + t1 * hy + qt;                                              // :817-819
@@ -421,14 +447,18 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
     const float idet = __fdividef(1.0f, detS);
     const float I00 = C00 * idet, I10 = C01 * idet, I20 = C02 * idet;
     const float I11 = (S00 * S22 - S20 * S20) * idet, I21 = (S20 * S10 - S00 * S21) * idet, I22 = (S00 * S11 - S10 * S10) * idet;
-    const float d0 = beta - zb, d1 = orr - L.r, d2 = og - L.g, d3 = ob - L.b;          // :911 / :846, no wrapping (F4e)
+    float d0 = beta - zb;                                                                // :911 / :846, no wrapping (F4e)
+    if (textbook) d0 = pk_wrap_pi(d0);
+    const float d1 = orr - L.r, d2 = og - L.g, d3 = ob - L.b;
     const float fro = sqrtf(s * s + S00 * S00 + S11 * S11 + S22 * S22 + 2.0f * (S10 * S10 + S20 * S20 + S21 * S21));
     const float y1 = d1 * I00 + d2 * I10 + d3 * I20;
     const float y2 = d1 * I10 + d2 * I11 + d3 * I21;
     const float y3 = d1 * I20 + d2 * I21 + d3 * I22;
     const float maha = d0 * inv_s * d0 + y1 * d1 + y2 * d2 + y3 * d3;
     // importance_factor :844-849: the exp and the product that follows stay fp64 (weights span hundreds of decades)
-    double factor = (double)rsqrtf(2.0f * 3.14159265358979f * fro) * pk_exp_f2d(-0.5f * maha);
+    const bool log_w = (prm.model & PK_MODEL_LOG_WEIGHTS) != 0;
+    double factor = log_w ? (double)(-0.5f * (__logf(2.0f * 3.14159265358979f * fro) + maha))
+                          : (double)rsqrtf(2.0f * 3.14159265358979f * fro) * pk_exp_f2d(-0.5f * maha);
 
     bool changed = false;
     if (!(L.meta & PK_META_IMMUTABLE)) {
@@ -464,7 +494,7 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
         changed = true;
     }
     if (id_out < 0) {
-        factor = prm.no_match_weight;
+        factor = log_w ? log(prm.no_match_weight) : prm.no_match_weight;
         if (L.meta & PK_META_POTENTIAL) {
             if ((L.meta & PK_META_COUNT_MASK) > prm.promote_count) {
                 L.meta &= ~PK_META_POTENTIAL;
@@ -481,11 +511,11 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
 template <typename T>
 __device__ __forceinline__ double ekf_update(unsigned char* block, int capacity, int j, double px, double py,
                                              double beta, double orr, double og, double ob, const pk_params& prm,
-                                             int& id_out, unsigned& flags, int& promoted) {
+                                             int& id_out, unsigned& flags, int& promoted, double pth = 0.0) {
     Landmark L;
     load_landmark<T>(block, capacity, j, L);
     bool changed = false;
-    const double factor = ekf_update_lm(L, px, py, beta, orr, og, ob, prm, id_out, flags, promoted, changed);
+    const double factor = ekf_update_lm(L, px, py, beta, orr, og, ob, prm, id_out, flags, promoted, changed, false, 0.0, pth);
     if (changed) store_landmark<T>(block, capacity, j, L);
     return factor;
 }

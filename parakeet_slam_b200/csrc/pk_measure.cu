@@ -149,6 +149,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     // two blobs of this frame may hit the same landmark only if their colours are close (ObsTable::twins); when no
     // pair is, the same-landmark ordering of the update phase (finding F2) is skipped altogether
     const bool twins = OT->twins != 0u;
+    // PK_MODEL_LOG_WEIGHTS: importance factors and particle weights are carried as logarithms
+    const bool log_w = (A.prm.model & PK_MODEL_LOG_WEIGHTS) != 0;
+    const double log_no_match = log(A.prm.no_match_weight);
     // this lane's items: item w = r * 32 + lane -> (particle pl, blob k) within a group
     int it_pl[R], it_k[R];
     unsigned it_key[R];
@@ -516,7 +519,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const bool act = w < nitems;
             const int pl = act ? it_pl[r] : 0;
             unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
-            const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1];
+            const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
             const bool matched = act && bestj[r] >= 0;
             // items on the same landmark of the same particle go one after the other (finding F2); that can
             // only happen when two blobs of the frame have close colours
@@ -527,7 +530,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 rank = __popc(peers & lt);
                 maxrank = __reduce_max_sync(kFull, matched ? rank : 0);
             }
-            double factor = A.prm.no_match_weight;  // :95 / :851-857
+            double factor = log_w ? log_no_match : A.prm.no_match_weight;  // :95 / :851-857
             int id_out = 0;
             int promoted = 0;
             for (int q = 0;; ++q) {
@@ -544,7 +547,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     // the bearing computed during association is that of the PRE-update landmark: it is re-used
                     // unless an earlier blob of this frame has moved the landmark since
                     factor = ekf_update_lm(L, px, py, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], A.prm, id_out, st_flags,
-                                           promoted, changed, !stale, best_pse[r]);
+                                           promoted, changed, !stale, best_pse[r], pth);
                     if (changed) store_landmark<T>(block, cap, bestj[r], L, key_before);
                 }
                 if (q >= maxrank) break;
@@ -568,8 +571,10 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 // particle folds its K factors left to right
                 if (act && it_k[0] == 0) {
                     const int base = pl * K;
-                    double wgt = 1.0;
-                    if (K == 8) {  // the usual scan size: four 16-byte loads, eight multiplications
+                    double wgt = log_w ? 0.0 : 1.0;
+                    if (log_w) {  // PK_MODEL_LOG_WEIGHTS: the factors are logarithms, the weight is their sum
+                        for (int k2 = 0; k2 < K; ++k2) wgt += S.factor[base + k2];
+                    } else if (K == 8) {  // the usual scan size: four 16-byte loads, eight multiplications
                         const double2* f2 = reinterpret_cast<const double2*>(&S.factor[base]);
 #pragma unroll
                         for (int k2 = 0; k2 < 4; ++k2) {
@@ -580,7 +585,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     } else {
                         for (int k2 = 0; k2 < K; ++k2) wgt *= S.factor[base + k2];
                     }
-                    if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
+                    if (log_w ? (wgt != wgt || wgt == INFINITY) : !isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
                     A.pose4[4 * (size_t)(p0 + pl) + 3] = wgt;
                     const int orphans = __popc((unseen >> base) & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)));
                     if (orphans) A.aux2[2 * (size_t)(p0 + pl) + 1] += orphans;
@@ -594,9 +599,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         if (R > 1) {
             __syncwarp();
             if (lane == 0 && gpn > 0) {
-                double wgt = 1.0;
-                for (int k = 0; k < K; ++k) wgt *= S.factor[k];
-                if (!isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
+                double wgt = log_w ? 0.0 : 1.0;
+                for (int k = 0; k < K; ++k) wgt = log_w ? wgt + S.factor[k] : wgt * S.factor[k];
+                if (log_w ? (wgt != wgt || wgt == INFINITY) : !isfinite(wgt)) st_flags |= PK_FLAG_NONFINITE_WEIGHT;
                 A.pose4[4 * (size_t)p0 + 3] = wgt;
                 const int orphans = S.unseen_acc;
                 if (orphans) A.aux2[2 * (size_t)p0 + 1] += orphans;
@@ -637,9 +642,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     }
 }
 
-__global__ void reset_weight_kernel(double* __restrict__ pose4, long long M) {
+__global__ void reset_weight_kernel(double* __restrict__ pose4, long long M, double value) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) pose4[4 * i + 3] = 1.0;  // cam_cb :73 with an empty scan
+    if (i < M) pose4[4 * i + 3] = value;  // cam_cb :73 with an empty scan (log mode: log 1)
 }
 
 template <typename T, int R, typename LM>
@@ -722,7 +727,8 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     if (M == 0) return PK_OK;
     if (K == 0) {
         const int threads = 256;
-        reset_weight_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(pose4, M);
+        reset_weight_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
+            pose4, M, (params->model & PK_MODEL_LOG_WEIGHTS) ? 0.0 : 1.0);
         PK_LAUNCH_CHECK("reset_weight_kernel");
         return PK_OK;
     }

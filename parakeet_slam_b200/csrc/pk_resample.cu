@@ -19,6 +19,7 @@
 //        particle that died (an exclusive scan of the dead flags pairs them up), moved by TMA
 //        bulk copies global -> shared -> global.  This is the deepcopy of :243.
 #include "pk_common.cuh"
+#include "pk_filter_math.cuh"
 
 namespace pk {
 
@@ -831,6 +832,78 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// Log-domain weight normaliser (PK_MODEL_LOG_WEIGHTS): max, then exp(lw - max) with sum and sum of squares.
+// Warp-shuffle reductions inside a CTA, one partial per CTA, a fixed-order second pass: deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+logw_max_partial_kernel(const double* __restrict__ pose4, long long M, double* __restrict__ ws) {
+    __shared__ double sh[8];
+    double m = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        const double v = pose4[4 * i + 3];
+        m = (v > m) ? v : m;   // NaN never wins
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v = __shfl_xor_sync(kFullMask, m, o);
+        m = (v > m) ? v : m;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = (sh[w] > m) ? sh[w] : m;
+        ws[blockIdx.x] = m;
+    }
+}
+
+__global__ void logw_max_final_kernel(const double* __restrict__ ws, int nblocks, double* __restrict__ max_out) {
+    double m = -INFINITY;
+    for (int b = threadIdx.x; b < nblocks; b += 32) m = (ws[b] > m) ? ws[b] : m;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v = __shfl_xor_sync(kFullMask, m, o);
+        m = (v > m) ? v : m;
+    }
+    if (threadIdx.x == 0) max_out[0] = m;
+}
+
+__global__ void __launch_bounds__(256)
+logw_normalise_kernel(double* __restrict__ pose4, long long M, const double* __restrict__ max_in, double* __restrict__ ws) {
+    __shared__ double sh[2][8];
+    const double mx = max_in[0];
+    double s = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        // all weights -inf (every factor was zero): keep them equal, as a uniform resample
+        const double w = (mx == -INFINITY) ? 1.0 : pk_exp(pose4[4 * i + 3] - mx);
+        pose4[4 * i + 3] = w;
+        s += w;
+        s2 += w * w;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(kFullMask, s, o);
+        s2 += __shfl_xor_sync(kFullMask, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = s;
+        sh[1][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double a = 0.0;
+        for (int w = 0; w < 8; ++w) a += sh[threadIdx.x][w];
+        ws[threadIdx.x * 1024 + blockIdx.x] = a;
+    }
+}
+
+__global__ void logw_sums_final_kernel(const double* __restrict__ ws, int nblocks, const double* __restrict__ max_in,
+                                       double* __restrict__ out3) {
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;  // two warps: sum, sum of squares
+    double a = 0.0;
+    for (int b = lane; b < nblocks; b += 32) a += ws[q * 1024 + b];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
+    if (lane == 0) out3[q] = a;
+    if (threadIdx.x == 0) out3[2] = max_in[0];
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6 summary / best particle
 // ---------------------------------------------------------------------------------------------
 constexpr int kRedBlocks = 1024;
@@ -1215,6 +1288,33 @@ int pk_copy_blocks(const void* pool_src, void* pool_dst, int capacity, int dtype
     if (n_max == 0) return PK_OK;
     return copy_blocks_launch(pool_src, pool_dst, capacity, dtype, src_slot, dst_slot, n_live, n_max, n_dev,
                               (cudaStream_t)stream);
+}
+
+int pk_log_weights_max(const double* pose4, long long M, double* max_out, double* workspace, void* stream) {
+    PK_CHECK_ARG(pose4 && max_out && workspace, "null pointer");
+    PK_CHECK_ARG(M > 0, "M <= 0");
+    long long blocks = (M + 255) / 256;
+    if (blocks > kRedBlocks) blocks = kRedBlocks;
+    cudaStream_t st = (cudaStream_t)stream;
+    logw_max_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(pose4, M, workspace);
+    PK_LAUNCH_CHECK("logw_max_partial_kernel");
+    logw_max_final_kernel<<<1, 32, 0, st>>>(workspace, (int)blocks, max_out);
+    PK_LAUNCH_CHECK("logw_max_final_kernel");
+    return PK_OK;
+}
+
+int pk_log_weights_normalise(double* pose4, long long M, const double* max_in, double* out3, double* workspace,
+                             void* stream) {
+    PK_CHECK_ARG(pose4 && max_in && out3 && workspace, "null pointer");
+    PK_CHECK_ARG(M > 0, "M <= 0");
+    long long blocks = (M + 255) / 256;
+    if (blocks > kRedBlocks) blocks = kRedBlocks;
+    cudaStream_t st = (cudaStream_t)stream;
+    logw_normalise_kernel<<<(unsigned)blocks, 256, 0, st>>>(pose4, M, max_in, workspace);
+    PK_LAUNCH_CHECK("logw_normalise_kernel");
+    logw_sums_final_kernel<<<1, 64, 0, st>>>(workspace, (int)blocks, max_in, out3);
+    PK_LAUNCH_CHECK("logw_sums_final_kernel");
+    return PK_OK;
 }
 
 int pk_summary_partial(const double* pose4, long long M, double* out5, double* workspace, void* stream) {

@@ -227,6 +227,11 @@ class ShardedFastSLAM(FastSLAM):
                     rank_n_lo=[int(v) for v in x[_lib.PK_XP_RANK_LO:_lib.PK_XP_RANK_LO + G]],
                     rank_n_loc=[int(v) for v in x[_lib.PK_XP_RANK_LOC:_lib.PK_XP_RANK_LOC + G]])
 
+    def _all_reduce_weight_stat(self, tensor, op):
+        """The weight normaliser across shards: NCCL all-reduce of the maximum log weight / of sum w and sum w^2."""
+        dist = self._dist
+        dist.all_reduce(tensor, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self._group)
+
     def _resample_peer(self):
         """low_variance_resample with every count on the device and both exchanges over peer memory."""
         torch, lib, dist = self._torch, self._lib, self._dist
@@ -236,6 +241,8 @@ class ShardedFastSLAM(FastSLAM):
             u01 = float(self._uniform())  # every rank must draw the same value (same seed / same source)
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
+            if self.weights == "log":
+                self._normalise_log_weights()
             pose_in, aux_in, slot_in = self._pose[cur], self._aux[cur], self._slot[cur]
             status = _lib.ptr(self._peer_status)
             # K3a + all-gather of the block totals in one kernel (stores into every rank's copy)
@@ -305,6 +312,8 @@ class ShardedFastSLAM(FastSLAM):
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
             pose_in, aux_in, slot_in = self._pose[cur], self._aux[cur], self._slot[cur]
+            if self.weights == "log":
+                self._normalise_log_weights()
             _lib.check(lib.pk_weight_scan(_lib.ptr(pose_in), Ml, _lib.ptr(self._cumsum), _lib.ptr(self._block_sums), st),
                        "pk_weight_scan")
             # weight normaliser: all ranks obtain all block totals, then fold them identically

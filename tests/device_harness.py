@@ -23,14 +23,16 @@ def make_features(scn):
 
 
 def run_device(scn, dtype="f64", frames=None, num_particles=None, checkpoints=(), noise="numpy", potential_slots=(),
-               spawn=False, known_map=True, capacity=None, orphan_capacity=32, arithmetic="f64"):
+               spawn=False, known_map=True, capacity=None, orphan_capacity=32, arithmetic="f64",
+               measurement_model="reference", weights="linear"):
     from parakeet_slam_b200.core import FastSLAM
     T = scn.frames if frames is None else frames
     M = scn.num_particles if num_particles is None else num_particles
     K = scn.obs_per_frame
     clock.set(0.0)
     fs = FastSLAM(make_features(scn) if known_map else [], num_particles=M, dtype=dtype, noise=noise, spawn=spawn,
-                  capacity=capacity, orphan_capacity=orphan_capacity, arithmetic=arithmetic)
+                  capacity=capacity, orphan_capacity=orphan_capacity, arithmetic=arithmetic,
+                  measurement_model=measurement_model, weights=weights)
     fs.keep_trace = True
     if len(potential_slots):
         # turn some preset landmarks into POTENTIAL features (id < 0), as potential_features[-id] of the reference

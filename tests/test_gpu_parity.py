@@ -352,3 +352,83 @@ def test_f32_arithmetic_state_against_oracle(lib):
     est, ref = np.array(fs.summary()), np.array(onp.summary(st.pose))
     assert np.max(np.abs(est - ref)) < 1e-3
     assert fs.stats()["flags"] == 0
+
+
+# ---- PK_MODEL_TEXTBOOK: the textbook bearing model as an option -------------------------
+@pytest.mark.parametrize("dtype,arith", [("f64", "f64"), ("f32", "f32")])
+def test_textbook_measurement_model_against_oracle(lib, dtype, arith):
+    """Robot-frame predicted bearing, Jacobian row [-dy/q, +dx/q], wrapped innovation (the reference's quirks F4 a/b/e
+    switched off) on the circle trajectory, where the heading is not ~0 and the models really differ: the device
+    against the NumPy restatement run with the same switch (no reference fixture can exist for a deviation).
+    f64: every index exact, state to 1e-9; fp32 algebra: frame 0 exact, >= 90 % of all indices."""
+    from device_harness import run_device
+    from oracle import fastslam_np as onp
+    from parakeet_slam_b200.scenario import make_scenario
+    scn = make_scenario("c1", num_particles=64, num_landmarks=20, frames=40, trajectory="circle")
+    to = onp.run_scenario(scn, record_landmarks_at=(39,), model="textbook")
+    tr = run_device(scn, dtype, checkpoints=(39,), arithmetic=arith, measurement_model="textbook")
+    ref_mode = onp.run_scenario(scn, model="reference")
+    assert not np.array_equal(to["weight"], ref_mode["weight"])          # the switch changes the filter
+    if dtype == "f64":
+        assert np.array_equal(tr["assoc"], to["assoc"]) and np.array_equal(tr["ancestors"], to["ancestors"])
+        assert np.max(np.abs(tr["pose_post"] - to["pose_post"])) < 1e-9
+        big = to["weight"] > 1e-300
+        assert _rel(tr["weight"][big], to["weight"][big]) < 1e-7
+        assert np.max(np.abs(tr["lm_mean"][39] - to["lm_mean"][39])) < 1e-8
+    else:
+        assert np.array_equal(tr["assoc"][0], to["assoc"][0]) and np.array_equal(tr["ancestors"][0], to["ancestors"][0])
+        assert float((tr["assoc"] == to["assoc"]).mean()) >= 0.90
+        assert float((tr["ancestors"] == to["ancestors"]).mean()) >= 0.90
+
+
+# ---- PK_MODEL_LOG_WEIGHTS: log-domain importance weights + log-sum-exp normaliser (north_star (3)) ---------------
+def test_log_weight_normaliser_kernels(lib):
+    """pk_log_weights_max / pk_log_weights_normalise against NumPy on log weights around -2000 (their linear forms
+    are exactly 0.0 in fp64), with -inf entries (a zero factor), and on the all -inf case."""
+    import ctypes
+    import torch
+    from parakeet_slam_b200 import _lib
+    L = _lib.load()
+    rs = np.random.RandomState(3)
+    for M, all_inf in ((100003, False), (257, True)):
+        lw = -2000.0 + 40.0 * rs.standard_normal(M)
+        lw[::17] = -np.inf
+        if all_inf:
+            lw[:] = -np.inf
+        pose = torch.zeros((M, 4), dtype=torch.float64, device="cuda")
+        pose[:, 3] = torch.from_numpy(lw).cuda()
+        mx = torch.zeros(1, dtype=torch.float64, device="cuda")
+        out3 = torch.zeros(3, dtype=torch.float64, device="cuda")
+        ws = torch.zeros(2 * 1024, dtype=torch.float64, device="cuda")
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(L.pk_log_weights_max(_lib.ptr(pose), M, _lib.ptr(mx), _lib.ptr(ws), st), "max")
+        _lib.check(L.pk_log_weights_normalise(_lib.ptr(pose), M, _lib.ptr(mx), _lib.ptr(out3), _lib.ptr(ws), st), "norm")
+        w = pose[:, 3].cpu().numpy()
+        o = out3.cpu().numpy()
+        if all_inf:
+            assert np.all(w == 1.0) and o[0] == M            # nothing to prefer: uniform
+            continue
+        assert float(mx.item()) == lw.max()
+        want = np.exp(lw - lw.max())
+        assert w.max() == 1.0 and np.all(w[::17] == 0.0)
+        assert np.max(np.abs(w - want)) < 1e-14
+        assert abs(o[0] - want.sum()) < 1e-9 * want.sum() and abs(o[1] - (want ** 2).sum()) < 1e-9 * (want ** 2).sum()
+
+
+@pytest.mark.parametrize("dtype,arith", [("f64", "f64"), ("f32", "f32")])
+def test_log_weights_filter_matches_linear_weights(lib, dtype, arith):
+    """FastSLAM(weights="log") against the same filter with the reference's linear weights on a reference fixture's
+    scenario: identical associations, log weight == log(linear weight), and the same ancestors (the normalised
+    weights are the linear ones divided by their maximum: only exact near-ties of a threshold may differ)."""
+    from device_harness import run_device
+    g = load_trace("trace_corridor_noisy_m48_t40")
+    scn = scenario_from_trace(g)
+    lin = run_device(scn, dtype, arithmetic=arith)
+    log = run_device(scn, dtype, arithmetic=arith, weights="log")
+    assert np.array_equal(lin["assoc"], log["assoc"])
+    w = lin["weight"][0]
+    big = w > 1e-300
+    assert np.max(np.abs(log["weight"][0][big] - np.log(w[big]))) < (1e-9 if arith == "f64" else 1e-4)
+    assert float((lin["ancestors"] == log["ancestors"]).mean()) >= 0.999
+    n_eff, lse = log["filter"].effective_sample_size()
+    assert 1.0 <= n_eff <= scn.num_particles and np.isfinite(lse)

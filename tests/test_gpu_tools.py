@@ -154,3 +154,60 @@ def test_calc_errors_matches_reference_helpers():
     along, off, head = SlamAnalyzer.calc_errors((0.0, -2.0, 0.0), (0.0, 0.0, math.pi / 2))
     assert along == pytest.approx(-2.0) and abs(off) < 1e-12
     assert SlamAnalyzer.calc_errors((0.0, 0.0, 1.0), (0.0, 0.0, 0.25)) == (0.0, 0.0, 0.75)
+
+
+def test_checkpoint_round_trip_and_layout_checks():
+    """state_dict / load_state_dict: a restored filter continues bit-identically (device state, Philox frame counter,
+    last control and time), and a checkpoint of another layout is refused."""
+    import random
+    import torch
+    from device_harness import make_features
+    from parakeet_slam_b200.core import FastSLAM
+    from parakeet_slam_b200.rosless import Time, messages
+    from parakeet_slam_b200.scenario import DT_NSEC, make_scenario
+    scn = make_scenario("c2", num_particles=2048, num_landmarks=16, frames=9)
+
+    class Clk(object):
+        ns = 0
+
+        def __call__(self):
+            return Time(0, self.ns)
+
+    def build(urng, clk, **kw):
+        fs = FastSLAM(make_features(scn), num_particles=2048, dtype="f32", arithmetic="f32", noise="philox", seed=3,
+                      uniform=urng.random, clock=clk, **kw)
+        tw = messages.Twist()
+        tw.linear.x, tw.angular.z = scn.v, 0.05
+        fs.last_control = tw
+        return fs, tw
+
+    def advance(fs, tw, clk, frames):
+        for t in frames:
+            clk.ns += DT_NSEC
+            fs.motion_update(tw)
+            fs.measurement_update(scn.observations[t])
+            fs.low_variance_resample()
+
+    clk_a, rng_a = Clk(), random.Random(1)
+    a, tw = build(rng_a, clk_a)
+    advance(a, tw, clk_a, range(0, 4))
+    sd = a.state_dict()
+    rng_state, ns = rng_a.getstate(), clk_a.ns
+    advance(a, tw, clk_a, range(4, 9))
+
+    clk_b, rng_b = Clk(), random.Random(7)
+    b, _ = build(rng_b, clk_b)
+    b.last_control = messages.Twist()                       # the checkpoint brings control and time back
+    b.load_state_dict(sd)
+    rng_b.setstate(rng_state)
+    clk_b.ns = ns
+    assert b.last_control.angular.z == 0.05 and b.last_update.to_nsec() == a.last_update.to_nsec() - 5 * DT_NSEC
+    advance(b, b.last_control, clk_b, range(4, 9))
+    assert torch.equal(a.pose, b.pose) and torch.equal(a.aux, b.aux)
+    ma, mb = a.export_maps(), b.export_maps()
+    assert all(np.array_equal(x, y) for x, y in zip(ma, mb))
+    c, _ = build(random.Random(1), Clk(), capacity=32)      # another capacity: another block layout
+    with pytest.raises(ValueError):
+        c.load_state_dict(sd)
+    with pytest.raises(ValueError):
+        a.import_maps(2040, *[x[:16] for x in ma[:5]])      # 16 particles from 2040: past the end
