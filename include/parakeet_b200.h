@@ -346,12 +346,25 @@ int pk_push_particles(const long long* xplan, const long long* out_lo, long long
                       long long send_capacity, int* workspace, void* stream);
 /* pk_resample_gather_sharded with the window split read from xplan; anc_window[Ml] = global ancestor
  * of each local output slot and `workspace` as left by pk_resample_plan with out_offset = rank * Ml, n_out = Ml. */
+/* peer_flags_tab != NULL: the flag barrier that makes the other ranks' pushes visible (pk_peer_barrier's) runs inside
+ * the first kernel of this call instead of in a launch of its own. */
 int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const long long* out_lo, const int* offspring, long long Ml,
                             long long particle_offset, const double* pose4_in, double* pose4_out,
                             const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
                             const void* recv, long long recv_capacity, void* pool, int capacity,
-                            int dtype, void* workspace, long long* total_dead_out, void* stream);
+                            int dtype, void* workspace, long long* total_dead_out,
+                            const unsigned long long* peer_flags_tab, int rank, int n_ranks,
+                            unsigned long long epoch, double timeout_s, unsigned long long* status,
+                            void* stream);
+/* K3b of the peer path in ONE single-CTA kernel: the flag barrier after the fused all-gather of the block totals,
+ * pk_resample_thresholds over all ranks' totals, and pk_exchange_plan (xplan, PK_PEER_OVERFLOW into status). */
+int pk_resample_thresholds_peer(const double* all_block_sums, long long nb_total, long long M_total,
+                                double u01, double* plan, double* block_prefix, long long* block_count,
+                                const unsigned long long* peer_flags_tab, int rank, int n_ranks,
+                                unsigned long long epoch, double timeout_s, long long Ml,
+                                long long capacity, long long* xplan, unsigned long long* status,
+                                void* stream);
 
 /* ---- log-domain weight normaliser (PK_MODEL_LOG_WEIGHTS; north_star "log-sum-exp normalisation") ----------------
  * pk_log_weights_max: max_out[0] = max_i pose4[i][3] (warp-shuffle + block reduction, fixed order).

@@ -100,16 +100,133 @@ __device__ __forceinline__ long long count_le(dd P, double c, double u0, double 
     return k + 1;
 }
 
+// ---- sharded path -------------------------------------------------------------------------------
+// A migrating particle travels as one RECORD: a 64-byte header (pose4: 32 B, aux2: 8 B, padding) followed
+// by its landmark block.  kHeaderBytes keeps the block 64-byte aligned inside the exchange buffer.
+constexpr int kHeaderBytes = 64;
+
+// ---- device-resident exchange plan (peer path) ------------------------------------------------------
+// Everything the exchange needs follows from E[g] = number of output slots whose ancestor lives on a
+// rank < g (E[g] = block_count[g * nb], which every rank computes identically in K3b): rank g's
+// offspring occupy the global output slots [E[g], E[g+1]) and output slot k belongs to rank k / Ml.
+// The same function runs on the host (pk_exchange_plan_host; CPU tests compare it with the Python
+// plan_exchange) and in a one-thread kernel, so no count ever crosses PCIe.
+enum {
+    XP_EMIT_LO = 0,    // E[me]
+    XP_EMIT_N = 1,     // E[me+1] - E[me]: outputs descending from my particles
+    XP_N_LO = 2,       // my output slots filled from lower ranks
+    XP_N_LOC = 3,      // ... from my own particles
+    XP_N_HI = 4,       // ... from higher ranks
+    XP_N_BELOW = 5,    // my offspring that live on lower ranks
+    XP_N_ABOVE = 6,    // ... on higher ranks
+    XP_ABOVE_START = 7,  // first global output slot of the N_ABOVE run
+    XP_N_SEND = 8,     // N_BELOW + N_ABOVE (0 when XP_OVERFLOW)
+    XP_N_IN = 9,       // N_LO + N_HI        (0 when XP_OVERFLOW)
+    XP_OVERFLOW = 10,  // some rank would receive more than the exchange capacity
+    XP_N_RANKS = 11,
+    XP_ML = 12,
+    XP_RANK_LO = 16,   // [PK_MAX_RANKS] n_lo of every rank
+    XP_RANK_LOC = 16 + PK_MAX_RANKS,  // [PK_MAX_RANKS] n_loc of every rank
+};
+static_assert(PK_XPLAN_LONGS >= 16 + 2 * PK_MAX_RANKS, "exchange plan size");
+
+__host__ __device__ inline long long xp_clamp(long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__host__ __device__ inline void make_exchange_plan(const long long* E, int G, long long Ml, int me, long long cap,
+                                                   long long* xp) {
+    for (int i = 0; i < PK_XPLAN_LONGS; ++i) xp[i] = 0;
+    bool overflow = false;
+    for (int g = 0; g < G; ++g) {
+        const long long w0 = (long long)g * Ml, w1 = w0 + Ml;
+        const long long n_lo = xp_clamp(E[g] - w0, 0, Ml);             // window slots below E[g]
+        const long long loc_hi = xp_clamp(E[g + 1], w0, w1), loc_lo = xp_clamp(E[g], w0, w1);
+        const long long n_loc = loc_hi - loc_lo;
+        xp[XP_RANK_LO + g] = n_lo;
+        xp[XP_RANK_LOC + g] = n_loc;
+        // capacity bounds what a rank RECEIVES; what it sends is then at most (G-1) * cap (the send
+        // lists are sized for that: one particle may own every output slot of the filter)
+        if (Ml - n_loc > cap) overflow = true;
+        if (g == me) {
+            xp[XP_EMIT_LO] = E[g];
+            xp[XP_EMIT_N] = E[g + 1] - E[g];
+            xp[XP_N_LO] = n_lo;
+            xp[XP_N_LOC] = n_loc;
+            xp[XP_N_HI] = Ml - n_lo - n_loc;
+            const long long below_end = xp_clamp(w0, E[g], E[g + 1]);    // offspring slots < my window
+            const long long above_start = xp_clamp(w1, E[g], E[g + 1]);  // offspring slots >= window end
+            xp[XP_N_BELOW] = below_end - E[g];
+            xp[XP_N_ABOVE] = E[g + 1] - above_start;
+            xp[XP_ABOVE_START] = above_start;
+        }
+    }
+    xp[XP_OVERFLOW] = overflow ? 1 : 0;
+    xp[XP_N_SEND] = overflow ? 0 : xp[XP_N_BELOW] + xp[XP_N_ABOVE];
+    xp[XP_N_IN] = overflow ? 0 : xp[XP_N_LO] + xp[XP_N_HI];
+    xp[XP_N_RANKS] = G;
+    xp[XP_ML] = Ml;
+}
+
+// Cross-rank barrier on flags in peer memory: thread g tells rank g "I am at `epoch`" and waits until
+// rank g said the same.  Everything this rank wrote to peer memory earlier on the stream is ordered
+// before the flag (fence + release); everything the peers wrote before their flag is visible after
+// the acquire.  A rank that never shows up trips the time-out instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Body of the cross-rank flag barrier for threads g < G of ONE CTA (callers follow it with __syncthreads()):
+// thread g tells rank g "I am at `epoch`" and waits until rank g said the same.
+struct PeerSync {
+    unsigned long long* const* flags;   // device table: flags base of every rank (NULL: no barrier)
+    int me, G;
+    unsigned long long epoch, timeout_ns;
+    unsigned long long* status;
+};
+__device__ __forceinline__ void peer_sync_thread(const PeerSync& ps, int g, bool post) {
+    if (g >= ps.G) return;
+    if (post) {
+        __threadfence_system();
+        st_release_sys(ps.flags[g] + ps.me, ps.epoch);
+    }
+    const unsigned long long* mine = ps.flags[ps.me] + g;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(mine) < ps.epoch) {
+        if (global_timer_ns() - t0 > ps.timeout_ns) {
+            atomicOr(ps.status, (unsigned long long)PK_PEER_TIMEOUT);
+            break;
+        }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3b  (single CTA of 1024 threads)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_total, double u01,
-                  double* __restrict__ plan, double* block_prefix, long long* block_count, int kGroupBlocks) {
+                  double* __restrict__ plan, double* block_prefix, long long* block_count, int kGroupBlocks,
+                  PeerSync ps, long long Ml, long long xcap, long long* __restrict__ xplan) {
     __shared__ double g_hi[kMaxScanGroups], g_lo[kMaxScanGroups];
     __shared__ long long g_cnt[kMaxScanGroups];
     __shared__ double s_r, s_u0;
     const int t = threadIdx.x;
+    if (ps.flags != nullptr) {
+        // sharded filter, peer exchange: the block totals of all ranks were stored into `sums` by their scan kernels
+        // (fused all-gather); wait for every rank's flag before reading them
+        peer_sync_thread(ps, t, true);
+        __syncthreads();
+    }
     const long long ngroups = (nb + kGroupBlocks - 1) / kGroupBlocks;
     const long long b0 = (long long)t * kGroupBlocks;
     const long long b1 = min(nb, b0 + kGroupBlocks);
@@ -240,6 +357,19 @@ thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_tot
                     block_count[b + 1] = v;
                 }
             }
+        }
+    }
+    if (xplan != nullptr) {
+        // the exchange plan follows from the emitted-output counts at the rank boundaries (one thread)
+        __syncthreads();
+        if (t == 0) {
+            const long long nbr = nb / ps.G;
+            long long E[PK_MAX_RANKS + 1];
+            for (int g = 0; g <= ps.G; ++g) E[g] = block_count[(long long)g * nbr];
+            long long xp[PK_XPLAN_LONGS];
+            make_exchange_plan(E, ps.G, Ml, ps.me, xcap, xp);
+            for (int i = 0; i < PK_XPLAN_LONGS; ++i) xplan[i] = xp[i];
+            if (xp[XP_OVERFLOW]) atomicOr(ps.status, (unsigned long long)PK_PEER_OVERFLOW);
         }
     }
 }
@@ -437,11 +567,18 @@ resample_plan_kernel(const double* __restrict__ cumsum, long long M_local, long 
 __global__ void __launch_bounds__(PK_SCAN_BLOCK)
 free_list_fused_kernel(const int* __restrict__ offspring_window, const int* __restrict__ slot_in, long long M,
                        int* __restrict__ dead_excl, const int* __restrict__ block_dead, long long nb,
-                       int* __restrict__ free_list, long long* __restrict__ total_out) {
+                       int* __restrict__ free_list, long long* __restrict__ total_out, PeerSync ps) {
     __shared__ int s_part[32];
     __shared__ int s_off;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long blk = blockIdx.x;
+    if (ps.flags != nullptr) {
+        // sharded filter, peer exchange: the arrivals were pushed into this rank's receive buffer by the other ranks'
+        // previous kernels; CTA 0 posts this rank's flag (its own pushes are done: earlier kernels of this stream),
+        // every CTA waits for all ranks' flags before anything downstream of this kernel reads the buffer
+        peer_sync_thread(ps, t, blk == 0);
+        __syncthreads();
+    }
     int s = 0;
     for (long long b = t; b < blk; b += PK_SCAN_BLOCK) s += block_dead[b];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
@@ -494,72 +631,6 @@ assign_kernel(const long long* __restrict__ ancestors, long long M, const double
     }
 }
 
-// ---- sharded path -------------------------------------------------------------------------------
-// A migrating particle travels as one RECORD: a 64-byte header (pose4: 32 B, aux2: 8 B, padding) followed
-// by its landmark block.  kHeaderBytes keeps the block 64-byte aligned inside the exchange buffer.
-constexpr int kHeaderBytes = 64;
-
-// ---- device-resident exchange plan (peer path) ------------------------------------------------------
-// Everything the exchange needs follows from E[g] = number of output slots whose ancestor lives on a
-// rank < g (E[g] = block_count[g * nb], which every rank computes identically in K3b): rank g's
-// offspring occupy the global output slots [E[g], E[g+1]) and output slot k belongs to rank k / Ml.
-// The same function runs on the host (pk_exchange_plan_host; CPU tests compare it with the Python
-// plan_exchange) and in a one-thread kernel, so no count ever crosses PCIe.
-enum {
-    XP_EMIT_LO = 0,    // E[me]
-    XP_EMIT_N = 1,     // E[me+1] - E[me]: outputs descending from my particles
-    XP_N_LO = 2,       // my output slots filled from lower ranks
-    XP_N_LOC = 3,      // ... from my own particles
-    XP_N_HI = 4,       // ... from higher ranks
-    XP_N_BELOW = 5,    // my offspring that live on lower ranks
-    XP_N_ABOVE = 6,    // ... on higher ranks
-    XP_ABOVE_START = 7,  // first global output slot of the N_ABOVE run
-    XP_N_SEND = 8,     // N_BELOW + N_ABOVE (0 when XP_OVERFLOW)
-    XP_N_IN = 9,       // N_LO + N_HI        (0 when XP_OVERFLOW)
-    XP_OVERFLOW = 10,  // some rank would receive more than the exchange capacity
-    XP_N_RANKS = 11,
-    XP_ML = 12,
-    XP_RANK_LO = 16,   // [PK_MAX_RANKS] n_lo of every rank
-    XP_RANK_LOC = 16 + PK_MAX_RANKS,  // [PK_MAX_RANKS] n_loc of every rank
-};
-static_assert(PK_XPLAN_LONGS >= 16 + 2 * PK_MAX_RANKS, "exchange plan size");
-
-__host__ __device__ inline long long xp_clamp(long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-__host__ __device__ inline void make_exchange_plan(const long long* E, int G, long long Ml, int me, long long cap,
-                                                   long long* xp) {
-    for (int i = 0; i < PK_XPLAN_LONGS; ++i) xp[i] = 0;
-    bool overflow = false;
-    for (int g = 0; g < G; ++g) {
-        const long long w0 = (long long)g * Ml, w1 = w0 + Ml;
-        const long long n_lo = xp_clamp(E[g] - w0, 0, Ml);             // window slots below E[g]
-        const long long loc_hi = xp_clamp(E[g + 1], w0, w1), loc_lo = xp_clamp(E[g], w0, w1);
-        const long long n_loc = loc_hi - loc_lo;
-        xp[XP_RANK_LO + g] = n_lo;
-        xp[XP_RANK_LOC + g] = n_loc;
-        // capacity bounds what a rank RECEIVES; what it sends is then at most (G-1) * cap (the send
-        // lists are sized for that: one particle may own every output slot of the filter)
-        if (Ml - n_loc > cap) overflow = true;
-        if (g == me) {
-            xp[XP_EMIT_LO] = E[g];
-            xp[XP_EMIT_N] = E[g + 1] - E[g];
-            xp[XP_N_LO] = n_lo;
-            xp[XP_N_LOC] = n_loc;
-            xp[XP_N_HI] = Ml - n_lo - n_loc;
-            const long long below_end = xp_clamp(w0, E[g], E[g + 1]);    // offspring slots < my window
-            const long long above_start = xp_clamp(w1, E[g], E[g + 1]);  // offspring slots >= window end
-            xp[XP_N_BELOW] = below_end - E[g];
-            xp[XP_N_ABOVE] = E[g + 1] - above_start;
-            xp[XP_ABOVE_START] = above_start;
-        }
-    }
-    xp[XP_OVERFLOW] = overflow ? 1 : 0;
-    xp[XP_N_SEND] = overflow ? 0 : xp[XP_N_BELOW] + xp[XP_N_ABOVE];
-    xp[XP_N_IN] = overflow ? 0 : xp[XP_N_LO] + xp[XP_N_HI];
-    xp[XP_N_RANKS] = G;
-    xp[XP_ML] = Ml;
-}
-
 __global__ void exchange_plan_kernel(const long long* __restrict__ block_count, long long nb, int G, int me, long long Ml,
                                      long long cap, long long* __restrict__ xplan, unsigned long long* __restrict__ status) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -571,41 +642,10 @@ __global__ void exchange_plan_kernel(const long long* __restrict__ block_count, 
     if (xp[XP_OVERFLOW]) atomicOr(status, (unsigned long long)PK_PEER_OVERFLOW);
 }
 
-// Cross-rank barrier on flags in peer memory: thread g tells rank g "I am at `epoch`" and waits until
-// rank g said the same.  Everything this rank wrote to peer memory earlier on the stream is ordered
-// before the flag (fence + release); everything the peers wrote before their flag is visible after
-// the acquire.  A rank that never shows up trips the time-out instead of hanging the GPU.
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 __global__ void __launch_bounds__(PK_MAX_RANKS)
 peer_barrier_kernel(unsigned long long* const* __restrict__ peer_flags, int me, int G, unsigned long long epoch,
                     unsigned long long timeout_ns, unsigned long long* __restrict__ status) {
-    const int g = threadIdx.x;
-    if (g >= G) return;
-    __threadfence_system();
-    st_release_sys(peer_flags[g] + me, epoch);
-    const unsigned long long* mine = peer_flags[me] + g;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys(mine) < epoch) {
-        if (global_timer_ns() - t0 > timeout_ns) {
-            atomicOr(status, (unsigned long long)PK_PEER_TIMEOUT);
-            break;
-        }
-        __nanosleep(64);
-    }
-    __threadfence_system();
+    peer_sync_thread(PeerSync{peer_flags, me, G, epoch, timeout_ns, status}, (int)threadIdx.x, true);
 }
 
 // One thread per migrating particle.  Send item j is global output slot k (the N_BELOW run starts at
@@ -1067,7 +1107,30 @@ int pk_resample_thresholds(const double* all_block_sums, long long nb_total, lon
     int group = kMinGroupBlocks;
     while ((long long)group * kMaxScanGroups < nb_total) group *= 2;
     thresholds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(all_block_sums, nb_total, M_total, u01, plan, block_prefix,
-                                                           block_count, group);
+                                                           block_count, group, PeerSync{nullptr, 0, 1, 0, 0, nullptr}, 0, 0,
+                                                           nullptr);
+    PK_LAUNCH_CHECK("thresholds_kernel");
+    return PK_OK;
+}
+
+int pk_resample_thresholds_peer(const double* all_block_sums, long long nb_total, long long M_total, double u01,
+                                double* plan, double* block_prefix, long long* block_count,
+                                const unsigned long long* peer_flags_tab, int rank, int n_ranks, unsigned long long epoch,
+                                double timeout_s, long long Ml, long long capacity, long long* xplan,
+                                unsigned long long* status, void* stream) {
+    PK_CHECK_ARG(all_block_sums && plan && block_prefix && block_count && peer_flags_tab && xplan && status, "null pointer");
+    PK_CHECK_ARG(nb_total > 0 && M_total > 0 && Ml > 0 && capacity >= 0, "sizes");
+    PK_CHECK_ARG(nb_total <= (long long)kMaxGroupBlocks * kMaxScanGroups, "more than 2^25 particles in one filter");
+    PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks && nb_total % n_ranks == 0,
+                 "rank / n_ranks");
+    PK_CHECK_ARG(epoch > 0 && timeout_s > 0.0, "barrier arguments");
+    int group = kMinGroupBlocks;
+    while ((long long)group * kMaxScanGroups < nb_total) group *= 2;
+    thresholds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+        all_block_sums, nb_total, M_total, u01, plan, block_prefix, block_count, group,
+        PeerSync{reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
+                 (unsigned long long)(timeout_s * 1e9), status},
+        Ml, capacity, xplan);
     PK_LAUNCH_CHECK("thresholds_kernel");
     return PK_OK;
 }
@@ -1176,7 +1239,8 @@ int pk_resample_gather_planned(const long long* ancestors, long long M, const do
     GatherWs g = carve(workspace, M);
     const long long nb = num_blocks(M);
     free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, M, g.dead_excl, g.block_dead, nb,
-                                                                  g.free_list, n_copied_out);
+                                                                  g.free_list, n_copied_out,
+                                                                  PeerSync{nullptr, 0, 1, 0, 0, nullptr});
     PK_LAUNCH_CHECK("free_list_fused_kernel");
     const int threads = 256;
     assign_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
@@ -1213,7 +1277,7 @@ int pk_pack_particles(const long long* emit_run, long long n, long long particle
     return PK_OK;
 }
 
-static int gather_sharded_impl(bool planned, const long long* local_run, const long long* xplan, long long recv_capacity,
+static int gather_sharded_impl(bool planned, PeerSync sync, const long long* local_run, const long long* xplan, long long recv_capacity,
                                const long long* out_lo, const int* offspring, long long Ml, long long particle_offset,
                                long long n_lo, long long n_loc, const double* pose4_in, double* pose4_out,
                                const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out, const void* recv,
@@ -1232,7 +1296,7 @@ static int gather_sharded_impl(bool planned, const long long* local_run, const l
         PK_LAUNCH_CHECK("dead_scan_kernel");
     }
     free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, Ml, g.dead_excl, g.block_dead,
-                                                                  nb, g.free_list, total_dead_out);
+                                                                  nb, g.free_list, total_dead_out, sync);
     PK_LAUNCH_CHECK("free_list_fused_kernel");
     assign_sharded_kernel<<<grid, threads, 0, st>>>(local_run, Ml, particle_offset, n_lo, n_loc, xplan, pose4_in, pose4_out,
                                                     aux2_in, aux2_out, slot_in, slot_out, (const unsigned char*)recv, stride,
@@ -1275,7 +1339,7 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
     PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
     PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    return gather_sharded_impl(false, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
+    return gather_sharded_impl(false, PeerSync{nullptr, 0, 1, 0, 0, nullptr}, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
 }
@@ -1419,13 +1483,22 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const int* offspring, long long Ml, long long particle_offset, const double* pose4_in,
                             double* pose4_out, const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out,
                             const void* recv, long long recv_capacity, void* pool, int capacity, int dtype,
-                            void* workspace, long long* total_dead_out, void* stream) {
+                            void* workspace, long long* total_dead_out, const unsigned long long* peer_flags_tab,
+                            int rank, int n_ranks, unsigned long long epoch, double timeout_s,
+                            unsigned long long* status, void* stream) {
     PK_CHECK_ARG(xplan && anc_window && out_lo && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in &&
                      slot_out && pool && workspace && total_dead_out && recv,
                  "null pointer");
     PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31) && recv_capacity >= 0, "sizes");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    return gather_sharded_impl(true, anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
+    PeerSync sync{nullptr, 0, 1, 0, 0, nullptr};
+    if (peer_flags_tab != nullptr) {
+        PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+        PK_CHECK_ARG(epoch > 0 && timeout_s > 0.0 && status != nullptr, "barrier arguments");
+        sync = PeerSync{reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
+                        (unsigned long long)(timeout_s * 1e9), status};
+    }
+    return gather_sharded_impl(true, sync, anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
 }

@@ -127,8 +127,12 @@ class ShardedFastSLAM(FastSLAM):
         G, me, nb, Ml, dev = self.world_size, self.rank, self._nb, self.num_particles, self._device
         rec = self._record_bytes
         if exchange_capacity is None:
-            # records a rank may receive per frame: the whole shard while that costs < 8 GiB
-            exchange_capacity = min(Ml, max(4096, (8 << 30) // rec))
+            # Records a rank may receive per frame.  A receive buffer that holds the WHOLE shard can never overflow
+            # (a rank cannot receive more than its own output window), so that is the default whenever it fits into
+            # 80 % of the memory still free beside the landmark pool (config 4: 36.5 GB beside a 36.5 GB pool); only a
+            # shard too big for that gets a smaller buffer, and only then can a frame report PK_PEER_OVERFLOW.
+            free, _total = torch.cuda.mem_get_info(dev)
+            exchange_capacity = min(Ml, max(4096, int(0.8 * free) // rec))
         cap = int(min(max(int(exchange_capacity), 1), Ml))
         self.exchange_capacity = cap
         off_sums = 4096
@@ -249,12 +253,15 @@ class ShardedFastSLAM(FastSLAM):
             _lib.check(lib.pk_weight_scan_publish(_lib.ptr(pose_in), Ml, _lib.ptr(self._cumsum),
                                                   _lib.ptr(self._block_sums), _lib.ptr(pr["sums_tab"]), me, G, st),
                        "pk_weight_scan_publish")
-            self._barrier(st)
-            _lib.check(lib.pk_resample_thresholds(pr["sums_ptr"], G * nb, Mt, u01, _lib.ptr(self._plan),
-                                                  _lib.ptr(self._all_prefix), _lib.ptr(self._all_count), st),
-                       "pk_resample_thresholds")
-            _lib.check(lib.pk_exchange_plan(_lib.ptr(self._all_count), nb, G, me, Ml, self.exchange_capacity,
-                                            _lib.ptr(self._xplan), status, st), "pk_exchange_plan")
+            # one single-CTA kernel: flag barrier (all ranks' totals have arrived), K3b over all ranks' totals, and
+            # the exchange plan derived from the emitted-output counts at the rank boundaries
+            pr["epoch"] += 1
+            _lib.check(lib.pk_resample_thresholds_peer(pr["sums_ptr"], G * nb, Mt, u01, _lib.ptr(self._plan),
+                                                       _lib.ptr(self._all_prefix), _lib.ptr(self._all_count),
+                                                       _lib.ptr(pr["flags_tab"]), me, G, pr["epoch"],
+                                                       self._barrier_timeout_s, Ml, self.exchange_capacity,
+                                                       _lib.ptr(self._xplan), status, st),
+                       "pk_resample_thresholds_peer")
             # ancestors of my own output window (entries owned by other ranks' particles stay untouched), each local
             # particle's offspring inside the window and the dead-particle scan, in one kernel
             _lib.check(lib.pk_resample_plan(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
@@ -268,13 +275,15 @@ class ShardedFastSLAM(FastSLAM):
                                              _lib.ptr(aux_in), _lib.ptr(slot_in), _lib.ptr(self._pool), self.capacity,
                                              self._dt, _lib.ptr(pr["recv_tab"]), self._send_capacity,
                                              _lib.ptr(self._push_ws), st), "pk_push_particles")
-            self._barrier(st)
+            # the second flag barrier (every rank's pushes have landed) runs inside the first kernel of the gather
+            pr["epoch"] += 1
             _lib.check(lib.pk_resample_gather_peer(
                 _lib.ptr(self._xplan), _lib.ptr(self._anc_window), _lib.ptr(self._out_lo), _lib.ptr(self._offspring), Ml,
                 self.particle_offset, _lib.ptr(pose_in), _lib.ptr(self._pose[nxt]), _lib.ptr(aux_in),
                 _lib.ptr(self._aux[nxt]), _lib.ptr(slot_in), _lib.ptr(self._slot[nxt]), pr["recv_ptr"],
                 self.exchange_capacity, _lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self._gather_ws),
-                _lib.ptr(self._n_copied), st), "pk_resample_gather_peer")
+                _lib.ptr(self._n_copied), _lib.ptr(pr["flags_tab"]), me, G, pr["epoch"], self._barrier_timeout_s,
+                status, st), "pk_resample_gather_peer")
             self._cur = nxt
             if self.keep_trace:
                 # debugging / parity traces only: every rank scatters its offspring into a global list
