@@ -10,7 +10,7 @@ against golden traces produced by running the *unmodified reference sources*
 (``/root/reference/src/prkt_core_v2.py``, ``matrix.py``, ``utils.py``) through
 ``oracle/ref_shim.py`` (``oracle/make_golden.py`` is the generating script, fixtures
 under ``tests/golden/``), and, in the development container, directly against the
-live reference (``tests/test_oracle_vs_reference.py``).
+live reference (``tests/test_reference_shim.py``).
 
 Every function cites the reference lines it follows (paths relative to
 ``/root/reference/src``).  Formulas are reproduced as written, including the ones
