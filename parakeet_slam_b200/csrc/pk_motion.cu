@@ -7,6 +7,7 @@
 // round-to-nearest intrinsics (no FMA contraction) so that, with injected noise, positions
 // reproduce the reference's Python-float arithmetic operation for operation.
 #include "pk_common.cuh"
+#include "pk_filter_math.cuh"
 
 namespace pk {
 
@@ -35,28 +36,24 @@ struct Philox {
     }
 };
 
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-    // (0,1) uniform with 53 random bits, never 0 or 1
-    uint64_t m = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
-    return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+__device__ __forceinline__ double u32_open(uint32_t x) {
+    // (0,1) uniform from 32 random bits, never 0 or 1 (Box-Muller tails reach 6.7 sigma)
+    return ((double)x + 0.5) * (1.0 / 4294967296.0);
 }
 
+// three standard normals from ONE Philox4x32-10 call: its four words are the uniforms of two Box-Muller pairs
 __device__ __forceinline__ void philox_normals3(unsigned long long seed, unsigned long long frame,
                                                 unsigned long long particle, double& z0, double& z1, double& z2) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t a[4] = {(uint32_t)particle, (uint32_t)(particle >> 32), (uint32_t)frame, ((uint32_t)(frame >> 32)) << 1};
-    uint32_t b[4] = {a[0], a[1], a[2], a[3] | 1u};
+    uint32_t a[4] = {(uint32_t)particle, (uint32_t)(particle >> 32), (uint32_t)frame, (uint32_t)(frame >> 32)};
     Philox::run(a, k0, k1);
-    Philox::run(b, k0, k1);
-    double u1 = u53(a[0], a[1]), u2 = u53(a[2], a[3]);
-    double u3 = u53(b[0], b[1]), u4 = u53(b[2], b[3]);
-    double r1 = sqrt(-2.0 * log(u1));
-    double r2 = sqrt(-2.0 * log(u3));
+    const double r1 = sqrt(-2.0 * log(u32_open(a[0])));
+    const double r2 = sqrt(-2.0 * log(u32_open(a[2])));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    sincospi(2.0 * u32_open(a[1]), &s, &c);
     z0 = r1 * c;
     z1 = r1 * s;
-    sincospi(2.0 * u4, &s, &c);
+    sincospi(2.0 * u32_open(a[3]), &s, &c);
     z2 = r2 * c;
 }
 
@@ -72,7 +69,7 @@ __device__ __forceinline__ double wrap_heading(double h) {
     double zs = __dmul_rn(z, s), ws = __dmul_rn(w, s);
     double m10 = __dmul_rn(zs, ws);
     double m00 = __dsub_rn(1.0, __dmul_rn(zs, zs));
-    return atan2(m10, m00);
+    return pk_atan2(m10, m00);   // branch-free, <= 1.5 ulp (libm's atan2 costs several times more here)
 }
 
 __global__ void __launch_bounds__(256)
