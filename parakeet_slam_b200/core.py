@@ -394,6 +394,7 @@ class FastSLAM(object):
         self._best2 = torch.zeros((2,), dtype=f64, device=dev)
         self._wmax = torch.zeros((1,), dtype=f64, device=dev)     # log-weight normaliser: maximum log weight
         self._wstats = torch.zeros((3,), dtype=f64, device=dev)   # ... sum w, sum w^2, max (after normalisation)
+        self._pinned = {}
         self._assoc = None
         self._obs_table = None
         self._noise_pinned = None
@@ -442,9 +443,14 @@ class FastSLAM(object):
         with self._lock:
             if self.num_particles == 0:
                 return
-            self.motion_update(self.last_control)
+            # (the scan is unpacked first so that the motion and measurement kernels are issued back to back)
             scan = ros_view.last_sensor_reading
-            obs = self._scan_to_array(scan)
+            try:
+                obs = self._scan_to_array(scan)
+            except AttributeError:
+                self.motion_update(self.last_control)      # the reference moves the particles before it trips (:75-82)
+                raise
+            self.motion_update(self.last_control)
             self.measurement_update(obs)
             if self.particle_track_pub is not None:
                 self._publish_sample(self.particle_track_pub)          # :126-127
@@ -680,9 +686,21 @@ class FastSLAM(object):
         with self._lock, self._on_device():
             _lib.check(lib.pk_summary_partial(_lib.ptr(self.pose), M, _lib.ptr(self._out5), _lib.ptr(self._red_ws),
                                               self._stream()), "pk_summary_partial")
-            s = self._out5.cpu().numpy()
+            s = self._read_back(self._out5)
         count = float(M)
         return (float(s[0] / count), float(s[1] / count), math.atan2(float(s[2]), float(s[3])),)
+
+    def _read_back(self, dev_tensor):
+        """Small device tensor -> NumPy through a pinned staging buffer (asynchronous copy + one stream
+        synchronisation; `.cpu()` would allocate pageable memory and take the slow synchronous-copy path)."""
+        torch = self._torch
+        key = (dev_tensor.dtype, tuple(dev_tensor.shape))
+        host = self._pinned.get(key)
+        if host is None:
+            host = self._pinned[key] = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+        host.copy_(dev_tensor, non_blocking=True)
+        torch.cuda.current_stream(self._device).synchronize()
+        return host.numpy().copy()
 
     def best_particle(self):
         """Additive API: (index, weight) of the first particle with the largest weight (weights
