@@ -3,7 +3,7 @@
 The reference is interpreted Python 2 with no build system; "building" it means byte-compiling its hot-path
 modules where they lie, after the same two textual Py2->3 substitutions ``oracle/ref_shim.py`` applies when it
 executes them from source (``xrange(`` -> ``range(``, ``.iteritems()`` -> ``.items()``).  The outputs are ordinary
-``.pyc`` files (CPython bytecode, no source text) under ``oracle/_ref/``, which is git-ignored but travels with a
+CPython bytecode files (the ``.pyc`` format, no source text; named ``*.bin`` because snapshot tools skip ``*.pyc``) under ``oracle/_ref/``, which is git-ignored but travels with a
 ``gpurun`` snapshot -- the GPU box runs the same interpreter, so ``bench.py --impl reference`` and the
 ``cpu_baseline`` leg can time the UNMODIFIED reference code there, and the reference's own unit tests can be run
 against the drop-in classes.  No reference source is copied into this repository.
@@ -25,7 +25,7 @@ PY2_SUBSTITUTIONS = (("xrange(", "range("), (".iteritems()", ".items()"))
 
 
 def pyc_path(name: str) -> str:
-    return os.path.join(OUT_DIR, "%s.cpython-%d%d.pyc" % (name, sys.version_info[0], sys.version_info[1]))
+    return os.path.join(OUT_DIR, "%s.cpython-%d%d.bin" % (name, sys.version_info[0], sys.version_info[1]))
 
 
 def source_available(src_dir: str = REFERENCE_SRC) -> bool:

@@ -13,7 +13,7 @@ classes ARE the reference implementation; golden vectors under ``tests/golden``
 are produced from them by ``oracle/make_golden.py``.
 
 ``/root/reference`` exists only in the development container.  ``oracle/build_ref.py`` byte-compiles the same
-(substituted) module texts into ``oracle/_ref/*.pyc`` -- build outputs, git-ignored, shipped with a ``gpurun``
+(substituted) module texts into ``oracle/_ref/*.bin`` -- build outputs, git-ignored, shipped with a ``gpurun``
 snapshot -- and the loader falls back to those code objects when the sources are absent, so the GPU box can
 still execute the unmodified reference (``available()`` says which, ``origin()`` says from where).
 """

@@ -110,6 +110,10 @@ struct Hits {
 // ---------------------------------------------------------------------------------------------
 // LM selects the arithmetic of the landmark algebra: Landmark (fp64, every instantiation that must reproduce the
 // reference) or LandmarkF (fp32 on fp32 storage, PK_DTYPE_ARITH_F32)
+// record prefetch of an item's first hit: 1 = the warp fetches the 32-record strip together, 0 = every lane its own
+#ifndef PK_COOP_PREFETCH
+#define PK_COOP_PREFETCH 1
+#endif
 #ifndef PK_MEASURE_MINB_F32
 #define PK_MEASURE_MINB_F32 8
 #endif
@@ -344,6 +348,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const size_t rec0 = (size_t)my_slot[r] * A.block_bytes + hot;
+#if PK_COOP_PREFETCH
             {
                 const bool have = H[r].cnt > 0;
                 const unsigned off32 = have ? (unsigned)((rec0 + (size_t)H[r].c0 * kRecBytes) >> 5) : 0xffffffffu;
@@ -356,6 +361,14 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     if (so != 0xffffffffu) cp_async16_a(strip + 16u * (unsigned)chunk, A.pool + ((size_t)so << 5) + 16 * part);
                 }
             }
+#else
+            if (H[r].cnt > 0) {  // every lane fetches its own record (fewer instructions, four times the L1 wavefronts)
+                const unsigned char* src = A.pool + rec0 + (size_t)H[r].c0 * kRecBytes;
+                const uint32_t dst = s_rec + (unsigned)(r * 32 + lane) * kRecBytes;
+#pragma unroll
+                for (int i = 0; i < kChunksPerRec; ++i) cp_async16_a(dst + 16u * i, src + 16 * i);
+            }
+#endif
             // second hit (one item in ten): fetched by its own lane
             if (kStaged > 1 && H[r].cnt > 1) {
                 const unsigned char* src = A.pool + rec0 + (size_t)H[r].c1 * kRecBytes;

@@ -3,7 +3,7 @@ against the DROP-IN classes: ``prkt_core_v2`` resolves to ``parakeet_slam_b200.d
 would with ``dropin/`` ahead of the reference's ``src/`` on ``sys.path``.
 
 The reference modules come from ``/root/reference/src`` in the development container and from their byte-compiled
-form ``oracle/_ref/*.pyc`` (``oracle/build_ref.py``; build outputs that travel with a gpurun snapshot) on the GPU box.
+form ``oracle/_ref/*.bin`` (``oracle/build_ref.py``; build outputs that travel with a gpurun snapshot) on the GPU box.
 Host-side helper cases run on CPU; everything that constructs a filter or evaluates ``probability_of_match`` needs
 the device and is marked ``gpu``."""
 import unittest
