@@ -74,6 +74,11 @@ def sharded_equals_single(particles_per_rank=8192, frames=8, exchange="peer", ca
                 moved += plan["n_lo"] + plan["n_hi"]
             out.append((fs.pose[:, :3].clone(), w, fs.last_ancestors.clone()))
         maps = list(fs.export_maps())
+        # slots at or beyond n_live hold whatever the block's previous owner left there (copy-on-resample moves live
+        # landmarks only): not part of the filter state
+        dead = np.arange(maps[0].shape[1])[None, :] >= maps[5][:, None]
+        for a in maps[:5]:
+            a[dead] = 0
         if spawn:
             rows, totals = fs.export_orphans()
             maps += [totals, np.array([len(r) for r in rows])]
