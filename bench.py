@@ -600,8 +600,8 @@ def run_ours(args):
                 "reference on every fixture (FastSLAM(dtype='f64'))")
             variants["ambiguous_colours"] = variant(
                 M_local, N, args.dtype, args.arith,
-                "6 colours shared by the 64 landmarks (~11 colour-compatible landmarks per blob: every item overflows the "
-                "8-entry hit list and re-walks its keys; association decided by the position likelihood)", num_colors=6)
+                "6 colours shared by the 64 landmarks (~11 colour-compatible landmarks per blob, all evaluated exactly; the "
+                "association is decided by the position likelihood)", num_colors=6)
     if (world == 8 and not args.no_config4) or args.config4:
         c4 = {}
         c4["balanced"] = variant(

@@ -54,7 +54,10 @@ constexpr int kKeyStride = kChunk + 4;  // words; +4 keeps the particles' key ro
 constexpr int kStages = 2;           // key stages in flight per warp
 constexpr int kMaxGroup = 8;         // particles per group
 constexpr int kMaxItems = 64;        // group * K
-constexpr int kMaxHits = 8;          // hits per item kept (two in registers, the rest in shared memory)
+#ifndef PK_MAX_HITS
+#define PK_MAX_HITS 16
+#endif
+constexpr int kMaxHits = PK_MAX_HITS;  // hits per item kept (two in registers, the rest in shared memory)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct MeasureArgs {

@@ -182,13 +182,14 @@ def _export_subset(fs, sub):
     return mean5, covp, covc, meta, ids, nlive
 
 
-@pytest.mark.parametrize("n_colours", [24, 6, 3, "mixed"])
+@pytest.mark.parametrize("n_colours", [24, 6, 3, 2, "mixed"])
 def test_colour_ambiguous_maps_against_oracle(n_colours):
     """Landmarks that share colours: every blob has several colour-compatible landmarks, so the
-    bearing / position terms decide.  Exercises the 2..4-candidate path (24 colours for 48 landmarks)
-    the shared-memory hit list (6 colours, 8 landmarks each) and the key re-walk (3 colours, 16 each);
-    "mixed": ONE colour shared by 16 landmarks, the other 32 unique -- items with more than eight hits (key
-    re-walk) and items with one hit sit in the same warp, which is the case the warp collectives of the
+    bearing / position terms decide.  Exercises the two-candidate path (24 colours for 48 landmarks), the
+    shared-memory hit list (6 colours, 8 landmarks each; 3 colours, 16 each = a full list) and the key re-walk
+    (2 colours, 24 each: more hits than the 16-entry list holds);
+    "mixed": ONE colour shared by 24 landmarks, the other 24 unique -- items with more hits than the list holds
+    (key re-walk) and items with one hit sit in the same warp, which is the case the warp collectives of the
     candidate loop must survive (they are executed by every lane, outside the per-lane conditions)."""
     import torch
     from oracle import fastslam_np as onp
@@ -201,9 +202,8 @@ def test_colour_ambiguous_maps_against_oracle(n_colours):
     # recolour the world: n_colours distinct colours, jittered by < 2 units
     rs = np.random.RandomState(8)
     if n_colours == "mixed":
-        palette = rs.uniform(20, 235, (33, 3))
-        which = np.where(np.arange(N) % 3 == 0, 0, 1 + np.arange(N) - np.arange(N) // 3 - 1)   # every third landmark: colour 0
-        which = np.clip(which, 0, 32)
+        palette = rs.uniform(20, 235, (25, 3))
+        which = np.where(np.arange(N) % 2 == 0, 0, 1 + np.arange(N) // 2)   # every other landmark: colour 0
     else:
         palette = rs.uniform(20, 235, (n_colours, 3))
         which = np.arange(N) % n_colours

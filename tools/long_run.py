@@ -35,6 +35,9 @@ def main(argv=None):
     ap.add_argument("--capacity", type=int, default=None)
     ap.add_argument("--report", type=int, default=None)
     ap.add_argument("--orphans", type=int, default=32)
+    ap.add_argument("--true-landmarks", type=int, default=None,
+                    help="landmarks in the world (default: 45 %% of the capacity for c5 -- pairing rays creates about as many "
+                         "spurious potential landmarks as true ones, and a full map cannot take in what comes into view -- the capacity for c3)")
     ap.add_argument("--arith", default="f32", choices=["f32", "f64"])
     ap.add_argument("--sample-every", type=int, default=20, help="frames between kernel-time samples")
     args = ap.parse_args(argv)
@@ -55,7 +58,8 @@ def main(argv=None):
 
     torch.cuda.set_device(0)
     free, total = torch.cuda.mem_get_info()
-    world = make_world(N, "corridor", T, 0.2, 0.1, seed=2024)
+    n_true = args.true_landmarks or (int(0.45 * N) if args.config == "c5" else N)
+    world = make_world(n_true, "corridor", T, 0.2, 0.1, seed=2024)
 
     class Clk(object):
         ns = 0
@@ -75,7 +79,8 @@ def main(argv=None):
     header = dict(config=args.config, particles=M, capacity=N, blobs=K, frames=T, orphan_slots=args.orphans,
                   landmark_storage="f32", arithmetic=args.arith, block_bytes=fs.block_bytes,
                   pool_gb=M * fs.block_bytes / 1e9, hbm_free_gb_before=free / 1e9,
-                  scans="BearingSimulator on device (K nearest landmarks of %d, sigma_bearing 0.02, sigma_colour 0.3)" % N)
+                  true_landmarks=n_true,
+                  scans="BearingSimulator on device (K nearest landmarks of %d, sigma_bearing 0.02, sigma_colour 0.3)" % n_true)
     print(json.dumps(header), flush=True)
     lines = []
     win_start = ev()
