@@ -396,7 +396,8 @@ def traffic_from_profiles(arith, dtype, M_local, N, K):
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as fh:
-                tr = json.load(fh)["measure_kernel<float,f32>" if arith == "f32" else "measure_kernel<float>"]
+                tr = json.load(fh)["measure_kernel<double>" if dtype == "f64" else
+                                   "measure_kernel<float,f32>" if arith == "f32" else "measure_kernel<float>"]
             if (dtype, M_local, N, K) == (tr["dtype"], tr["particles_per_gpu"], tr["landmarks"], tr["blobs"]):
                 return tr["dram_bytes"], name
         except Exception:
