@@ -552,6 +552,12 @@ def run_ours(args):
                          else KERNELS_PER_STEP_NCCL) * steps,
         "summary_last": list(e2e_step.last),
     }
+    if world > 1:
+        mig = torch.tensor([st.get("migrated_in", 0)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(mig)
+        line["config"]["migrations_last_frame_all_ranks"] = int(mig.item())
+        if getattr(R.fs, "_timing_on", False):
+            line["peer_chain_ms"] = R.fs.timing_report()
     if selfcheck is not None:
         line["sharded_identical"] = selfcheck["identical"]
         line["selfcheck"] = selfcheck

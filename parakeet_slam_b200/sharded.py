@@ -85,6 +85,9 @@ class ShardedFastSLAM(FastSLAM):
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.exchange = exchange
+        import os as _os
+        self._timing_on = _os.environ.get("PK_TIMING", "") == "1"
+        self._timing = []
 
         self._dist = dist
         self._group = group
@@ -231,6 +234,26 @@ class ShardedFastSLAM(FastSLAM):
                     rank_n_lo=[int(v) for v in x[_lib.PK_XP_RANK_LO:_lib.PK_XP_RANK_LO + G]],
                     rank_n_loc=[int(v) for v in x[_lib.PK_XP_RANK_LOC:_lib.PK_XP_RANK_LOC + G]])
 
+    def _tick(self, name):
+        """PK_TIMING=1: CUDA events between the launches of the peer resampling chain (debugging aid; timing_report()
+        averages them).  A no-op otherwise."""
+        if not self._timing_on:
+            return
+        ev = self._torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._timing.append((name, ev))
+
+    def timing_report(self):
+        """Average milliseconds per segment of the peer resampling chain (needs PK_TIMING=1)."""
+        self._torch.cuda.synchronize(self._device)
+        acc, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(self._timing, self._timing[1:]):
+            if n1 == "start":
+                continue
+            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        return {k: acc[k] / cnt[k] for k in acc}
+
     def _all_reduce_weight_stat(self, tensor, op):
         """The weight normaliser across shards: NCCL all-reduce of the maximum log weight / of sum w and sum w^2."""
         dist = self._dist
@@ -245,6 +268,8 @@ class ShardedFastSLAM(FastSLAM):
             u01 = float(self._uniform())  # every rank must draw the same value (same seed / same source)
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
+            tick = self._tick
+            tick("start")
             if self.weights == "log":
                 self._normalise_log_weights()
             pose_in, aux_in, slot_in = self._pose[cur], self._aux[cur], self._slot[cur]
@@ -253,6 +278,7 @@ class ShardedFastSLAM(FastSLAM):
             _lib.check(lib.pk_weight_scan_publish(_lib.ptr(pose_in), Ml, _lib.ptr(self._cumsum),
                                                   _lib.ptr(self._block_sums), _lib.ptr(pr["sums_tab"]), me, G, st),
                        "pk_weight_scan_publish")
+            tick("scan+publish")
             # one single-CTA kernel: flag barrier (all ranks' totals have arrived), K3b over all ranks' totals, and
             # the exchange plan derived from the emitted-output counts at the rank boundaries
             pr["epoch"] += 1
@@ -262,6 +288,7 @@ class ShardedFastSLAM(FastSLAM):
                                                        self._barrier_timeout_s, Ml, self.exchange_capacity,
                                                        _lib.ptr(self._xplan), status, st),
                        "pk_resample_thresholds_peer")
+            tick("barrier+thresholds+plan")
             # ancestors of my own output window (entries owned by other ranks' particles stay untouched), each local
             # particle's offspring inside the window and the dead-particle scan, in one kernel
             _lib.check(lib.pk_resample_plan(_lib.ptr(self._cumsum), Ml, self.particle_offset, me * nb,
@@ -270,11 +297,13 @@ class ShardedFastSLAM(FastSLAM):
                                             _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
                                             _lib.ptr(self._anc_window), _lib.ptr(self._gather_ws), st),
                        "pk_resample_plan")
+            tick("resample_plan")
             # offspring that live on other ranks: header + landmark block straight into their receive buffers
             _lib.check(lib.pk_push_particles(_lib.ptr(self._xplan), _lib.ptr(self._out_lo), Ml, me, _lib.ptr(pose_in),
                                              _lib.ptr(aux_in), _lib.ptr(slot_in), _lib.ptr(self._pool), self.capacity,
                                              self._dt, _lib.ptr(pr["recv_tab"]), self._send_capacity,
                                              _lib.ptr(self._push_ws), st), "pk_push_particles")
+            tick("push")
             # the second flag barrier (every rank's pushes have landed) runs inside the first kernel of the gather
             pr["epoch"] += 1
             _lib.check(lib.pk_resample_gather_peer(
@@ -284,6 +313,7 @@ class ShardedFastSLAM(FastSLAM):
                 self.exchange_capacity, _lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self._gather_ws),
                 _lib.ptr(self._n_copied), _lib.ptr(pr["flags_tab"]), me, G, pr["epoch"], self._barrier_timeout_s,
                 status, st), "pk_resample_gather_peer")
+            tick("barrier+gather")
             self._cur = nxt
             if self.keep_trace:
                 # debugging / parity traces only: every rank scatters its offspring into a global list
