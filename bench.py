@@ -558,6 +558,16 @@ def run_ours(args):
         line["config"]["migrations_last_frame_all_ranks"] = int(mig.item())
         if getattr(R.fs, "_timing_on", False):
             line["peer_chain_ms"] = R.fs.timing_report()
+        if exchange == "peer":
+            # time every rank spent inside the two flag barriers of a frame (accumulated by the kernels themselves):
+            # what lock-step costs on top of the kernels
+            bw = R.fs.barrier_wait_report()
+            t = torch.tensor([bw["totals_barrier_ms"], bw["pushes_barrier_ms"]], dtype=torch.float64, device="cuda")
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            line["barrier_wait_ms_per_rank"] = {"totals": [round(float(a[0]), 4) for a in allt],
+                                                "pushes": [round(float(a[1]), 4) for a in allt],
+                                                "frames": bw["frames"]}
     if selfcheck is not None:
         line["sharded_identical"] = selfcheck["identical"]
         line["selfcheck"] = selfcheck

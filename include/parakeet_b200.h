@@ -91,6 +91,9 @@ extern "C" {
 #define PK_PEER_HANDLE_BYTES 64  /* size of an exported peer-memory handle (cudaIpcMemHandle_t) */
 #define PK_PEER_OVERFLOW 1ull    /* status bit: a rank would receive more than the exchange capacity */
 #define PK_PEER_TIMEOUT 2ull     /* status bit: a peer did not reach a barrier within the time-out */
+#define PK_PEER_STATUS_WORDS 4   /* status array of the fused entry points (pk_resample_thresholds_peer,
+                                  * pk_resample_gather_peer): [0] sticky PK_PEER_* bits, [1] / [2] nanoseconds this rank
+                                  * has spent inside the first / second flag barrier of its frames, [3] frames counted */
 /* words of the exchange plan a caller may read back (the rest is internal) */
 #define PK_XP_EMIT_LO 0
 #define PK_XP_EMIT_N 1
@@ -347,7 +350,7 @@ int pk_push_particles(const long long* xplan, const long long* out_lo, long long
 /* pk_resample_gather_sharded with the window split read from xplan; anc_window[Ml] = global ancestor
  * of each local output slot and `workspace` as left by pk_resample_plan with out_offset = rank * Ml, n_out = Ml. */
 /* peer_flags_tab != NULL: the flag barrier that makes the other ranks' pushes visible (pk_peer_barrier's) runs inside
- * the first kernel of this call instead of in a launch of its own. */
+ * the first kernel of this call instead of in a launch of its own; status: PK_PEER_STATUS_WORDS device uint64. */
 int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const long long* out_lo, const int* offspring, long long Ml,
                             long long particle_offset, const double* pose4_in, double* pose4_out,
@@ -358,7 +361,8 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             unsigned long long epoch, double timeout_s, unsigned long long* status,
                             void* stream);
 /* K3b of the peer path in ONE single-CTA kernel: the flag barrier after the fused all-gather of the block totals,
- * pk_resample_thresholds over all ranks' totals, and pk_exchange_plan (xplan, PK_PEER_OVERFLOW into status). */
+ * pk_resample_thresholds over all ranks' totals, and pk_exchange_plan (xplan, PK_PEER_OVERFLOW into status[0];
+ * status: PK_PEER_STATUS_WORDS device uint64). */
 int pk_resample_thresholds_peer(const double* all_block_sums, long long nb_total, long long M_total,
                                 double u01, double* plan, double* block_prefix, long long* block_count,
                                 const unsigned long long* peer_flags_tab, int rank, int n_ranks,

@@ -54,6 +54,7 @@ PK_MAX_RANKS = 32
 PK_XPLAN_LONGS = 80
 PK_PEER_HANDLE_BYTES = 64
 PK_PEER_OVERFLOW, PK_PEER_TIMEOUT = 1, 2
+PK_PEER_STATUS_WORDS = 4
 (PK_XP_EMIT_LO, PK_XP_EMIT_N, PK_XP_N_LO, PK_XP_N_LOC, PK_XP_N_HI, PK_XP_N_BELOW, PK_XP_N_ABOVE,
  PK_XP_ABOVE_START, PK_XP_N_SEND, PK_XP_N_IN, PK_XP_OVERFLOW) = range(11)
 PK_XP_RANK_LO = 16

@@ -9,7 +9,7 @@
 //   K3a  one warp per block of PK_SCAN_BLOCK particles: fp64 inclusive prefix sums that are
 //        monotone by construction (each lane folds 32 consecutive weights left to right, lane
 //        bases are a left fold of the lane totals);
-//   K3b  one CTA folds the block totals of ALL shards, in global block order and with a fixed
+//   K3b  one cluster of 8 CTAs folds the block totals of ALL shards, in global block order and with a fixed
 //        tree, into double-double block prefixes -> total, r, u0 and the number of outputs emitted
 //        before every block.  Nothing depends on how many GPUs the particles are spread over;
 //   K4   one thread per particle: its run of output slots is [N(C_{i-1}), N(C_i)) with
@@ -25,7 +25,7 @@ namespace pk {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kScanWarps = 4;
-constexpr int kMinGroupBlocks = 8;  // scan blocks folded sequentially by one thread in K3b (doubles while > 1024 groups)
+constexpr int kMinGroupBlocks = 8;  // scan blocks per group in K3b (doubles while > 1024 groups)
 constexpr int kMaxGroupBlocks = 32;
 constexpr int kMaxScanGroups = 1024;
 
@@ -190,8 +190,14 @@ struct PeerSync {
     unsigned long long* const* flags;   // device table: flags base of every rank (NULL: no barrier)
     int me, G;
     unsigned long long epoch, timeout_ns;
-    unsigned long long* status;
+    unsigned long long* status;         // [0] sticky PK_PEER_* bits, [1 + which] nanoseconds spent waiting, [3] barriers
+    int which;                          // 0: first barrier of the frame (block totals), 1: second (pushes landed)
 };
+// accounting of one CTA's wait (thread 0, after the __syncthreads() that follows peer_sync_thread)
+__device__ __forceinline__ void peer_sync_account(const PeerSync& ps, unsigned long long t_entry) {
+    atomicAdd(ps.status + 1 + ps.which, global_timer_ns() - t_entry);
+    if (ps.which == 0) atomicAdd(ps.status + 3, 1ull);
+}
 __device__ __forceinline__ void peer_sync_thread(const PeerSync& ps, int g, bool post) {
     if (g >= ps.G) return;
     if (post) {
@@ -211,161 +217,206 @@ __device__ __forceinline__ void peer_sync_thread(const PeerSync& ps, int g, bool
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3b  (single CTA of 1024 threads)
+// K3b  (ONE thread-block cluster: kThrCluster CTAs of 1024 threads, distributed shared memory)
+//
+// Block totals s_b (b in global block order) -> double-double exclusive block prefixes P_b, total,
+// r, u0 and the number of outputs emitted up to the end of every block.  The fold tree is a fixed
+// function of the TOTAL number of blocks (never of the launch geometry or of how the blocks are
+// spread over ranks; every rank of a sharded filter runs this kernel on the same array):
+//   group  = GB consecutive blocks (GB = 8, doubling while there would be more than 1024 groups):
+//            Kogge-Stone inclusive scan over the GB lanes of the group        -> L_b, T_g
+//   super  = 32 consecutive groups: Kogge-Stone scan over the lanes of a warp -> X_g, S_w
+//   top    = Kogge-Stone scan of the <= 32 super totals (one warp)            -> Y_w, total
+//   P_b    = (Y_w + X_g) + L_b
+// A single SM's fp64 pipe made the former single-CTA form cost 15 us at 1024 blocks and 60-80 us
+// at 8192 (8 ranks); spread over 8 SMs with 5-step scans it is a few microseconds at any size.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+constexpr int kThrCluster = 8;
+constexpr int kThrGroupsPerCta = kMaxScanGroups / kThrCluster;   // 128 groups = 4 supers per CTA
+constexpr int kThrMaxRounds = kMaxGroupBlocks / 8;               // blocks of a CTA / 1024 threads
+static_assert(kThrGroupsPerCta * kMinGroupBlocks == 1024, "one block per thread and round");
+
+__device__ __forceinline__ dd shfl_up_dd(dd v, int o) {
+    return dd{__shfl_up_sync(kFullMask, v.hi, o), __shfl_up_sync(kFullMask, v.lo, o)};
+}
+// inclusive scan over aligned segments of `width` lanes (power of two <= 32): element = earlier + later
+__device__ __forceinline__ dd seg_scan_dd(dd v, int lane, int width) {
+    const int pos = lane & (width - 1);
+    for (int o = 1; o < width; o <<= 1) {
+        const dd up = shfl_up_dd(v, o);
+        if (pos >= o) v = dd_add(up, v);
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory object of this kernel) in CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ unsigned dsmem_addr(T* p, unsigned rank) {
+    const unsigned local = (unsigned)__cvta_generic_to_shared(p);
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void dsmem_store(unsigned addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_store(unsigned addr, long long v) {
+    asm volatile("st.shared::cluster.s64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(kThrCluster, 1, 1) __launch_bounds__(1024)
 thresholds_kernel(const double* __restrict__ sums, long long nb, long long M_total, double u01,
-                  double* __restrict__ plan, double* block_prefix, long long* block_count, int kGroupBlocks,
+                  double* __restrict__ plan, double* __restrict__ block_prefix, long long* block_count, int GB,
                   PeerSync ps, long long Ml, long long xcap, long long* __restrict__ xplan) {
-    __shared__ double g_hi[kMaxScanGroups], g_lo[kMaxScanGroups];
-    __shared__ long long g_cnt[kMaxScanGroups];
+    __shared__ double T_hi[kThrGroupsPerCta], T_lo[kThrGroupsPerCta];  // group totals, then group prefixes
+    __shared__ double S_hi[32], S_lo[32];                              // super totals of the cluster, then prefixes
+    __shared__ long long w_max[32];
+    __shared__ long long c_max[kThrCluster];
     __shared__ double s_r, s_u0;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned cta = cluster_ctarank();
     if (ps.flags != nullptr) {
         // sharded filter, peer exchange: the block totals of all ranks were stored into `sums` by their scan kernels
-        // (fused all-gather); wait for every rank's flag before reading them
-        peer_sync_thread(ps, t, true);
+        // (fused all-gather); CTA 0 posts this rank's flag, every CTA waits for every rank's flag before reading them
+        const unsigned long long t_entry = global_timer_ns();
+        peer_sync_thread(ps, t, cta == 0);
         __syncthreads();
+        if (cta == 0 && t == 0) peer_sync_account(ps, t_entry);
     }
-    const long long ngroups = (nb + kGroupBlocks - 1) / kGroupBlocks;
-    const long long b0 = (long long)t * kGroupBlocks;
-    const long long b1 = min(nb, b0 + kGroupBlocks);
-    // phase A: per-thread sequential double-double fold of its group's block totals
-    // (loads are issued eight at a time so the fold does not pay one L2 round trip per block)
-    constexpr int kBatch = 8;
-    static_assert(kMinGroupBlocks % kBatch == 0, "batch size");
-    dd acc{0.0, 0.0};
-    if (t < ngroups) {
-        for (long long bb = b0; bb < b1; bb += kBatch) {
-            double v[kBatch];
+    const int rounds = GB / kMinGroupBlocks;                       // 1024 blocks of this CTA per round
+    const long long cta_block0 = (long long)cta * kThrGroupsPerCta * GB;
+    // phase A: one thread per block; inclusive scan inside each group of GB lanes
+    double sv[kThrMaxRounds];
+    dd L[kThrMaxRounds];
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) v[j] = (bb + j < b1) ? sums[bb + j] : 0.0;
-#pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const long long b = bb + j;
-                if (b < b1) {
-                    block_prefix[2 * b] = acc.hi;  // local exclusive prefix for now
-                    block_prefix[2 * b + 1] = acc.lo;
-                    acc = dd_add_d(acc, v[j]);
-                }
+    for (int k = 0; k < kThrMaxRounds; ++k) {
+        sv[k] = 0.0;
+        L[k] = dd{0.0, 0.0};
+        if (k < rounds) {
+            const int j = k * 1024 + t;
+            const long long b = cta_block0 + j;
+            sv[k] = (b < nb) ? sums[b] : 0.0;
+            const dd inc = seg_scan_dd(dd{sv[k], 0.0}, lane, GB);
+            const dd up = shfl_up_dd(inc, 1);
+            if ((lane & (GB - 1)) != 0) L[k] = up;
+            if ((lane & (GB - 1)) == GB - 1) {
+                T_hi[j / GB] = inc.hi;
+                T_lo[j / GB] = inc.lo;
             }
         }
-        g_hi[t] = acc.hi;
-        g_lo[t] = acc.lo;
     }
-    __syncthreads();
-    // phase B: exclusive double-double scan of the group totals.  One warp; each lane folds a
-    // contiguous run of groups left to right, lane bases by a left fold over the lane totals (a fixed
-    // tree: every rank runs this kernel on the same array, so the result does not depend on the
-    // number of shards).
-    if (t < 32) {
-        const int per = (int)((ngroups + 31) / 32);
-        const long long q0 = (long long)t * per, q1 = min(ngroups, q0 + per);
-        dd run{0.0, 0.0};
-        for (long long g = q0; g < q1; ++g) run = dd_add(run, dd{g_hi[g], g_lo[g]});
-        dd base{0.0, 0.0};
-        for (int l = 0; l < 32; ++l) {
-            const double h = __shfl_sync(0xffffffffu, run.hi, l), lo2 = __shfl_sync(0xffffffffu, run.lo, l);
-            if (l < t) base = dd_add(base, dd{h, lo2});
-            if (l == 31 && t == 31) run = dd_add(base, run);  // grand total, held by lane 31
+    cluster_sync_all();   // (also: every CTA of the cluster is running before its shared memory is written remotely)
+    // phase B1: warp w < 4 scans the 32 groups of super cta * 4 + w; its total goes to every CTA of the cluster
+    if (warp < kThrGroupsPerCta / 32) {
+        const int g = warp * 32 + lane;
+        const dd inc = seg_scan_dd(dd{T_hi[g], T_lo[g]}, lane, 32);
+        dd ex = shfl_up_dd(inc, 1);
+        if (lane == 0) ex = dd{0.0, 0.0};
+        T_hi[g] = ex.hi;
+        T_lo[g] = ex.lo;
+        const double th = __shfl_sync(kFullMask, inc.hi, 31), tl = __shfl_sync(kFullMask, inc.lo, 31);
+        if (lane < kThrCluster) {
+            const int w = (int)cta * (kThrGroupsPerCta / 32) + warp;
+            dsmem_store(dsmem_addr(&S_hi[w], (unsigned)lane), th);
+            dsmem_store(dsmem_addr(&S_lo[w], (unsigned)lane), tl);
         }
-        dd acc2 = base;
-        for (long long g = q0; g < q1; ++g) {
-            const dd cur{g_hi[g], g_lo[g]};
-            g_hi[g] = acc2.hi;
-            g_lo[g] = acc2.lo;
-            acc2 = dd_add(acc2, cur);
-        }
-        if (t == 31) {
-            const double total = run.hi + run.lo;
+    }
+    cluster_sync_all();
+    // phase B2: every CTA scans the 32 super totals itself (same operations, same bits)
+    if (warp == 0) {
+        const dd inc = seg_scan_dd(dd{S_hi[lane], S_lo[lane]}, lane, 32);
+        dd ex = shfl_up_dd(inc, 1);
+        if (lane == 0) ex = dd{0.0, 0.0};
+        S_hi[lane] = ex.hi;
+        S_lo[lane] = ex.lo;
+        if (lane == 31) {
+            const double total = inc.hi + inc.lo;
             const double r = total / (double)M_total;  // range_ = sum_/float(len(particles)) :225
             const double u0 = u01 * r;                 // step = random()*range_             :226
             s_r = r;
             s_u0 = u0;
-            plan[0] = total;
-            plan[1] = r;
-            plan[2] = u0;
-            plan[3] = run.hi;
-            plan[4] = run.lo;
-            plan[5] = (double)M_total;
-            plan[6] = u01;
-            plan[7] = 0.0;
+            if (cta == 0) {
+                plan[0] = total;
+                plan[1] = r;
+                plan[2] = u0;
+                plan[3] = inc.hi;
+                plan[4] = inc.lo;
+                plan[5] = (double)M_total;
+                plan[6] = u01;
+                plan[7] = 0.0;
+            }
         }
     }
     __syncthreads();
-    // phase C: global block prefixes, and the emitted-output count at the end of every block
+    if (t < kThrGroupsPerCta) {
+        const int w = (int)cta * (kThrGroupsPerCta / 32) + (t >> 5);
+        const dd G = dd_add(dd{S_hi[w], S_lo[w]}, dd{T_hi[t], T_lo[t]});
+        T_hi[t] = G.hi;
+        T_lo[t] = G.lo;
+    }
+    __syncthreads();
+    // phase C: global block prefixes, the emitted-output count at the end of every block, running maximum
     const double r = s_r, u0 = s_u0;
-    long long runmax = 0;
-    if (t < ngroups) {
-        const dd gb{g_hi[t], g_lo[t]};
-        for (long long bb = b0; bb < b1; bb += kBatch) {
-            double ph[kBatch], pl[kBatch], sv[kBatch];
+    long long e_inc[kThrMaxRounds];
+    long long carry = 0;
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const bool in = bb + j < b1;
-                ph[j] = in ? block_prefix[2 * (bb + j)] : 0.0;
-                pl[j] = in ? block_prefix[2 * (bb + j) + 1] : 0.0;
-                sv[j] = in ? sums[bb + j] : 0.0;
+    for (int k = 0; k < kThrMaxRounds; ++k) {
+        e_inc[k] = 0;
+        if (k < rounds) {
+            const int j = k * 1024 + t;
+            const long long b = cta_block0 + j;
+            long long e = 0;
+            if (b < nb) {
+                const dd P = dd_add(dd{T_hi[j / GB], T_lo[j / GB]}, L[k]);
+                block_prefix[2 * b] = P.hi;
+                block_prefix[2 * b + 1] = P.lo;
+                e = count_le(P, sv[k], u0, r, M_total);
             }
-#pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const long long b = bb + j;
-                if (b < b1) {
-                    const dd P = dd_add(gb, dd{ph[j], pl[j]});
-                    block_prefix[2 * b] = P.hi;
-                    block_prefix[2 * b + 1] = P.lo;
-                    const long long e = count_le(P, sv[j], u0, r, M_total);
-                    runmax = max(runmax, e);
-                    block_count[b + 1] = runmax;  // local running max for now
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(kFullMask, e, o);
+                if (lane >= o) e = max(e, up);
             }
-        }
-        g_cnt[t] = runmax;
-    }
-    __syncthreads();
-    if (t < 32) {
-        const int per = (int)((ngroups + 31) / 32);
-        const long long q0 = (long long)t * per, q1 = min(ngroups, q0 + per);
-        long long mx = 0;
-        for (long long g = q0; g < q1; ++g) mx = max(mx, g_cnt[g]);
-        long long base = 0;
-        for (int l = 0; l < 32; ++l) {
-            const long long v = __shfl_sync(0xffffffffu, mx, l);
-            if (l < t) base = max(base, v);
-        }
-        long long run = base;
-        for (long long g = q0; g < q1; ++g) {
-            const long long cur = g_cnt[g];
-            g_cnt[g] = run;
-            run = max(run, cur);
-        }
-        if (t == 0) block_count[0] = 0;
-    }
-    __syncthreads();
-    if (t < ngroups) {
-        const long long gbase = g_cnt[t];
-        for (long long bb = b0; bb < b1; bb += kBatch) {
-            long long c[kBatch];
-#pragma unroll
-            for (int j = 0; j < kBatch; ++j) c[j] = (bb + j < b1) ? block_count[bb + j + 1] : 0;
-#pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const long long b = bb + j;
-                if (b < b1) {
-                    long long v = max(c[j], gbase);
-                    if (b == nb - 1) v = M_total;  // every output slot is assigned
-                    block_count[b + 1] = v;
-                }
+            if (lane == 31) w_max[warp] = e;
+            __syncthreads();
+            long long base = carry, all = carry;
+            for (int w = 0; w < 32; ++w) {
+                const long long v = w_max[w];
+                if (w < warp) base = max(base, v);
+                all = max(all, v);
             }
+            e_inc[k] = max(e, base);
+            carry = all;
+            __syncthreads();
         }
     }
+    // running maximum across the CTAs of the cluster
+    if (t < kThrCluster) dsmem_store(dsmem_addr(&c_max[cta], (unsigned)t), carry);
+    cluster_sync_all();
+    long long cbase = 0;
+    for (unsigned c = 0; c < cta; ++c) cbase = max(cbase, c_max[c]);
+#pragma unroll
+    for (int k = 0; k < kThrMaxRounds; ++k) {
+        if (k < rounds) {
+            const long long b = cta_block0 + k * 1024 + t;
+            if (b < nb) block_count[b + 1] = (b == nb - 1) ? M_total : max(e_inc[k], cbase);  // every output slot is assigned
+        }
+    }
+    if (cta == 0 && t == 0) block_count[0] = 0;
     if (xplan != nullptr) {
         // the exchange plan follows from the emitted-output counts at the rank boundaries (one thread)
-        __syncthreads();
-        if (t == 0) {
+        __threadfence();
+        cluster_sync_all();
+        if (cta == 0 && t == 0) {
             const long long nbr = nb / ps.G;
             long long E[PK_MAX_RANKS + 1];
-            for (int g = 0; g <= ps.G; ++g) E[g] = block_count[(long long)g * nbr];
+            for (int g = 0; g <= ps.G; ++g) E[g] = __ldcg(block_count + (long long)g * nbr);
             long long xp[PK_XPLAN_LONGS];
             make_exchange_plan(E, ps.G, Ml, ps.me, xcap, xp);
             for (int i = 0; i < PK_XPLAN_LONGS; ++i) xplan[i] = xp[i];
@@ -576,8 +627,10 @@ free_list_fused_kernel(const int* __restrict__ offspring_window, const int* __re
         // sharded filter, peer exchange: the arrivals were pushed into this rank's receive buffer by the other ranks'
         // previous kernels; CTA 0 posts this rank's flag (its own pushes are done: earlier kernels of this stream),
         // every CTA waits for all ranks' flags before anything downstream of this kernel reads the buffer
+        const unsigned long long t_entry = global_timer_ns();
         peer_sync_thread(ps, t, blk == 0);
         __syncthreads();
+        if (blk == 0 && t == 0) peer_sync_account(ps, t_entry);
     }
     int s = 0;
     for (long long b = t; b < blk; b += PK_SCAN_BLOCK) s += block_dead[b];
@@ -645,7 +698,7 @@ __global__ void exchange_plan_kernel(const long long* __restrict__ block_count, 
 __global__ void __launch_bounds__(PK_MAX_RANKS)
 peer_barrier_kernel(unsigned long long* const* __restrict__ peer_flags, int me, int G, unsigned long long epoch,
                     unsigned long long timeout_ns, unsigned long long* __restrict__ status) {
-    peer_sync_thread(PeerSync{peer_flags, me, G, epoch, timeout_ns, status}, (int)threadIdx.x, true);
+    peer_sync_thread(PeerSync{peer_flags, me, G, epoch, timeout_ns, status, 0}, (int)threadIdx.x, true);
 }
 
 // One thread per migrating particle.  Send item j is global output slot k (the N_BELOW run starts at
@@ -1106,8 +1159,8 @@ int pk_resample_thresholds(const double* all_block_sums, long long nb_total, lon
     // the fold tree depends on the TOTAL block count only, never on how the blocks are spread over ranks
     int group = kMinGroupBlocks;
     while ((long long)group * kMaxScanGroups < nb_total) group *= 2;
-    thresholds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(all_block_sums, nb_total, M_total, u01, plan, block_prefix,
-                                                           block_count, group, PeerSync{nullptr, 0, 1, 0, 0, nullptr}, 0, 0,
+    thresholds_kernel<<<kThrCluster, 1024, 0, (cudaStream_t)stream>>>(all_block_sums, nb_total, M_total, u01, plan, block_prefix,
+                                                           block_count, group, PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0}, 0, 0,
                                                            nullptr);
     PK_LAUNCH_CHECK("thresholds_kernel");
     return PK_OK;
@@ -1126,10 +1179,10 @@ int pk_resample_thresholds_peer(const double* all_block_sums, long long nb_total
     PK_CHECK_ARG(epoch > 0 && timeout_s > 0.0, "barrier arguments");
     int group = kMinGroupBlocks;
     while ((long long)group * kMaxScanGroups < nb_total) group *= 2;
-    thresholds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+    thresholds_kernel<<<kThrCluster, 1024, 0, (cudaStream_t)stream>>>(
         all_block_sums, nb_total, M_total, u01, plan, block_prefix, block_count, group,
         PeerSync{reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
-                 (unsigned long long)(timeout_s * 1e9), status},
+                 (unsigned long long)(timeout_s * 1e9), status, 0},
         Ml, capacity, xplan);
     PK_LAUNCH_CHECK("thresholds_kernel");
     return PK_OK;
@@ -1240,7 +1293,7 @@ int pk_resample_gather_planned(const long long* ancestors, long long M, const do
     const long long nb = num_blocks(M);
     free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, M, g.dead_excl, g.block_dead, nb,
                                                                   g.free_list, n_copied_out,
-                                                                  PeerSync{nullptr, 0, 1, 0, 0, nullptr});
+                                                                  PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0});
     PK_LAUNCH_CHECK("free_list_fused_kernel");
     const int threads = 256;
     assign_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
@@ -1339,7 +1392,7 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
     PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
     PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    return gather_sharded_impl(false, PeerSync{nullptr, 0, 1, 0, 0, nullptr}, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
+    return gather_sharded_impl(false, PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0}, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
 }
@@ -1491,12 +1544,12 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                  "null pointer");
     PK_CHECK_ARG(Ml > 0 && Ml < (1ll << 31) && recv_capacity >= 0, "sizes");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    PeerSync sync{nullptr, 0, 1, 0, 0, nullptr};
+    PeerSync sync{nullptr, 0, 1, 0, 0, nullptr, 0};
     if (peer_flags_tab != nullptr) {
         PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
         PK_CHECK_ARG(epoch > 0 && timeout_s > 0.0 && status != nullptr, "barrier arguments");
         sync = PeerSync{reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
-                        (unsigned long long)(timeout_s * 1e9), status};
+                        (unsigned long long)(timeout_s * 1e9), status, 1};
     }
     return gather_sharded_impl(true, sync, anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,

@@ -178,7 +178,7 @@ class ShardedFastSLAM(FastSLAM):
                               flags_tab=tab(0), sums_tab=tab(off_sums), recv_tab=tab(off_recv),
                               sums_ptr=bases[me] + off_sums, recv_ptr=bases[me] + off_recv, epoch=0)
             self._xplan = torch.zeros((_lib.PK_XPLAN_LONGS,), dtype=i64, device=dev)
-            self._peer_status = torch.zeros((1,), dtype=i64, device=dev)
+            self._peer_status = torch.zeros((_lib.PK_PEER_STATUS_WORDS,), dtype=i64, device=dev)
             self._anc_window = torch.zeros((Ml,), dtype=i64, device=dev)
             self._send_capacity = max(1, (G - 1) * cap)   # one particle may own every output slot
             self._push_ws = torch.zeros((4 * self._send_capacity,), dtype=torch.int32, device=dev)
@@ -211,7 +211,7 @@ class ShardedFastSLAM(FastSLAM):
         status word is sticky; reading it synchronises the stream)."""
         if self._peer is None:
             return
-        bits = int(self._peer_status.item())
+        bits = int(self._peer_status[0].item())
         if bits & _lib.PK_PEER_OVERFLOW:
             raise _lib.ParakeetLibraryError(
                 "a resampling step had to move more than exchange_capacity=%d particles between ranks; the filter "
@@ -253,6 +253,18 @@ class ShardedFastSLAM(FastSLAM):
             acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
             cnt[n1] = cnt.get(n1, 0) + 1
         return {k: acc[k] / cnt[k] for k in acc}
+
+    def barrier_wait_report(self, reset=True):
+        """Average milliseconds per frame this rank spent inside the two flag barriers of the peer resampling chain
+        (from kernel entry to all flags seen; accumulated on the device by the kernels that hold the barriers)."""
+        if self._peer is None:
+            return {}
+        s = self._peer_status.cpu().numpy()
+        n = max(1, int(s[3]))
+        out = dict(frames=int(s[3]), totals_barrier_ms=float(s[1]) / n * 1e-6, pushes_barrier_ms=float(s[2]) / n * 1e-6)
+        if reset:
+            self._peer_status[1:] = 0
+        return out
 
     def _all_reduce_weight_stat(self, tensor, op):
         """The weight normaliser across shards: NCCL all-reduce of the maximum log weight / of sum w and sum w^2."""
