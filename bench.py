@@ -46,8 +46,8 @@ LANDMARKS = 64
 BLOBS = 8
 # launches per frame: motion, measure, weight_scan, thresholds, resample_plan, free_list_fused, assign,
 # copy_blocks
-KERNELS_PER_STEP = 7
-KERNELS_PER_STEP_PEER = 11   # weight_scan(+all-gather), thresholds(+barrier+plan), plan, push headers, push blocks, free list(+barrier), assign, 2 x copy
+KERNELS_PER_STEP = 8
+KERNELS_PER_STEP_PEER = 12   # weight_scan(+all-gather), thresholds(+barrier+plan), plan, push headers, push blocks, free list, assign (local), copy, assign (arrivals, +barrier), copy
 KERNELS_PER_STEP_NCCL = 16   # + 2 x (pack headers, pack blocks), offspring window, unpack (plus 2 NCCL collectives)
 REF_SAMPLE_PARTICLES = 16    # particles per replica of the bounded reference sample (config-2 map, 8 blobs)
 

@@ -350,7 +350,11 @@ int pk_push_particles(const long long* xplan, const long long* out_lo, long long
 /* pk_resample_gather_sharded with the window split read from xplan; anc_window[Ml] = global ancestor
  * of each local output slot and `workspace` as left by pk_resample_plan with out_offset = rank * Ml, n_out = Ml. */
 /* peer_flags_tab != NULL: the flag barrier that makes the other ranks' pushes visible (pk_peer_barrier's) runs inside
- * the first kernel of this call instead of in a launch of its own; status: PK_PEER_STATUS_WORDS device uint64. */
+ * this call instead of in a launch of its own, in front of the part that reads the receive buffer: the free list, the
+ * slots filled from local ancestors and the copies of the local duplicates run first, while the pushes are still in
+ * flight.  status: PK_PEER_STATUS_WORDS device uint64.  pushes_done_event: NULL, or a cudaEvent_t recorded after this
+ * rank's pk_push_particles when that ran on ANOTHER stream (so that it overlaps the free list and the slot assignment
+ * of this call); `stream` waits for it before any landmark block is overwritten and before the rank's flag is posted. */
 int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const long long* out_lo, const int* offspring, long long Ml,
                             long long particle_offset, const double* pose4_in, double* pose4_out,
@@ -359,7 +363,7 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             int dtype, void* workspace, long long* total_dead_out,
                             const unsigned long long* peer_flags_tab, int rank, int n_ranks,
                             unsigned long long epoch, double timeout_s, unsigned long long* status,
-                            void* stream);
+                            void* pushes_done_event, void* stream);
 /* K3b of the peer path in ONE single-CTA kernel: the flag barrier after the fused all-gather of the block totals,
  * pk_resample_thresholds over all ranks' totals, and pk_exchange_plan (xplan, PK_PEER_OVERFLOW into status[0];
  * status: PK_PEER_STATUS_WORDS device uint64). */

@@ -618,20 +618,11 @@ resample_plan_kernel(const double* __restrict__ cumsum, long long M_local, long 
 __global__ void __launch_bounds__(PK_SCAN_BLOCK)
 free_list_fused_kernel(const int* __restrict__ offspring_window, const int* __restrict__ slot_in, long long M,
                        int* __restrict__ dead_excl, const int* __restrict__ block_dead, long long nb,
-                       int* __restrict__ free_list, long long* __restrict__ total_out, PeerSync ps) {
+                       int* __restrict__ free_list, long long* __restrict__ total_out) {
     __shared__ int s_part[32];
     __shared__ int s_off;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long blk = blockIdx.x;
-    if (ps.flags != nullptr) {
-        // sharded filter, peer exchange: the arrivals were pushed into this rank's receive buffer by the other ranks'
-        // previous kernels; CTA 0 posts this rank's flag (its own pushes are done: earlier kernels of this stream),
-        // every CTA waits for all ranks' flags before anything downstream of this kernel reads the buffer
-        const unsigned long long t_entry = global_timer_ns();
-        peer_sync_thread(ps, t, blk == 0);
-        __syncthreads();
-        if (blk == 0 && t == 0) peer_sync_account(ps, t_entry);
-    }
     int s = 0;
     for (long long b = t; b < blk; b += PK_SCAN_BLOCK) s += block_dead[b];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
@@ -777,17 +768,35 @@ offspring_window_kernel(const long long* __restrict__ out_lo, const int* __restr
 // xplan == NULL: n_lo / n_loc are the host's values and local_run[j] is the ancestor of local output
 // n_lo + j (NCCL path).  xplan != NULL: the split is read from the device-resident exchange plan and
 // local_run is indexed by the output slot itself (peer path; nothing on this path visits the host).
+//
+// `part`: kAssignAll -- every output slot in one launch (NCCL path: the arrivals are in `recv` already);
+// kAssignLocal -- slots filled from local ancestors only; the arrival slots just mark their entry of the
+// pool-to-pool copy list as "not a copy", so the local duplicates can be copied while the other ranks' pushes
+// are still in flight; kAssignArrivals -- thread i handles arrival i of the receive buffer, after the flag
+// barrier (`ps`) that makes every rank's pushes visible.
+enum { kAssignAll = 0, kAssignLocal = 1, kAssignArrivals = 2 };
+
 __global__ void __launch_bounds__(256)
-assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, long long particle_offset, long long n_lo,
+assign_sharded_kernel(int part, PeerSync ps, const long long* __restrict__ local_run, long long Ml,
+                      long long particle_offset, long long n_lo,
                       long long n_loc, const long long* __restrict__ xplan, const double* __restrict__ pose_in,
                       double* __restrict__ pose_out,
                       const int* __restrict__ aux_in, int* __restrict__ aux_out, const int* __restrict__ slot_in,
-                      int* __restrict__ slot_out, const unsigned char* __restrict__ recv, long long stride,
+                      int* __restrict__ slot_out, const unsigned char* recv, long long stride,
                       const int* __restrict__ dead_excl, const int* __restrict__ free_list,
                       const long long* __restrict__ total_dead, int* __restrict__ copy_src, int* __restrict__ copy_dst,
                       int* __restrict__ copy_nlive, int* __restrict__ unpack_src, int* __restrict__ unpack_dst,
                       int* __restrict__ unpack_nlive) {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ps.flags != nullptr) {
+        // sharded filter, peer exchange: the arrivals were pushed into this rank's receive buffer by the other ranks;
+        // CTA 0 posts this rank's flag (its own pushes: earlier kernels of this stream, fenced), every CTA waits for
+        // all ranks' flags before it reads the buffer
+        const unsigned long long t_entry = global_timer_ns();
+        peer_sync_thread(ps, (int)threadIdx.x, blockIdx.x == 0);
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) peer_sync_account(ps, t_entry);
+    }
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Ml) return;
     long long run_shift = n_lo;
     if (xplan != nullptr) {
@@ -798,10 +807,19 @@ assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, lon
     }
     const long long n_in = Ml - n_loc;
     const long long n_dups = *total_dead - n_in;  // local outputs that are not the first of their ancestor
+    if (part == kAssignArrivals) {
+        if (k >= n_in) return;
+        if (k >= n_lo) k += n_loc;  // arrival index -> output slot
+    }
     double2* dst = reinterpret_cast<double2*>(pose_out + 4 * k);
     if (k < n_lo || k >= n_lo + n_loc) {
         const long long r = (k < n_lo) ? k : k - n_loc;  // index in the receive buffer (source-rank order)
         const long long nidx = (k < n_lo) ? k : n_lo + n_dups + (k - n_lo - n_loc);
+        if (part == kAssignLocal) {
+            copy_src[nidx] = -1;  // not a pool-to-pool copy
+            copy_nlive[nidx] = 0;
+            return;
+        }
         const double2* src = reinterpret_cast<const double2*>(recv + (size_t)r * stride);
         dst[0] = src[0];
         dst[1] = src[1];
@@ -812,11 +830,14 @@ assign_sharded_kernel(const long long* __restrict__ local_run, long long Ml, lon
         unpack_src[r] = (int)r;
         unpack_dst[r] = d;
         unpack_nlive[r] = ax.x;
-        copy_src[nidx] = -1;  // not a pool-to-pool copy
-        copy_dst[nidx] = d;
-        copy_nlive[nidx] = 0;
+        if (part == kAssignAll) {
+            copy_src[nidx] = -1;  // not a pool-to-pool copy
+            copy_dst[nidx] = d;
+            copy_nlive[nidx] = 0;
+        }
         return;
     }
+    if (part == kAssignArrivals) return;
     const long long a = local_run[k - run_shift] - particle_offset;  // local ancestor
     const double2* src = reinterpret_cast<const double2*>(pose_in + 4 * a);
     dst[0] = src[0];
@@ -1292,8 +1313,7 @@ int pk_resample_gather_planned(const long long* ancestors, long long M, const do
     GatherWs g = carve(workspace, M);
     const long long nb = num_blocks(M);
     free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, M, g.dead_excl, g.block_dead, nb,
-                                                                  g.free_list, n_copied_out,
-                                                                  PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0});
+                                                                  g.free_list, n_copied_out);
     PK_LAUNCH_CHECK("free_list_fused_kernel");
     const int threads = 256;
     assign_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
@@ -1335,7 +1355,7 @@ static int gather_sharded_impl(bool planned, PeerSync sync, const long long* loc
                                long long n_lo, long long n_loc, const double* pose4_in, double* pose4_out,
                                const int* aux2_in, int* aux2_out, const int* slot_in, int* slot_out, const void* recv,
                                void* pool, int capacity, int dtype, void* workspace, long long* total_dead_out,
-                               cudaStream_t st) {
+                               cudaStream_t st, cudaEvent_t pushes_done = nullptr) {
     GatherWs g = carve(workspace, Ml);
     const long long nb = num_blocks(Ml);
     const long long stride = pk_particle_record_bytes(capacity, dtype);
@@ -1348,20 +1368,39 @@ static int gather_sharded_impl(bool planned, PeerSync sync, const long long* loc
             g.offspring_local, Ml, g.dead_excl, g.block_dead, nb);
         PK_LAUNCH_CHECK("dead_scan_kernel");
     }
+    const PeerSync no_sync{nullptr, 0, 1, 0, 0, nullptr, 0};
     free_list_fused_kernel<<<(unsigned)nb, PK_SCAN_BLOCK, 0, st>>>(g.offspring_local, slot_in, Ml, g.dead_excl, g.block_dead,
-                                                                  nb, g.free_list, total_dead_out, sync);
+                                                                  nb, g.free_list, total_dead_out);
     PK_LAUNCH_CHECK("free_list_fused_kernel");
-    assign_sharded_kernel<<<grid, threads, 0, st>>>(local_run, Ml, particle_offset, n_lo, n_loc, xplan, pose4_in, pose4_out,
-                                                    aux2_in, aux2_out, slot_in, slot_out, (const unsigned char*)recv, stride,
-                                                    g.dead_excl, g.free_list, total_dead_out, g.copy_src, g.copy_dst,
-                                                    g.copy_nlive, g.unpack_src, g.unpack_dst, g.unpack_nlive);
+    auto assign = [&](int part, const PeerSync& ps) {
+        assign_sharded_kernel<<<grid, threads, 0, st>>>(part, ps, local_run, Ml, particle_offset, n_lo, n_loc, xplan, pose4_in,
+                                                        pose4_out, aux2_in, aux2_out, slot_in, slot_out,
+                                                        (const unsigned char*)recv, stride, g.dead_excl, g.free_list,
+                                                        total_dead_out, g.copy_src, g.copy_dst, g.copy_nlive, g.unpack_src,
+                                                        g.unpack_dst, g.unpack_nlive);
+    };
+    // peer exchange: everything that does not need the arrivals runs first -- the other ranks' pushes (and this
+    // rank's own) are still draining over NVLink while the local duplicates are copied at HBM speed; the flag barrier
+    // sits in front of the arrivals' part
+    const bool split = sync.flags != nullptr;
+    assign(split ? kAssignLocal : kAssignAll, no_sync);
     PK_LAUNCH_CHECK("assign_sharded_kernel");
+    const long long* skip = xplan ? xplan + XP_OVERFLOW : nullptr;
+    // this rank's pushes were launched on another stream: a particle whose offspring all live on other ranks is dead
+    // here, and its block -- which the push still reads -- may be handed to a local duplicate; the flag must not be
+    // posted before the pushes are complete either
+    if (pushes_done != nullptr) PK_CUDA(cudaStreamWaitEvent(st, pushes_done, 0));
     if (capacity > 0) {
-        const long long* skip = xplan ? xplan + XP_OVERFLOW : nullptr;
         // local duplicates: pool -> pool (entries that belong to incoming particles carry src = -1 and are skipped)
         int rc = copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, Ml, total_dead_out, st,
                                     0, 0, nullptr, nullptr, skip);
         if (rc != PK_OK) return rc;
+    }
+    if (split) {
+        assign(kAssignArrivals, sync);
+        PK_LAUNCH_CHECK("assign_sharded_kernel(arrivals)");
+    }
+    if (capacity > 0) {
         // arrivals: exchange buffer -> pool
         if (xplan != nullptr) {
             const long long n_max = recv_capacity < Ml ? recv_capacity : Ml;
@@ -1538,7 +1577,7 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const void* recv, long long recv_capacity, void* pool, int capacity, int dtype,
                             void* workspace, long long* total_dead_out, const unsigned long long* peer_flags_tab,
                             int rank, int n_ranks, unsigned long long epoch, double timeout_s,
-                            unsigned long long* status, void* stream) {
+                            unsigned long long* status, void* pushes_done_event, void* stream) {
     PK_CHECK_ARG(xplan && anc_window && out_lo && offspring && pose4_in && pose4_out && aux2_in && aux2_out && slot_in &&
                      slot_out && pool && workspace && total_dead_out && recv,
                  "null pointer");
@@ -1553,7 +1592,7 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
     }
     return gather_sharded_impl(true, sync, anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
-                               total_dead_out, (cudaStream_t)stream);
+                               total_dead_out, (cudaStream_t)stream, (cudaEvent_t)pushes_done_event);
 }
 
 /* peer memory: plain cudaMalloc allocations shared between the ranks of one node by CUDA IPC */

@@ -182,6 +182,9 @@ class ShardedFastSLAM(FastSLAM):
             self._anc_window = torch.zeros((Ml,), dtype=i64, device=dev)
             self._send_capacity = max(1, (G - 1) * cap)   # one particle may own every output slot
             self._push_ws = torch.zeros((4 * self._send_capacity,), dtype=torch.int32, device=dev)
+            self._push_stream = torch.cuda.Stream(device=dev)
+            self._ev_plan = torch.cuda.Event()
+            self._ev_push = torch.cuda.Event()
             torch.cuda.synchronize(dev)
         dist.barrier(group=self._group)   # every mapping exists and every flag is zero before the first frame
 
@@ -310,13 +313,20 @@ class ShardedFastSLAM(FastSLAM):
                                             _lib.ptr(self._anc_window), _lib.ptr(self._gather_ws), st),
                        "pk_resample_plan")
             tick("resample_plan")
-            # offspring that live on other ranks: header + landmark block straight into their receive buffers
+            # offspring that live on other ranks: header + landmark block straight into their receive buffers -- on a
+            # side stream, so that they overlap the free list and the slot assignment of the gather (the copies of the
+            # local duplicates wait for them: a sender that is dead locally donates its block)
+            main = torch.cuda.current_stream(self._device)
+            side = self._push_stream
+            self._ev_plan.record(main)
+            side.wait_event(self._ev_plan)
             _lib.check(lib.pk_push_particles(_lib.ptr(self._xplan), _lib.ptr(self._out_lo), Ml, me, _lib.ptr(pose_in),
                                              _lib.ptr(aux_in), _lib.ptr(slot_in), _lib.ptr(self._pool), self.capacity,
                                              self._dt, _lib.ptr(pr["recv_tab"]), self._send_capacity,
-                                             _lib.ptr(self._push_ws), st), "pk_push_particles")
-            tick("push")
-            # the second flag barrier (every rank's pushes have landed) runs inside the first kernel of the gather
+                                             _lib.ptr(self._push_ws), side.cuda_stream), "pk_push_particles")
+            self._ev_push.record(side)
+            # the second flag barrier (every rank's pushes have landed) runs inside the gather, in front of the part
+            # that reads the receive buffer; the stream waits for this rank's own pushes before it posts its flag
             pr["epoch"] += 1
             _lib.check(lib.pk_resample_gather_peer(
                 _lib.ptr(self._xplan), _lib.ptr(self._anc_window), _lib.ptr(self._out_lo), _lib.ptr(self._offspring), Ml,
@@ -324,7 +334,7 @@ class ShardedFastSLAM(FastSLAM):
                 _lib.ptr(self._aux[nxt]), _lib.ptr(slot_in), _lib.ptr(self._slot[nxt]), pr["recv_ptr"],
                 self.exchange_capacity, _lib.ptr(self._pool), self.capacity, self._dt, _lib.ptr(self._gather_ws),
                 _lib.ptr(self._n_copied), _lib.ptr(pr["flags_tab"]), me, G, pr["epoch"], self._barrier_timeout_s,
-                status, st), "pk_resample_gather_peer")
+                status, self._ev_push.cuda_event, st), "pk_resample_gather_peer")
             tick("barrier+gather")
             self._cur = nxt
             if self.keep_trace:
