@@ -330,6 +330,10 @@ int pk_weight_scan_publish(const double* pose4, long long M, double* cumsum, dou
 int pk_peer_barrier(const unsigned long long* peer_flags_tab, int rank, int n_ranks,
                     unsigned long long epoch, double timeout_s, unsigned long long* status,
                     void* stream);
+/* First half of a split-phase barrier: post this rank's flag for `epoch` (everything the stream wrote to peer memory
+ * before is ordered in front of it); the matching wait is the one inside pk_resample_gather_peer. */
+int pk_peer_post(const unsigned long long* peer_flags_tab, int rank, int n_ranks,
+                 unsigned long long epoch, void* stream);
 /* Exchange plan of this rank from block_count (K3b output over all ranks' blocks, nb_per_rank each):
  * xplan[PK_XPLAN_LONGS] device int64.  `capacity` = records a rank may RECEIVE per frame (the size
  * of its receive buffer); a rank then sends at most (n_ranks - 1) * capacity.  Exceeding it sets
@@ -353,8 +357,9 @@ int pk_push_particles(const long long* xplan, const long long* out_lo, long long
  * this call instead of in a launch of its own, in front of the part that reads the receive buffer: the free list, the
  * slots filled from local ancestors and the copies of the local duplicates run first, while the pushes are still in
  * flight.  status: PK_PEER_STATUS_WORDS device uint64.  pushes_done_event: NULL, or a cudaEvent_t recorded after this
- * rank's pk_push_particles when that ran on ANOTHER stream (so that it overlaps the free list and the slot assignment
- * of this call); `stream` waits for it before any landmark block is overwritten and before the rank's flag is posted. */
+ * rank's pk_push_particles AND pk_peer_post(epoch) when those ran on ANOTHER stream (so that they overlap the free list
+ * and the slot assignment of this call, and the other ranks do not wait for this rank's local copies): `stream` waits
+ * for it before any landmark block is overwritten, and this call only waits for the flags. */
 int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
                             const long long* out_lo, const int* offspring, long long Ml,
                             long long particle_offset, const double* pose4_in, double* pose4_out,

@@ -166,6 +166,7 @@ SIGNATURES = {
     "pk_push_particles": (_I, [_P, _P, _LL, _I, _P, _P, _P, _P, _I, _I, _P, _LL, _P, _P]),
     "pk_resample_gather_peer": (_I, [_P, _P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _LL, _P, _I, _I,
                                      _P, _P, _P, _I, _I, _ULL, _D, _P, _P, _P]),
+    "pk_peer_post": (_I, [_P, _I, _I, _ULL, _P]),
     "pk_resample_thresholds_peer": (_I, [_P, _LL, _LL, _D, _P, _P, _P, _P, _I, _I, _ULL, _D, _LL, _LL, _P, _P, _P]),
     "pk_log_weights_max": (_I, [_P, _LL, _P, _P, _P]),
     "pk_log_weights_normalise": (_I, [_P, _LL, _P, _P, _P, _P]),

@@ -192,6 +192,7 @@ struct PeerSync {
     unsigned long long epoch, timeout_ns;
     unsigned long long* status;         // [0] sticky PK_PEER_* bits, [1 + which] nanoseconds spent waiting, [3] barriers
     int which;                          // 0: first barrier of the frame (block totals), 1: second (pushes landed)
+    bool posted;                        // the rank's flag was posted earlier (pk_peer_post): wait only
 };
 // accounting of one CTA's wait (thread 0, after the __syncthreads() that follows peer_sync_thread)
 __device__ __forceinline__ void peer_sync_account(const PeerSync& ps, unsigned long long t_entry) {
@@ -689,7 +690,17 @@ __global__ void exchange_plan_kernel(const long long* __restrict__ block_count, 
 __global__ void __launch_bounds__(PK_MAX_RANKS)
 peer_barrier_kernel(unsigned long long* const* __restrict__ peer_flags, int me, int G, unsigned long long epoch,
                     unsigned long long timeout_ns, unsigned long long* __restrict__ status) {
-    peer_sync_thread(PeerSync{peer_flags, me, G, epoch, timeout_ns, status, 0}, (int)threadIdx.x, true);
+    peer_sync_thread(PeerSync{peer_flags, me, G, epoch, timeout_ns, status, 0, false}, (int)threadIdx.x, true);
+}
+
+// First half of a split-phase barrier: post this rank's flag only (the wait sits in a later kernel, possibly of
+// another stream).
+__global__ void __launch_bounds__(PK_MAX_RANKS)
+peer_post_kernel(unsigned long long* const* __restrict__ peer_flags, int me, int G, unsigned long long epoch) {
+    const int g = (int)threadIdx.x;
+    if (g >= G) return;
+    __threadfence_system();
+    st_release_sys(peer_flags[g] + me, epoch);
 }
 
 // One thread per migrating particle.  Send item j is global output slot k (the N_BELOW run starts at
@@ -792,7 +803,7 @@ assign_sharded_kernel(int part, PeerSync ps, const long long* __restrict__ local
         // CTA 0 posts this rank's flag (its own pushes: earlier kernels of this stream, fenced), every CTA waits for
         // all ranks' flags before it reads the buffer
         const unsigned long long t_entry = global_timer_ns();
-        peer_sync_thread(ps, (int)threadIdx.x, blockIdx.x == 0);
+        peer_sync_thread(ps, (int)threadIdx.x, blockIdx.x == 0 && !ps.posted);
         __syncthreads();
         if (blockIdx.x == 0 && threadIdx.x == 0) peer_sync_account(ps, t_entry);
     }
@@ -1181,7 +1192,7 @@ int pk_resample_thresholds(const double* all_block_sums, long long nb_total, lon
     int group = kMinGroupBlocks;
     while ((long long)group * kMaxScanGroups < nb_total) group *= 2;
     thresholds_kernel<<<kThrCluster, 1024, 0, (cudaStream_t)stream>>>(all_block_sums, nb_total, M_total, u01, plan, block_prefix,
-                                                           block_count, group, PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0}, 0, 0,
+                                                           block_count, group, PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0, false}, 0, 0,
                                                            nullptr);
     PK_LAUNCH_CHECK("thresholds_kernel");
     return PK_OK;
@@ -1203,7 +1214,7 @@ int pk_resample_thresholds_peer(const double* all_block_sums, long long nb_total
     thresholds_kernel<<<kThrCluster, 1024, 0, (cudaStream_t)stream>>>(
         all_block_sums, nb_total, M_total, u01, plan, block_prefix, block_count, group,
         PeerSync{reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
-                 (unsigned long long)(timeout_s * 1e9), status, 0},
+                 (unsigned long long)(timeout_s * 1e9), status, 0, false},
         Ml, capacity, xplan);
     PK_LAUNCH_CHECK("thresholds_kernel");
     return PK_OK;
@@ -1431,7 +1442,7 @@ int pk_resample_gather_sharded(const long long* local_run, const long long* out_
     PK_CHECK_ARG(n_loc == 0 || local_run != nullptr, "local_run is NULL");
     PK_CHECK_ARG(n_loc == Ml || recv != nullptr, "receive buffer is NULL");
     PK_CHECK_ARG(dtype_valid(dtype), "dtype");
-    return gather_sharded_impl(false, PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0}, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
+    return gather_sharded_impl(false, PeerSync{nullptr, 0, 1, 0, 0, nullptr, 0, false}, local_run, nullptr, 0, out_lo, offspring, Ml, particle_offset, n_lo, n_loc, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,
                                total_dead_out, (cudaStream_t)stream);
 }
@@ -1527,6 +1538,16 @@ int pk_peer_barrier(const unsigned long long* peer_flags_tab, int rank, int n_ra
     return PK_OK;
 }
 
+int pk_peer_post(const unsigned long long* peer_flags_tab, int rank, int n_ranks, unsigned long long epoch, void* stream) {
+    PK_CHECK_ARG(peer_flags_tab != nullptr, "null pointer");
+    PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    PK_CHECK_ARG(epoch > 0, "epoch must start at 1");
+    peer_post_kernel<<<1, PK_MAX_RANKS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch);
+    PK_LAUNCH_CHECK("peer_post_kernel");
+    return PK_OK;
+}
+
 int pk_exchange_plan(const long long* block_count, long long nb_per_rank, int n_ranks, int rank, long long Ml,
                      long long capacity, long long* xplan, unsigned long long* status, void* stream) {
     PK_CHECK_ARG(block_count && xplan && status, "null pointer");
@@ -1588,7 +1609,7 @@ int pk_resample_gather_peer(const long long* xplan, const long long* anc_window,
         PK_CHECK_ARG(n_ranks >= 1 && n_ranks <= PK_MAX_RANKS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
         PK_CHECK_ARG(epoch > 0 && timeout_s > 0.0 && status != nullptr, "barrier arguments");
         sync = PeerSync{reinterpret_cast<unsigned long long* const*>(peer_flags_tab), rank, n_ranks, epoch,
-                        (unsigned long long)(timeout_s * 1e9), status, 1};
+                        (unsigned long long)(timeout_s * 1e9), status, 1, pushes_done_event != nullptr};
     }
     return gather_sharded_impl(true, sync, anc_window, xplan, recv_capacity, out_lo, offspring, Ml, particle_offset, 0, 0, pose4_in,
                                pose4_out, aux2_in, aux2_out, slot_in, slot_out, recv, pool, capacity, dtype, workspace,

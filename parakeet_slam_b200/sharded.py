@@ -324,10 +324,12 @@ class ShardedFastSLAM(FastSLAM):
                                              _lib.ptr(aux_in), _lib.ptr(slot_in), _lib.ptr(self._pool), self.capacity,
                                              self._dt, _lib.ptr(pr["recv_tab"]), self._send_capacity,
                                              _lib.ptr(self._push_ws), side.cuda_stream), "pk_push_particles")
-            self._ev_push.record(side)
-            # the second flag barrier (every rank's pushes have landed) runs inside the gather, in front of the part
-            # that reads the receive buffer; the stream waits for this rank's own pushes before it posts its flag
+            # split-phase second barrier: the flag "my pushes have landed" is posted right behind them on the side
+            # stream, the wait sits inside the gather in front of the part that reads the receive buffer -- a rank
+            # with many local duplicates to copy does not hold the others up
             pr["epoch"] += 1
+            _lib.check(lib.pk_peer_post(_lib.ptr(pr["flags_tab"]), me, G, pr["epoch"], side.cuda_stream), "pk_peer_post")
+            self._ev_push.record(side)
             _lib.check(lib.pk_resample_gather_peer(
                 _lib.ptr(self._xplan), _lib.ptr(self._anc_window), _lib.ptr(self._out_lo), _lib.ptr(self._offspring), Ml,
                 self.particle_offset, _lib.ptr(pose_in), _lib.ptr(self._pose[nxt]), _lib.ptr(aux_in),
