@@ -47,7 +47,7 @@ BLOBS = 8
 # launches per frame: motion, measure, weight_scan, thresholds, resample_plan, free_list_fused, assign,
 # copy_blocks
 KERNELS_PER_STEP = 8
-KERNELS_PER_STEP_PEER = 12   # weight_scan(+all-gather), thresholds(+barrier+plan), plan, push headers, push blocks, free list, assign (local), copy, assign (arrivals, +barrier), copy
+KERNELS_PER_STEP_PEER = 13   # weight_scan(+all-gather), thresholds(+barrier+plan), plan, push headers, push blocks, flag post, free list, assign (local), copy, assign (arrivals, +barrier wait), copy
 KERNELS_PER_STEP_NCCL = 16   # + 2 x (pack headers, pack blocks), offspring window, unpack (plus 2 NCCL collectives)
 REF_SAMPLE_PARTICLES = 16    # particles per replica of the bounded reference sample (config-2 map, 8 blobs)
 
