@@ -558,19 +558,31 @@ resample_plan_kernel(const double* __restrict__ cumsum, long long M_local, long 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long blk = blockIdx.x;
     const long long i = blk * PK_SCAN_BLOCK + t;
+    __shared__ long long s_edge[32];
     if (t == 0) s_nbig = 0;
-    __syncthreads();
     const bool in = i < M_local;
     long long klo = 0, khi = 0;
+    // N(C_i) once per particle: the start of particle i's run is the end of particle i-1's (shuffle; shared memory
+    // across warp boundaries), the block's first run starts at the block's emitted-output count
+    long long c_lo = 0, c_hi = 0, raw = 0;
+    bool last = false;
     if (in) {
         const double r = plan[1], u0 = plan[2];
         const long long b = block_offset + blk;
         const dd P{block_prefix[2 * b], block_prefix[2 * b + 1]};
-        const long long c_lo = block_count[b], c_hi = block_count[b + 1];
+        c_lo = block_count[b];
+        c_hi = block_count[b + 1];
+        last = (t == PK_SCAN_BLOCK - 1) || (particle_offset + i == M_total - 1);
+        raw = min(max(count_le(P, cumsum[i], u0, r, M_total), c_lo), c_hi);
+    }
+    if (lane == 31) s_edge[warp] = raw;
+    __syncthreads();
+    long long prev = __shfl_up_sync(kFullMask, raw, 1);
+    if (lane == 0 && warp > 0) prev = s_edge[warp - 1];
+    if (in) {
         const long long gi = particle_offset + i;
-        const bool last = (t == PK_SCAN_BLOCK - 1) || (gi == M_total - 1);
-        long long hi = last ? c_hi : min(max(count_le(P, cumsum[i], u0, r, M_total), c_lo), c_hi);
-        long long lo = (t == 0) ? c_lo : min(max(count_le(P, cumsum[i - 1], u0, r, M_total), c_lo), c_hi);
+        long long hi = last ? c_hi : raw;
+        const long long lo = (t == 0) ? c_lo : prev;
         if (hi < lo) hi = lo;
         out_lo[i] = lo;
         offspring[i] = (int)(hi - lo);
