@@ -270,6 +270,12 @@ int pk_resample_gather_planned(const long long* ancestors, long long M, const do
                                double* pose4_out, const int* aux2_in, int* aux2_out,
                                const int* slot_in, int* slot_out, void* pool, int capacity, int dtype,
                                void* workspace, long long* n_copied_out, void* stream);
+/* The block copies of pk_resample_gather_planned on their own: call that function with capacity = 0 (free list and
+ * permutation only, two launches) and this one with the real capacity on ANOTHER stream, ordered after it by an event.
+ * Nothing but the landmark pool is touched here, so the next frame's motion update (poses only) can run beside the copies;
+ * whatever reads or writes the pool next must wait for `stream`.  Replaces the same deepcopy (prkt_core_v2.py:243). */
+int pk_resample_copy_blocks(void* pool, int capacity, int dtype, long long M, void* workspace,
+                            const long long* n_copied, void* stream);
 /* Single-GPU form.  ancestors[M] ascending (int64, local indices).  Survivors keep their landmark
  * block; every extra copy of a particle is written into the block of a particle that died
  * (#copies == #dead).  pose/aux are permuted out of place.  n_copied_out (device int64) receives

@@ -148,6 +148,7 @@ SIGNATURES = {
     "pk_resample_plan": (_I, [_P, _LL, _LL, _LL, _P, _P, _P, _LL, _LL, _LL, _P, _P, _P, _P, _P]),
     "pk_gather_workspace_bytes": (_LL, [_LL]),
     "pk_resample_gather_planned": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "pk_resample_copy_blocks": (_I, [_P, _I, _I, _LL, _P, _P, _P]),
     "pk_resample_gather": (_I, [_P, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "pk_particle_record_bytes": (_LL, [_I, _I]),
     "pk_pack_particles": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -291,13 +291,14 @@ class FastSLAM(object):
     def __init__(self, preset_features=[], *, num_particles=50, capacity=None, dtype="f64",
                  device=None, noise="numpy", seed=0, uniform=None, clock=None, params=None,
                  spawn=False, orphan_capacity=32, pair_gate=300.0 ** 0.5, arithmetic="f64", publish_particles=0,
-                 measurement_model="reference", weights="linear"):
+                 measurement_model="reference", weights="linear", overlap_copy=True):
         import torch
 
         _lib.require_device()
         self._torch = torch
         self._lib = _lib.load()
         self._lock = threading.RLock()
+        self._overlap_copy = bool(overlap_copy)
         self._clock = clock if clock is not None else _ros_now
         self._device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
 
@@ -373,7 +374,12 @@ class FastSLAM(object):
         self._aux = [torch.zeros((M, 2), dtype=i32, device=dev) for _ in range(2)]
         self._slot = [torch.zeros((M,), dtype=i32, device=dev) for _ in range(2)]
         self._cur = 0
-        self._pool = torch.zeros((max(1, M * self.block_bytes),), dtype=torch.uint8, device=dev)
+        self._pool_t = torch.zeros((max(1, M * self.block_bytes),), dtype=torch.uint8, device=dev)
+        # copy-on-resample runs on its own stream beside the next frame's motion update (see low_variance_resample)
+        self._copy_stream = torch.cuda.Stream(device=dev) if self._overlap_copy else None
+        self._ev_permuted = torch.cuda.Event()
+        self._ev_blocks = torch.cuda.Event()
+        self._blocks_pending = False
         nb = int(lib.pk_num_scan_blocks(max(M, 1)))
         self._nb = nb
         self._cumsum = torch.zeros((max(M, 1),), dtype=f64, device=dev)
@@ -409,6 +415,27 @@ class FastSLAM(object):
         if torch.cuda.current_device() == self._device.index:
             return _NULL_CTX
         return torch.cuda.device(self._device)
+
+    @property
+    def _pool(self):
+        """The landmark pool.  Every access first orders the current stream behind block copies of the last resampling
+        that may still be running on the copy stream, so no reader or writer of the pool can overtake them."""
+        self.wait_blocks()
+        return self._pool_t
+
+    def __del__(self):
+        # block copies still running on the copy stream must not outlive the pool they write into
+        try:
+            if getattr(self, "_blocks_pending", False):
+                self._ev_blocks.synchronize()
+        except Exception:
+            pass
+
+    def wait_blocks(self):
+        """Make the current stream wait for the block copies of the last resampling (no-op when none are pending)."""
+        if self._blocks_pending:
+            self._torch.cuda.current_stream(self._device).wait_event(self._ev_blocks)
+            self._blocks_pending = False
 
     @property
     def pose(self):
@@ -624,6 +651,7 @@ class FastSLAM(object):
             u01 = float(self._uniform())
             st = self._stream()
             cur, nxt = self._cur, 1 - self._cur
+            self.wait_blocks()  # two resamplings in a row: the copy lists in the workspace are still being read
             if self.weights == "log":
                 self._normalise_log_weights()
             _lib.check(lib.pk_weight_scan(_lib.ptr(self._pose[cur]), M, _lib.ptr(self._cumsum),
@@ -637,13 +665,27 @@ class FastSLAM(object):
                                             _lib.ptr(self._out_lo), _lib.ptr(self._offspring),
                                             _lib.ptr(self._ancestors), _lib.ptr(self._gather_ws), st),
                        "pk_resample_plan")
+            overlap = self._copy_stream is not None and self.capacity > 0
             _lib.check(lib.pk_resample_gather_planned(_lib.ptr(self._ancestors), M,
                                                       _lib.ptr(self._pose[cur]), _lib.ptr(self._pose[nxt]),
                                                       _lib.ptr(self._aux[cur]), _lib.ptr(self._aux[nxt]),
                                                       _lib.ptr(self._slot[cur]), _lib.ptr(self._slot[nxt]),
-                                                      _lib.ptr(self._pool), self.capacity, self._dt,
+                                                      _lib.ptr(self._pool_t), 0 if overlap else self.capacity, self._dt,
                                                       _lib.ptr(self._gather_ws), _lib.ptr(self._n_copied), st),
                        "pk_resample_gather_planned")
+            if overlap:
+                # The block copies (deepcopy :243) touch nothing but the landmark pool: they go to the copy stream,
+                # ordered behind the permutation, and the next frame's motion update (poses only, bound by its fp64
+                # arithmetic) runs beside them (bound by HBM).  Whatever touches the pool next waits: `_pool`.
+                main = torch.cuda.current_stream(self._device)
+                self._ev_permuted.record(main)
+                self._copy_stream.wait_event(self._ev_permuted)
+                _lib.check(lib.pk_resample_copy_blocks(_lib.ptr(self._pool_t), self.capacity, self._dt, M,
+                                                       _lib.ptr(self._gather_ws), _lib.ptr(self._n_copied),
+                                                       ctypes.c_void_p(self._copy_stream.cuda_stream)),
+                           "pk_resample_copy_blocks")
+                self._ev_blocks.record(self._copy_stream)
+                self._blocks_pending = True
             self._cur = nxt
             if self.keep_trace:
                 self.last_ancestors = self._ancestors.clone()

@@ -448,6 +448,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// sum of the absolute differences of the four byte lanes, plus c (one VABSDIFF4.U8.ACC)
+__device__ __forceinline__ unsigned vsad4_acc(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ int4 lds16_a(uint32_t addr) {
     int4 v;
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

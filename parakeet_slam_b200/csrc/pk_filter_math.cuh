@@ -214,7 +214,8 @@ __device__ __forceinline__ float pk_wrap_pi(float a) {
 __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double py, double beta, double orr, double og,
                                                 double ob, const pk_params& prm, int& id_out, unsigned& flags,
                                                 int& promoted, bool& changed_out, bool have_zb = false,
-                                                double zb_in = 0.0, double pth = 0.0) {
+                                                double zb_in = 0.0, double pth = 0.0, bool have_log_nm = false,
+                                                double log_nm = 0.0) {
     id_out = L.id;
     const double qt = prm.qt_diag;
     // measurement_jacobian :785-797 (sign and order as written, finding F4b)
@@ -302,7 +303,8 @@ __device__ __forceinline__ double ekf_update_lm(Landmark& L, double px, double p
     }
     if (id_out < 0) {
         // potential feature :109-118: weight as if unseen; promote when update_count > 5
-        factor = log_w ? log(prm.no_match_weight) : prm.no_match_weight;
+        // (K2 passes log(no_match_weight) in: an fp64 log set up inside its main loop costs every group)
+        factor = log_w ? (have_log_nm ? log_nm : log(prm.no_match_weight)) : prm.no_match_weight;
         if (L.meta & PK_META_POTENTIAL) {
             if ((L.meta & PK_META_COUNT_MASK) > prm.promote_count) {
                 L.meta &= ~PK_META_POTENTIAL;
@@ -420,7 +422,8 @@ __device__ __forceinline__ float match_likelihood(const LandmarkF& L, double px,
 
 __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double py, float beta, float orr, float og, float ob,
                                                 const pk_params& prm, int& id_out, unsigned& flags, int& promoted,
-                                                bool& changed_out, bool have_zb = false, float zb_in = 0.0f, double pth = 0.0) {
+                                                bool& changed_out, bool have_zb = false, float zb_in = 0.0f, double pth = 0.0,
+                                                bool have_log_nm = false, double log_nm = 0.0) {
     id_out = L.id;
     const float qt = (float)prm.qt_diag;
     const float dx = (float)((double)L.x - px), dy = (float)((double)L.y - py);
@@ -494,7 +497,8 @@ __device__ __forceinline__ double ekf_update_lm(LandmarkF& L, double px, double 
         changed = true;
     }
     if (id_out < 0) {
-        factor = log_w ? log(prm.no_match_weight) : prm.no_match_weight;
+        // (K2 passes log(no_match_weight) in: an fp64 log set up inside its main loop costs every group)
+        factor = log_w ? (have_log_nm ? log_nm : log(prm.no_match_weight)) : prm.no_match_weight;
         if (L.meta & PK_META_POTENTIAL) {
             if ((L.meta & PK_META_COUNT_MASK) > prm.promote_count) {
                 L.meta &= ~PK_META_POTENTIAL;

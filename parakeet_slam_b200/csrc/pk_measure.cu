@@ -68,12 +68,14 @@ struct MeasureArgs {
     int* assoc;
     unsigned long long* stats;
     int M;            // particles of this launch (< 2^31: all group / particle indices are 32-bit)
-    size_t block_bytes;
+    unsigned block_bytes;  // < 2^32 (capacity < 2^16): slot * block_bytes is one 32 x 32 -> 64-bit multiply-add
     unsigned hot_bytes;  // hot_region_bytes(capacity): offset of the cold region inside a block
     int capacity;
     int K;
     int group;        // particles per warp group
     int key_thr;      // squared byte-distance bound of the colour screen
+    int key_thr1;     // the same bound as a sum of absolute byte differences (contains the squared one)
+    double log_no_match;  // log(prm.no_match_weight) (PK_MODEL_LOG_WEIGHTS)
     int warp_smem;    // bytes of shared memory per warp
     int keys_off;     // offset of the key ring inside a warp's shared memory
     int rec_off;      // offset of the record staging area
@@ -83,7 +85,7 @@ struct MeasureArgs {
 };
 
 // fixed part of a warp's shared memory; the key ring [kStages][group][kKeyStride] and the record
-// staging area [kStaged][32 * R] follow at keys_off / rec_off
+// staging area [strips][32 * R] follow at keys_off / rec_off
 template <int R>
 struct alignas(128) WarpSmemT {
     static constexpr int kItems = 32 * R;
@@ -104,6 +106,21 @@ template <typename T, typename LM = Landmark>
 __host__ __device__ constexpr int staged_candidates() {
     return sizeof(LM) == sizeof(LandmarkF) ? PK_STAGED_F32 : (sizeof(typename Rec<T>::Cold) <= 64 ? 2 : 1);
 }
+// Third and later candidates of an item (colour-ambiguous maps, duplicate landmarks of the spawning pipeline): their
+// records are requested two candidates ahead with per-lane cp.async copies into a ring of three strips -- candidate c
+// lives in strip c % 3, entry = item -- instead of being loaded synchronously when their turn comes, so the exact
+// evaluations of candidates c and c + 1 hide the DRAM latency of candidate c + 2.  (64-byte records only.)
+#ifndef PK_CLOOP_PREFETCH
+#define PK_CLOOP_PREFETCH 1
+#endif
+template <typename T, typename LM = Landmark>
+__host__ __device__ constexpr bool candidate_ring() {
+    return PK_CLOOP_PREFETCH != 0 && staged_candidates<T, LM>() == 2;
+}
+template <typename T, typename LM = Landmark>
+__host__ __device__ constexpr int staging_strips() {
+    return candidate_ring<T, LM>() ? 3 : staged_candidates<T, LM>();
+}
 
 // per-item screen result, kept in registers between screen(g) and evaluate(g)
 struct Hits {
@@ -114,23 +131,37 @@ struct Hits {
 // LM selects the arithmetic of the landmark algebra: Landmark (fp64, every instantiation that must reproduce the
 // reference) or LandmarkF (fp32 on fp32 storage, PK_DTYPE_ARITH_F32)
 // record prefetch of an item's first hit: 1 = the warp fetches the 32-record strip together, 0 = every lane its own
+// colour screen: 1 = sum of absolute byte differences (two instructions per key), 0 = squared distance (three)
+#ifndef PK_SCREEN_SAD
+#define PK_SCREEN_SAD 1
+#endif
 #ifndef PK_COOP_PREFETCH
 #define PK_COOP_PREFETCH 1
 #endif
 #ifndef PK_MEASURE_MINB_F32
 #define PK_MEASURE_MINB_F32 8
 #endif
-template <typename LM> struct ArithOf { using S = double; using Pre = MatchPre; static constexpr int kMinB = PK_MEASURE_MINB; };
-template <> struct ArithOf<LandmarkF> { using S = float; using Pre = MatchPreF; static constexpr int kMinB = PK_MEASURE_MINB_F32; };
+// PK_K2_REGCAP_F32 > 0: cap the fp32-algebra kernel's registers directly (__maxnreg__) instead of through the
+// minimum-CTAs bound; the occupancy query at launch then decides how many CTAs are resident
+#ifndef PK_K2_REGCAP_F32
+#define PK_K2_REGCAP_F32 0
+#endif
+template <typename LM> struct ArithOf { using S = double; using Pre = MatchPre; static constexpr int kMinB = PK_MEASURE_MINB; static constexpr int kMaxReg = 168; };
+template <> struct ArithOf<LandmarkF> { using S = float; using Pre = MatchPreF; static constexpr int kMinB = PK_MEASURE_MINB_F32; static constexpr int kMaxReg = PK_K2_REGCAP_F32 > 0 ? PK_K2_REGCAP_F32 : 128; };
 
 template <typename T, int R, typename LM>
+#if PK_K2_REGCAP_F32 > 0
+__global__ void __maxnreg__(ArithOf<LM>::kMaxReg)
+#else
 __global__ void __launch_bounds__(kWarpsPerCta * 32, ArithOf<LM>::kMinB)
+#endif
 measure_kernel(const __grid_constant__ MeasureArgs A) {
     using Cold = typename Rec<T>::Cold;
     using S_t = typename ArithOf<LM>::S;
     using Pre_t = typename ArithOf<LM>::Pre;
     constexpr unsigned kRecBytes = (unsigned)sizeof(Cold);
     constexpr int kStaged = staged_candidates<T, LM>();  // candidates per item prefetched into shared memory
+    constexpr bool kRing = candidate_ring<T, LM>();      // later candidates travel through a ring of three strips
     constexpr int kChunksPerRec = (int)(kRecBytes / 16u);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,7 +170,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     WarpSmem& S = *reinterpret_cast<WarpSmem*>(wbase);
     const uint32_t s_base = smem_u32(wbase);
     const uint32_t s_keys = s_base + (uint32_t)A.keys_off;  // [kStages][GP][kKeyStride] words
-    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [kStaged][32 * R] Cold
+    const uint32_t s_rec = s_base + (uint32_t)A.rec_off;    // [staging_strips][32 * R] Cold
     const uint32_t s_pose = smem_u32(&S.pose[0][0][0]);
     const unsigned lt = lanemask_lt();
 
@@ -151,6 +182,9 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     const int gw = (int)blockIdx.x * kWarpsPerCta + warp;
     const int my_groups = (gw < n_groups) ? (n_groups - gw + total_warps - 1) / total_warps : 0;
     const unsigned hot = A.hot_bytes;
+    const unsigned bb = A.block_bytes;
+    // byte offset of a landmark block inside the pool (slots are non-negative)
+    auto blk_off = [bb](int sl) -> size_t { return (size_t)((unsigned long long)(unsigned)sl * (unsigned long long)bb); };
 
     const ObsTable* OT = A.tab_dev ? A.tab_dev : &A.tab;
     // two blobs of this frame may hit the same landmark only if their colours are close (ObsTable::twins); when no
@@ -158,7 +192,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
     const bool twins = OT->twins != 0u;
     // PK_MODEL_LOG_WEIGHTS: importance factors and particle weights are carried as logarithms
     const bool log_w = (A.prm.model & PK_MODEL_LOG_WEIGHTS) != 0;
-    const double log_no_match = log(A.prm.no_match_weight);
+    const double log_no_match = A.log_no_match;  // computed by the host: nothing of an fp64 log inside the main loop
     // this lane's items: item w = r * 32 + lane -> (particle pl, blob k) within a group
     int it_pl[R], it_k[R];
     unsigned it_key[R];
@@ -237,7 +271,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 const int nl = __shfl_sync(kFull, op_nlive, pl);
                 const int sl = __shfl_sync(kFull, op_slot, pl);
                 if (pl0 + kc_pl < GP && first_key < nl)
-                    cp_async16_line(dst0 + (unsigned)pl0 * (kKeyStride * 4u), kc_src + (size_t)sl * A.block_bytes + (size_t)(p_step * kChunk * 4));
+                    cp_async16_line(dst0 + (unsigned)pl0 * (kKeyStride * 4u), kc_src + blk_off(sl) + (unsigned)(p_step * kChunk * 4));
             }
             ++p_cnt;
             if (++p_step >= p_ns) {
@@ -280,10 +314,20 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 const int nl = my_nl[r] - step * kChunk;  // keys of this chunk that are live (<= 0: none)
                 const uint32_t kp = s_keys + ((stage * (unsigned)GP + (unsigned)pl) * kKeyStride) * 4u;
                 const unsigned mykey = it_key[r];
+#if PK_SCREEN_SAD
+                // two integer instructions per key: the sum of the absolute byte differences accumulated onto
+                // -(bound + 1) in ONE instruction (VABSDIFF4.U8.ACC; negative <=> inside the bound) and a funnel
+                // shift that pushes the sign bit into the hit mask (key i of a 32-key half ends up at bit 31 - i:
+                // reversed afterwards).  The L1 bound floor(sqrt(3 * key_thr)) contains the squared-distance bound
+                // (Cauchy-Schwarz over the three channels), which contains the reference's gate; its extra false
+                // positives (0.18 instead of 0.11 per item at 64 random colours) fail the exact gate later.
+                const unsigned neg_thr1 = (unsigned)(-(A.key_thr1 + 1));
+#else
                 // three integer instructions per key: |difference| per byte, dot product accumulated onto
                 // -(threshold + 1) (negative <=> inside the bound), and a funnel shift that pushes the sign bit
                 // into the hit mask (key i of a 32-key half ends up at bit 31 - i: reversed afterwards)
                 const unsigned neg_thr1 = (unsigned)(-(key_thr + 1));
+#endif
                 unsigned lo = 0u, hi = 0u;
 #pragma unroll
                 for (int q = 0; q < kChunk / 4; ++q) {
@@ -291,8 +335,12 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     const unsigned kk[4] = {(unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
+#if PK_SCREEN_SAD
+                        const unsigned sgn = vsad4_acc(kk[e], mykey, neg_thr1);
+#else
                         const unsigned d = __vabsdiffu4(kk[e], mykey);
                         const unsigned sgn = __dp4a(d, d, neg_thr1);
+#endif
                         if (4 * q + e < 32) lo = __funnelshift_l(sgn, lo, 1); else hi = __funnelshift_l(sgn, hi, 1);
                     }
                 }
@@ -307,11 +355,12 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                 const unsigned mlo2 = mlo & (mlo - 1u), mhi2 = mlo ? mhi : (mhi & (mhi - 1u));
                 const int j1 = base + (mlo2 ? __ffs((int)mlo2) - 1 : 31 + __ffs((int)mhi2));
                 const int c_before = H[r].cnt;
-                if (c_before == 0) {
-                    if (n > 0) H[r].c0 = j0;
-                    if (n > 1) H[r].c1 = j1;
-                } else if (c_before == 1) {
-                    if (n > 0) H[r].c1 = j0;
+                if (step == 0) {  // warp-uniform; the only step of maps up to 64 landmarks
+                    H[r].c0 = n > 0 ? j0 : -1;
+                    H[r].c1 = n > 1 ? j1 : -1;
+                } else {  // selects, not branches: c_before differs from lane to lane
+                    H[r].c1 = (c_before == 0 && n > 1) ? j1 : ((c_before == 1 && n > 0) ? j0 : H[r].c1);
+                    H[r].c0 = (c_before == 0 && n > 0) ? j0 : H[r].c0;
                 }
                 H[r].cnt = c_before + n;
                 if (__any_sync(kFull, c_before + n > 2)) {
@@ -350,7 +399,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
         // travels between lanes as ONE 32-bit word: its offset inside the pool in units of 32 bytes.
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const size_t rec0 = (size_t)my_slot[r] * A.block_bytes + hot;
+            const size_t rec0 = blk_off(my_slot[r]) + hot;
 #if PK_COOP_PREFETCH
             {
                 const bool have = H[r].cnt > 0;
@@ -405,7 +454,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const int w = r * 32 + lane;
             const bool act = w < nitems;
             const int pl = act ? it_pl[r] : 0;
-            const unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
+            const unsigned char* block = A.pool + blk_off(S.slot_s[gi][pl]);
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
             const int cnt = act ? H[r].cnt : 0;
             // match_one :353-381: arg-max, strict '>' from 0.0, first (lowest slot) maximum wins
@@ -454,21 +503,41 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             // candidate record: its own registers when L must keep the best one so far (kKeepWinner), else L itself
             LM Lc_own;
             LM& Lc = kKeepWinner ? Lc_own : L;
+            // candidate ring: request candidate c (>= 2) of this lane's item into strip c % 3.  Strip 0 is free (the
+            // first hit is in registers), strip 1 holds the second hit, strip 2 is the ring's own.  Every call commits
+            // exactly one cp.async group, so `wait_group 1` in iteration c leaves only candidate c + 1 in flight.
+            auto ring_fetch = [&](int c) {
+                if (c < ncand) {
+                    const unsigned char* src = block + hot + (size_t)S.more_hits[par][w][c - 2] * kRecBytes;
+                    const uint32_t dst = s_rec + ((unsigned)(c % 3) * 32u * R + (unsigned)w) * kRecBytes;
+#pragma unroll
+                    for (int i = 0; i < kChunksPerRec; ++i) cp_async16_a(dst + 16u * i, src + 16 * i);
+                }
+                cp_async_commit();
+            };
+            if (kRing && maxcnt > 2) {
+                ring_fetch(2);
+                ring_fetch(3);
+            }
             for (int c = 1; c < maxcnt; ++c) {
                 // Most extra hits are false positives of the byte-key screen: apply the exact colour
                 // gate (:441) first and run the full likelihood only if some lane still needs it.
                 bool need = false;
                 int j = -1;
+                if (kRing && c >= 2) cp_async_wait<1>();  // candidate c has landed (own copies: no warp barrier needed)
                 if (c < ncand) {
                     j = (c == 1) ? H[r].c1 : (int)S.more_hits[par][w][c - 2];
                     if (c < kStaged)
                         load_staged<T>(s_rec + ((unsigned)c * 32u * R + (unsigned)w) * kRecBytes, Lc);
+                    else if (kRing)
+                        load_staged<T>(s_rec + ((unsigned)(c % 3) * 32u * R + (unsigned)w) * kRecBytes, Lc);
                     else
                         load_landmark<T>(block, cap, j, Lc);
                     if (!kKeepWinner) L_j = j;
                     const S_t dr = ob_r[r] - Lc.r, dg = ob_g[r] - Lc.g, db = ob_b[r] - Lc.b;
                     need = !(fabs((double)(dr * dr + dg * dg + db * db)) > A.prm.color_gate);
                 }
+                if (kRing && c >= 2) ring_fetch(c + 2);  // into the strip candidate c - 1 has left
                 if (!__any_sync(kFull, need)) continue;
                 st_eval += __popc(__ballot_sync(kFull, need));
                 if (need) {
@@ -534,7 +603,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
             const int w = r * 32 + lane;
             const bool act = w < nitems;
             const int pl = act ? it_pl[r] : 0;
-            unsigned char* block = A.pool + (size_t)S.slot_s[gi][pl] * A.block_bytes;
+            unsigned char* block = A.pool + blk_off(S.slot_s[gi][pl]);
             const double px = S.pose[gi][pl][0], py = S.pose[gi][pl][1], pth = S.pose[gi][pl][2];
             const bool matched = act && bestj[r] >= 0;
             // items on the same landmark of the same particle go one after the other (finding F2); that can
@@ -563,7 +632,7 @@ measure_kernel(const __grid_constant__ MeasureArgs A) {
                     // the bearing computed during association is that of the PRE-update landmark: it is re-used
                     // unless an earlier blob of this frame has moved the landmark since
                     factor = ekf_update_lm(L, px, py, ob_beta[r], ob_r[r], ob_g[r], ob_b[r], A.prm, id_out, st_flags,
-                                           promoted, changed, !stale, best_pse[r], pth);
+                                           promoted, changed, !stale, best_pse[r], pth, true, log_no_match);
                     if (changed) store_landmark<T>(block, cap, bestj[r], L, key_before);
                 }
                 if (q >= maxrank) break;
@@ -668,7 +737,7 @@ static int launch_measure(MeasureArgs& args, cudaStream_t st) {
     auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     args.keys_off = (int)align128(sizeof(WarpSmemT<R>));
     args.rec_off = (int)align128(args.keys_off + (size_t)kStages * args.group * kKeyStride * 4);
-    args.warp_smem = (int)align128(args.rec_off + (size_t)staged_candidates<T, LM>() * 32 * R * sizeof(typename Rec<T>::Cold));
+    args.warp_smem = (int)align128(args.rec_off + (size_t)staging_strips<T, LM>() * 32 * R * sizeof(typename Rec<T>::Cold));
     const size_t smem = (size_t)args.warp_smem * kWarpsPerCta;
     // the attribute is per device (a process may run filters on several): set it on every launch, it is cheap
     if (smem > 48 * 1024)
@@ -759,7 +828,7 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     args.assoc = assoc;
     args.stats = stats;
     args.M = (int)M;
-    args.block_bytes = block_bytes(capacity, dtype);
+    args.block_bytes = (unsigned)block_bytes(capacity, dtype);
     args.hot_bytes = (unsigned)hot_region_bytes(capacity);
     args.capacity = capacity;
     args.K = K;
@@ -768,6 +837,7 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     if (group > kMaxGroup) group = kMaxGroup;
     args.group = group;
     args.prm = *params;
+    args.log_no_match = log(params->no_match_weight);
     args.tab_dev = nullptr;
     if (obs_dev != nullptr) {
         PK_CHECK_ARG(table_ws != nullptr, "table workspace is NULL");
@@ -811,6 +881,14 @@ static int measurement_common(double* pose4, int* aux2, const int* slot, void* p
     if (g >= 0.0) bound = floor(g + 2.0 * sqrt(3.0 * g) + 3.0) + 1.0;
     if (!(g == g)) bound = 2.0e9;  // NaN gate: `abs(cd) > nan` is False, everything passes
     args.key_thr = (int)(bound > 2.0e9 ? 2.0e9 : bound);
+    // sum |d| <= sqrt(3 * sum d^2): the largest integer t with t^2 <= 3 * key_thr (-1: nothing passes)
+    {
+        const long long three = 3ll * (long long)args.key_thr;
+        long long t = three < 0 ? -1 : (long long)floor(sqrt((double)three));
+        while (three >= 0 && (t + 1) * (t + 1) <= three) ++t;
+        while (t >= 0 && t * t > three) --t;
+        args.key_thr1 = (int)t;
+    }
     if (dtype_arith_f32(dtype)) return dispatch_measure<float, LandmarkF>(args, st);
     if (dtype_base(dtype) == PK_DTYPE_F32) return dispatch_measure<float, Landmark>(args, st);
     return dispatch_measure<double, Landmark>(args, st);

@@ -1348,6 +1348,17 @@ int pk_resample_gather_planned(const long long* ancestors, long long M, const do
     return PK_OK;
 }
 
+int pk_resample_copy_blocks(void* pool, int capacity, int dtype, long long M, void* workspace,
+                            const long long* n_copied, void* stream) {
+    PK_CHECK_ARG(pool && workspace && n_copied, "null pointer");
+    PK_CHECK_ARG(M > 0 && M < (1ll << 31), "M");
+    PK_CHECK_ARG(dtype_valid(dtype), "dtype");
+    if (capacity <= 0) return PK_OK;
+    GatherWs g = carve(workspace, M);
+    return copy_blocks_launch(pool, pool, capacity, dtype, g.copy_src, g.copy_dst, g.copy_nlive, M, n_copied,
+                              (cudaStream_t)stream);
+}
+
 long long pk_particle_record_bytes(int capacity, int dtype) {
     return (long long)kHeaderBytes + (long long)block_bytes(capacity, dtype);
 }

@@ -8,7 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _make(M, N, dtype, frames, noise="philox", arithmetic="f64", **kw):
+def _make(M, N, dtype, frames, noise="philox", arithmetic="f64", fs_kw={}, **kw):
     from device_harness import make_features
     from parakeet_slam_b200.core import FastSLAM
     from parakeet_slam_b200.rosless import Time, messages
@@ -23,7 +23,7 @@ def _make(M, N, dtype, frames, noise="philox", arithmetic="f64", **kw):
     clk = Clk()
     urng = random.Random(4)
     fs = FastSLAM(make_features(scn), num_particles=M, dtype=dtype, noise=noise, seed=11, uniform=urng.random, clock=clk,
-                  arithmetic=arithmetic)
+                  arithmetic=arithmetic, **fs_kw)
     tw = messages.Twist()
     tw.linear.x, tw.angular.z = scn.v, scn.w
     fs.last_control = tw
@@ -476,3 +476,38 @@ def test_blob_counts_f32_arithmetic(K):
             big = wgt > 1e-300
             assert np.max(np.abs(w[big] - wgt[big]) / wgt[big]) < 1e-3
     assert min(m for m, _ in match) >= 0.90 and min(r for _, r in match) >= 0.90, match
+
+
+def test_block_copies_on_the_copy_stream_change_nothing():
+    """copy-on-resample (deepcopy, prkt_core_v2.py:243) runs on the filter's copy stream beside the next frame's motion
+    update: the state must be bit-identical to the single-stream order, also when the pool is read straight after a
+    resampling, when two resamplings follow each other, and when weights are degenerate (most blocks copied)."""
+    import torch
+    from parakeet_slam_b200.scenario import DT_NSEC
+    M, N, T = 1 << 16, 64, 12
+    runs = []
+    for overlap in (True, False):
+        scn, fs, clk, tw = _make(M, N, "f32", T, arithmetic="f32", fs_kw=dict(overlap_copy=overlap))
+        assert (fs._copy_stream is not None) == overlap
+        snaps = []
+        for t in range(T):
+            clk.ns += DT_NSEC
+            fs.motion_update(tw)
+            fs.measurement_update(scn.observations[t])
+            if t % 4 == 3:   # degenerate weights: every 16th particle survives, 15/16 of the blocks are copied
+                fs.pose[:, 3] = torch.where(torch.arange(M, device="cuda") % 16 == 0, 1.0, 0.0).to(torch.float64)
+            fs.low_variance_resample()
+            if t == 5:
+                fs.low_variance_resample()   # twice in a row: the second must not overtake the first one's copies
+            if t in (3, 5, T - 1):           # read the pool right behind the resampling
+                snaps.append([a.copy() for a in fs.export_maps(0, 4096)])
+        torch.cuda.synchronize()
+        runs.append((fs.pose.cpu().numpy(), fs.slot.cpu().numpy(), fs.aux.cpu().numpy(), fs._pool.cpu().numpy(), snaps,
+                     fs.stats()))
+    a, b = runs
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    for sa, sb in zip(a[4], b[4]):
+        for x, y in zip(sa, sb):
+            assert np.array_equal(x, y)
+    assert a[5] == b[5]

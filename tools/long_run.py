@@ -99,12 +99,14 @@ def main(argv=None):
             e[0].record()
         fs.motion_update(tw)
         if sampled:
+            fs.wait_blocks()   # the previous frame's block copies (copy stream) stay out of K2's interval
             e[1].record()
         fs.measurement_update(scan)                    # K2 + K2b, scan resident on the device
         if sampled:
             e[2].record()
         fs.low_variance_resample()
         if sampled:
+            fs.wait_blocks()   # sampled frames time the whole resampling chain, copies included
             e[3].record()
             samples.append(e)
             st = fs.stats()                            # (synchronises; only on sampled frames)
