@@ -890,6 +890,9 @@ assign_sharded_kernel(int part, PeerSync ps, const long long* __restrict__ local
 constexpr int kCopyBufs = 4;
 constexpr int kCopyChunk = 4096;
 
+#ifndef PK_COPY_META_CACHE
+#define PK_COPY_META_CACHE 1
+#endif
 __global__ void __launch_bounds__(32)
 copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __restrict__ dst_base, long long src_stride,
                    long long dst_stride, int hot_b, int cold_b, int capacity, const int* __restrict__ src_slot, const int* __restrict__ dst_slot,
@@ -898,22 +901,67 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
                    const long long* __restrict__ skip_flag, long long orph_off, int orph_len) {
     __shared__ __align__(128) unsigned char buf[kCopyBufs][kCopyChunk];
     __shared__ uint64_t bar[kCopyBufs];
-    if (threadIdx.x != 0) return;
+    // The copy list of this CTA's items (source slot, destination slot / rank, live landmarks), 64 items at a time:
+    // the lanes that do not drive the bulk copies fetch it 32 items ahead, so the driving lane never waits for a
+    // dependent global load between two chunks (with 4 KB blocks that wait was as long as the copy itself).
+    __shared__ int m_src[64], m_dst[64], m_nl[64], m_rank[64];
+    const int lane = threadIdx.x;
+#if !PK_COPY_META_CACHE
+    if (lane != 0) return;
+#endif
     if (skip_flag != nullptr && *skip_flag != 0) return;  // exchange overflow: the frame's copies are void
     long long n = n_dev ? *n_dev : n_max;
     if (n > n_max) n = n_max;
-    for (int b = 0; b < kCopyBufs; ++b) mbar_init(&bar[b], 1);
-    mbar_fence_init();
+    if (lane == 0) {
+        for (int b = 0; b < kCopyBufs; ++b) mbar_init(&bar[b], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const long long stride = gridDim.x;
+    const long long first = blockIdx.x;
+    const long long n_mine = first < n ? (n - first + stride - 1) / stride : 0;  // items of this CTA: first + k * stride
 
-    // chunk stream state: issue side (li_*) and drain side (ld_*)
+#if PK_COPY_META_CACHE
+    long long cached = 0;  // items [0, cached) of this CTA have been fetched (ring of 64: the last two batches are valid)
+    auto ensure = [&](long long k) {  // warp-uniform
+        while (k >= cached && cached < n_mine) {
+            const long long kk = cached + lane;
+            if (kk < n_mine) {
+                const long long item = first + kk * stride;
+                const int e = (int)(kk & 63);
+                m_src[e] = src_slot[item];
+                m_dst[e] = dst_slot[item];
+                m_nl[e] = nlive ? min(nlive[item], capacity) : capacity;
+                m_rank[e] = dst_tab ? dst_rank[item] : 0;
+            }
+            cached += 32;
+            __syncwarp();
+        }
+    };
+    auto src_of = [&](long long k) { return m_src[k & 63]; };
+    auto dst_of = [&](long long k) { return m_dst[k & 63]; };
+    auto nl_of = [&](long long k) { return m_nl[k & 63]; };
+    auto rank_of = [&](long long k) { return m_rank[k & 63]; };
+#else
+    auto ensure = [&](long long) {};
+    auto src_of = [&](long long k) { return src_slot[first + k * stride]; };
+    auto dst_of = [&](long long k) { return dst_slot[first + k * stride]; };
+    auto nl_of = [&](long long k) { return nlive ? min(nlive[first + k * stride], capacity) : capacity; };
+    auto rank_of = [&](long long k) { return dst_rank[first + k * stride]; };
+#endif
+
+    // chunk stream: the issue cursor walks this CTA's items (`k` counts them); what the drain side needs -- where a
+    // buffer goes and how many bytes -- is noted per buffer when its load is issued
+    __shared__ unsigned long long pend_dst[kCopyBufs];
+    __shared__ unsigned pend_bytes[kCopyBufs];
     struct Cursor {
-        long long item;
+        long long k;
         int seg;        // 0 = hot range, 1 = cold range, 2 = orphan region (spawn mode)
         long long off;  // offset inside the segment
     };
-    auto seg_len = [&](long long item, int seg) -> long long {
-        if (src_slot[item] < 0) return 0;  // entry not served by this launch (e.g. filled from a receive buffer)
-        const int nl = nlive ? min(nlive[item], capacity) : capacity;
+    auto seg_len = [&](long long k, int seg) -> long long {
+        if (src_of(k) < 0) return 0;  // entry not served by this launch (e.g. filled from a receive buffer)
+        const int nl = nl_of(k);
         // hot keys are 4 B each: round the range up to the 16 B granularity of a bulk copy
         if (seg == 2) return (long long)orph_len;
         return seg == 0 ? (((long long)nl * hot_b + 15) & ~15ll) : (long long)nl * cold_b;
@@ -921,51 +969,57 @@ copy_blocks_kernel(const unsigned char* __restrict__ src_base, unsigned char* __
     auto seg_base = [&](int seg) -> long long {
         return seg == 0 ? 0 : (seg == 1 ? (long long)hot_region_bytes(capacity) : orph_off);
     };
-    auto advance = [&](Cursor& c, long long stride) {
-        // move to the next chunk, skipping empty segments; item strides over the grid
+    auto advance = [&](Cursor& c) {
+        // move to the next chunk, skipping empty segments
         c.off += kCopyChunk;
-        while (c.item < n && c.off >= seg_len(c.item, c.seg)) {
+        while (c.k < n_mine) {
+            ensure(c.k);
+            if (c.off < seg_len(c.k, c.seg)) break;
             c.off = 0;
             if (++c.seg > 2) {
                 c.seg = 0;
-                c.item += stride;
+                ++c.k;
             }
         }
     };
-    const long long stride = gridDim.x;
-    Cursor ci{(long long)blockIdx.x, 0, -(long long)kCopyChunk}, cd = ci;
-    advance(ci, stride);
-    advance(cd, stride);
+    Cursor ci{0, 0, -(long long)kCopyChunk};
+    advance(ci);
     long long issued = 0, drained = 0;
-    while (cd.item < n) {
+    while (ci.k < n_mine || drained < issued) {
         // keep up to kCopyBufs-1 loads in flight
-        while (ci.item < n && issued < drained + (kCopyBufs - 1)) {
+        while (ci.k < n_mine && issued < drained + (kCopyBufs - 1)) {
             const int b = (int)(issued % kCopyBufs);
-            if (issued >= kCopyBufs) tma_store_wait_read0();  // the store that last read this buffer
-            const long long len = seg_len(ci.item, ci.seg);
+            const long long len = seg_len(ci.k, ci.seg);
             const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - ci.off);
-            const unsigned char* s = src_base + (size_t)src_slot[ci.item] * src_stride + seg_base(ci.seg) + ci.off;
-            mbar_arrive_expect_tx(&bar[b], bytes);
-            tma_load_1d(buf[b], s, bytes, &bar[b]);
+            const long long in_block = seg_base(ci.seg) + ci.off;
+            const unsigned char* s = src_base + (size_t)src_of(ci.k) * src_stride + in_block;
+            // dst_tab != NULL: the item goes to the receive buffer of rank dst_rank[item] (peer memory) and
+            // dst_base only carries the byte offset inside a record (the header size)
+            unsigned char* db = dst_tab ? reinterpret_cast<unsigned char*>(dst_tab[rank_of(ci.k)]) +
+                                              reinterpret_cast<size_t>(dst_base)
+                                        : dst_base;
+            unsigned char* d = db + (size_t)dst_of(ci.k) * dst_stride + in_block;
+            if (lane == 0) {
+                pend_dst[b] = reinterpret_cast<unsigned long long>(d);
+                pend_bytes[b] = bytes;
+                if (issued >= kCopyBufs) tma_store_wait_read0();  // the store that last read this buffer
+                mbar_arrive_expect_tx(&bar[b], bytes);
+                tma_load_1d(buf[b], s, bytes, &bar[b]);
+            }
             ++issued;
-            advance(ci, stride);
+            advance(ci);
         }
-        const int b = (int)(drained % kCopyBufs);
-        mbar_wait(&bar[b], (unsigned)((drained / kCopyBufs) & 1));
-        const long long len = seg_len(cd.item, cd.seg);
-        const unsigned bytes = (unsigned)min((long long)kCopyChunk, len - cd.off);
-        // dst_tab != NULL: the item goes to the receive buffer of rank dst_rank[item] (peer memory) and
-        // dst_base only carries the byte offset inside a record (the header size)
-        unsigned char* db = dst_tab ? reinterpret_cast<unsigned char*>(dst_tab[dst_rank[cd.item]]) +
-                                          reinterpret_cast<size_t>(dst_base)
-                                    : dst_base;
-        unsigned char* d = db + (size_t)dst_slot[cd.item] * dst_stride + seg_base(cd.seg) + cd.off;
-        tma_store_1d(d, buf[b], bytes);
-        tma_store_commit();
-        ++drained;
-        advance(cd, stride);
+        if (drained < issued) {
+            const int b = (int)(drained % kCopyBufs);
+            if (lane == 0) {
+                mbar_wait(&bar[b], (unsigned)((drained / kCopyBufs) & 1));
+                tma_store_1d(reinterpret_cast<void*>(pend_dst[b]), buf[b], pend_bytes[b]);
+                tma_store_commit();
+            }
+            ++drained;
+        }
     }
-    tma_store_wait0();
+    if (lane == 0) tma_store_wait0();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ VARIANTS = {
     "reg112": ["-DPK_K2_REGCAP_F32=112"],
     "reg120w1": ["-DPK_K2_REGCAP_F32=120", "-DPK_MEASURE_WARPS=1"],
     "reg112w3": ["-DPK_K2_REGCAP_F32=112", "-DPK_MEASURE_WARPS=3"],
+    "nometa": ["-DPK_COPY_META_CACHE=0"],
 }
 
 
@@ -74,6 +75,30 @@ def _worker(name, what):
         _, mf, ev, fd = R.stats()
         out[tag] = {"ms_per_step": m["median_ms"] / steps, **{k: round(v, 5) for k, v in m["kernel_ms"].items()},
                     "matched": round(mf, 5), "evals_pp": round(ev, 3), "f_dup": round(fd, 4), "blocks": len(m["block_ms"])}
+        R.close()
+    if not what or "sweep" in what:
+        # the resampling chain at stated duplicate fractions (weights set by hand), block copies included
+        import statistics
+        import torch
+        R = bench.Runner(args, 1, 0, 1 << 20, 64, "f32", "f32", "peer")
+        for _ in range(3):
+            R.step()
+        fs, idx = R.fs, torch.arange(1 << 20, device="cuda")
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        sw = {}
+        for label, dead in (("4%", idx % 25 == 0), ("10%", idx % 10 == 0), ("50%", idx % 2 == 1), ("94%", idx % 16 != 0)):
+            ts = []
+            for rep in range(6):
+                fs.pose[:, 3] = torch.where(dead, 0.0, 1.0).to(torch.float64)
+                a, b = ev(), ev()
+                a.record()
+                fs.low_variance_resample()
+                fs.wait_blocks()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            sw[label] = round(statistics.median(ts[1:]), 4)
+        out["resample_ms_at_f_dup"] = sw
         R.close()
     print("VARIANT " + json.dumps(out), flush=True)
 
