@@ -53,7 +53,10 @@ __device__ __forceinline__ void st16x4(void* p, int4 a, int4 b, int4 c, int4 d) 
     __stcg(q, a); __stcg(q + 1, b); __stcg(q + 2, c); __stcg(q + 3, d);
 }
 constexpr size_t kBlock = 4352;  // 256 B keys + 64 x 64 B records
-constexpr int kStages = 4;
+#ifndef PROBE_STAGES
+#define PROBE_STAGES 4
+#endif
+constexpr int kStages = PROBE_STAGES;
 constexpr int kStageBytes = 4 * 256 + 32 * 64 + 128;
 constexpr int kSmem = 4 * kStages * kStageBytes;
 
@@ -150,6 +153,7 @@ int main(int argc, char** argv) {
     const int M = 1 << 20;
     const int flavour = argc > 1 ? atoi(argv[1]) : 0;
     const int only_perm = argc > 2 ? atoi(argv[2]) : -1;
+    printf("stages %d, ", kStages);
     printf("store flavour %d (0 st.cg.v8, 1 st.v8, 2 st.cs.v8, 3 L2 evict_first, 4 L2 evict_last, 5 4 x st.cg.v4)\n", flavour);
     unsigned char* pool;
     int *slot, *assoc;
