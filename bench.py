@@ -374,6 +374,11 @@ class Runner(object):
                 kms.append(t[1:])
             if nblocks is None:   # every rank sees the same (max-reduced) first block: same decision everywhere
                 nblocks = int(min(max_blocks, max(3, math.ceil(min_total_ms / max(t[0], 1e-3)))))
+                # frames get dearer within a re-initialisation cycle (duplicates grow): time whole cycles, so that the
+                # medians of two passes (device-resident, e2e) are taken over the same mix of blocks
+                cycle = (self.scn.frames - 4) // steps   # maybe_reset(): 4 settling frames, then whole blocks
+                if cycle > 1 and nblocks > cycle:
+                    nblocks = int(min(max_blocks, cycle * math.ceil(nblocks / cycle)))
             if len(blocks) >= nblocks:
                 break
         out = {"block_ms": blocks, "median_ms": statistics.median(blocks)}
@@ -544,7 +549,8 @@ def run_ours(args):
                           "fp32 landmark algebra in K2 (gates, Mahalanobis forms, EKF); fp64 poses, weights, resampling",
             "motion_noise": "philox4x32-10 on device",
             "resample": "systematic every frame, copy-on-resample (duplicates only)",
-            "timing": "median of %d blocks of %d steps (>= 1 s of device time in total), CUDA events, max over ranks"
+            "timing": "median of %d blocks of %d steps (>= 1 s of device time in total, whole re-initialisation cycles), "
+                      "CUDA events, max over ranks; per-kernel split from a second pass with four events per step"
                       % (len(main["block_ms"]), steps),
             "l2": "inputs larger than L2 (%.1f GB landmark pool per GPU vs 126 MB)"
                   % (M_local * N * ((64 if args.dtype == "f32" else 160) + 4) / 1e9),
