@@ -131,9 +131,12 @@ struct Hits {
 // LM selects the arithmetic of the landmark algebra: Landmark (fp64, every instantiation that must reproduce the
 // reference) or LandmarkF (fp32 on fp32 storage, PK_DTYPE_ARITH_F32)
 // record prefetch of an item's first hit: 1 = the warp fetches the 32-record strip together, 0 = every lane its own
-// colour screen: 1 = sum of absolute byte differences (two instructions per key), 0 = squared distance (three)
+// colour screen: 0 = squared byte distance (three instructions per key), 1 = sum of absolute byte differences (two:
+// VABSDIFF4.U8.ACC + funnel shift).  Measured (tools/k2_variants.py): at 64 landmarks both cost the same (K2 0.438 ms
+// either way: the kernel is not bound by its instruction count), on maps of hundreds of landmarks the L1 form's 1.65x
+// false positives push items over the hit list and into the key re-walk (config 5: 57.1 s instead of 49.2 s).
 #ifndef PK_SCREEN_SAD
-#define PK_SCREEN_SAD 1
+#define PK_SCREEN_SAD 0
 #endif
 #ifndef PK_COOP_PREFETCH
 #define PK_COOP_PREFETCH 1

@@ -92,3 +92,32 @@ def test_layout_code_helpers():
         assert lib.pk_block_bytes(cap, _lib.PK_DTYPE_F32) % 64 == 0
         assert lib.pk_block_bytes(cap, _lib.PK_DTYPE_F64) % 32 == 0
     assert lib.pk_obs_table_bytes() >= 6 * 64 * 8 + 64 * 4
+
+
+def test_colour_screen_bound_contains_the_gate():
+    """The screen of the fused kernel tests the squared key distance against B = floor(gate + 2 sqrt(3 gate) + 3) + 1
+    (its -DPK_SCREEN_SAD=1 form: `sum |key difference| <= floor(sqrt(3 B))`; pk_measure.cu, measurement_common): both
+    restated here and checked against the exact gate (prkt_core_v2.py:441,
+    `abs(dr^2 + dg^2 + db^2) > gate` rejects) on random colour pairs, pairs on the gate's sphere in the all-equal direction
+    (the worst case of an L1 bound) and pairs at the clamps of the 8-bit keys."""
+    import math
+    import numpy as np
+
+    def key(c):
+        return np.rint(np.clip(c, 0.0, 255.0)).astype(np.int64)
+
+    rs = np.random.RandomState(3)
+    for gate in (300.0, 0.0, 1.0, 75.0, 1200.0, 50000.0):
+        B = math.floor(gate + 2.0 * math.sqrt(3.0 * gate) + 3.0) + 1
+        t = math.isqrt(3 * B)
+        a = rs.uniform(-5.0, 260.0, (200000, 3))
+        r = math.sqrt(gate / 3.0)
+        off = np.concatenate([rs.normal(0.0, 1.0, (100000, 3)) * (r + 1.0),
+                              rs.choice([-1.0, 1.0], (100000, 3)) * rs.uniform(0.9 * r, 1.0 * r, (100000, 1))])
+        b = a + off
+        inside = np.abs(((a - b) ** 2).sum(1)) <= gate          # the reference does not reject
+        l1 = np.abs(key(a) - key(b)).sum(1)
+        l2 = ((key(a) - key(b)) ** 2).sum(1)
+        assert inside.sum() > 1000
+        assert np.all(l2[inside] <= B), gate
+        assert np.all(l1[inside] <= t), gate

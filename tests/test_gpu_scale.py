@@ -511,3 +511,60 @@ def test_block_copies_on_the_copy_stream_change_nothing():
         for x, y in zip(sa, sb):
             assert np.array_equal(x, y)
     assert a[5] == b[5]
+
+
+@pytest.mark.parametrize("dtype,arithmetic", [("f64", "f64"), ("f32", "f32")])
+def test_colour_screen_contains_the_gate_on_its_boundary(dtype, arithmetic):
+    """The byte-key screen is a bound on the distance of two 8-bit keys that must CONTAIN the reference's colour gate
+    (`abs(colour distance) > 300` rejects, prkt_core_v2.py:441).  Hard cases: the blob's colour differs from the
+    landmark's by the same amount in every channel (largest L1 distance for a given squared distance), with landmark
+    colours at x.5 (key rounding) and near 0 / 255 (key clamping).  Blobs just inside the gate must still be matched, blobs
+    just outside must not -- exactly as the oracle decides."""
+    from oracle import fastslam_np as onp
+    from parakeet_slam_b200.scenario import DT_NSEC
+    M, N, T = 1024, 48, 4
+    noise_rs = np.random.RandomState(15)
+    blocks = [noise_rs.standard_normal((M, 3)) for _ in range(T)]
+    it = iter(blocks)
+    scn, fs, clk, tw = _make(M, N, dtype, T, noise=lambda m: next(it))
+    rs = np.random.RandomState(18)
+    col = np.floor(rs.uniform(30, 225, (N, 3))) + 0.5          # x.5: the key rounds to even
+    col[::7] = rs.uniform(0.0, 6.0, (len(col[::7]), 3))         # near the clamp at 0
+    col[3::7] = rs.uniform(249.0, 255.0, (len(col[3::7]), 3))   # ... and at 255
+    scn.landmarks[:, 2:5] = col
+    # per blob: a signed offset of equal size per channel, squared distance 3 d^2 around the gate (d = 10 <=> 300)
+    d = np.array([9.9, 9.99, 9.999, 10.001, 10.01, 10.2, 9.5, 0.3])
+    for t in range(T):
+        sign = rs.choice([-1.0, 1.0], (8, 3))
+        lmc = scn.landmarks[scn.obs_landmark[t], 2:5]
+        scn.observations[t, :, 1:4] = lmc + sign * np.roll(d, t)[:, None]
+    from device_harness import make_features
+    from parakeet_slam_b200.core import FastSLAM
+    fs2 = FastSLAM(make_features(scn), num_particles=M, dtype=dtype, arithmetic=arithmetic, noise=lambda m: next(it),
+                   uniform=random.Random(4).random, clock=clk)
+    fs2.last_control = tw
+    fs2.keep_trace = True
+    st = onp.OracleState(M, scn.landmarks, preset_covar=scn.preset_covar)
+    urng = random.Random(4)
+    seen_match = seen_gate = 0
+    for t in range(T):
+        clk.ns += DT_NSEC
+        fs2.motion_update(tw)
+        fs2.measurement_update(scn.observations[t])
+        fs2.low_variance_resample()
+        ids, wgt, anc, _ = onp.frame(st, scn.observations[t], blocks[t], scn.v, scn.w, scn.dt, urng.random(),
+                                     sequential_resample=False)
+        got = fs2.last_assoc.cpu().numpy()
+        if arithmetic == "f64":
+            assert np.array_equal(got, ids), "frame %d" % t
+            assert np.array_equal(fs2.last_ancestors.cpu().numpy(), anc), "frame %d" % t
+        else:
+            # fp32 algebra evaluates the gate on fp32 colours: a blob within 1e-3 of the gate may fall on either side
+            dd = np.roll(d, t)
+            sure = np.abs(3.0 * dd * dd - 300.0) > 0.5
+            assert np.array_equal(got[:, sure], ids[:, sure]), "frame %d" % t
+            break   # (the two filters' maps differ from here on if a borderline blob was decided differently)
+        seen_match += int((ids > 0).sum())
+        seen_gate += int((ids == 0).sum())
+    if arithmetic == "f64":
+        assert seen_match > 0 and seen_gate > 0   # both sides of the gate were exercised

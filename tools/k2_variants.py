@@ -29,6 +29,8 @@ VARIANTS = {
     "reg120w1": ["-DPK_K2_REGCAP_F32=120", "-DPK_MEASURE_WARPS=1"],
     "reg112w3": ["-DPK_K2_REGCAP_F32=112", "-DPK_MEASURE_WARPS=3"],
     "nometa": ["-DPK_COPY_META_CACHE=0"],
+    "l2noring": ["-DPK_SCREEN_SAD=0", "-DPK_CLOOP_PREFETCH=0"],
+    "sad": ["-DPK_SCREEN_SAD=1"],
 }
 
 
