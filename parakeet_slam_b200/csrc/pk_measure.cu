@@ -11,17 +11,17 @@
 //
 // Shape of the kernel (persistent; one warp owns a *group* of consecutive particles sized so that
 // group x K blobs fills the 32 lanes, i.e. every lane is one (particle, blob) ITEM):
-//   * the 4-byte colour KEYS of the group's maps are streamed global -> shared by 1-D TMA bulk
-//     copies (cp.async.bulk + mbarrier), one copy per particle issued by its own lane, through a
+//   * the 4-byte colour KEYS of the group's maps (and its pose records) are streamed global -> shared with per-thread
+//     16-byte cp.async copies (16 lanes cover a particle's 64 keys, i.e. whole 128-byte lines per instruction) through a
 //     per-warp ring of stages that runs ahead of the consumer across groups;
-//   * SCREEN: each lane scans its particle's keys against its blob's key with two integer SIMD
-//     instructions per pair (vabsdiff4 + dp4a = squared byte distance, keys read 4 at a time with
-//     LDS.128) against a bound that provably contains the reference's colour gate (:441) -- the
-//     cheapest and most selective of its gates, and probability_of_match is 0 whenever it fails,
-//     whatever the evaluation order.  Hits (about one per item) stay in registers; the lane
-//     requests the cold record of its first hit at once into its own staging slot in shared
-//     memory with per-thread cp.async copies (a scattered, per-lane fetch -- cp.async.bulk takes
-//     warp-uniform operands and would serialise over the lanes);
+//   * SCREEN: each lane scans its particle's keys against its blob's key with three integer instructions per pair
+//     (vabsdiff4 + dp4a = squared byte distance accumulated onto -(bound + 1), funnel shift of the sign into the hit
+//     mask; keys read 4 at a time with LDS.128) against a bound that provably contains the reference's colour gate
+//     (:441) -- the cheapest and most selective of its gates, and probability_of_match is 0 whenever it fails,
+//     whatever the evaluation order.  Hits (about one per item) stay in registers; the cold records of the items'
+//     first hits are requested into a 32-slot strip of shared memory by the whole warp together (per-thread cp.async
+//     copies whose lanes cover whole records), a second hit by its own lane, third and later ones through the
+//     candidate ring during the evaluation;
 //   * the warp is software-pipelined across groups: it screens group g+1 (and so has that
 //     group's records in flight) BEFORE it evaluates group g, so neither the key stream nor the
 //     scattered record fetches expose DRAM latency;
@@ -31,8 +31,9 @@
 //     re-using the bearing it already computed.  Items that hit the same landmark of the same
 //     particle are ordered in rounds so the second sees the first's result (finding F2);
 //   * the weight is the scan-order product of the K factors (:124).
-// All arithmetic is fp64; the template parameter T is only the landmark STORAGE type, R the number
-// of items a lane carries (1 when group x K <= 32, 2 for 32 < K <= 64).
+// Template parameters: T the landmark STORAGE type, R the number of items a lane carries (1 when group x K <= 32, 2 for
+// 32 < K <= 64), LM the landmark ALGEBRA (Landmark: fp64, every instantiation that must reproduce the reference;
+// LandmarkF: fp32 on fp32 records -- poses, differences pose - landmark, weights stay fp64).
 #include <math.h>
 
 #include "pk_common.cuh"
