@@ -14,13 +14,18 @@ measured as well.
 Timing.  A BLOCK is exactly ``--steps`` frames bracketed by a barrier + ``torch.cuda.synchronize()`` on both sides
 and timed with CUDA events on the launching stream (max over ranks).  One block of a sub-millisecond frame is a few
 milliseconds, far too short to be repeatable, so blocks are repeated until they add up to >= 1 s of device time and
-the MEDIAN block is reported (``ms_per_step`` = median block / steps; ``blocks`` says how many, ``block_ms`` their
-spread).  Clocks are sampled over the whole repeated window.
+the MEDIAN block is reported (``ms_per_step`` = median block / steps; ``blocks`` says how many -- whole
+re-initialisation cycles of the scenario, because frames get dearer as duplicates grow within a cycle --, ``block_ms``
+their spread).  The throughput passes (``value``, ``e2e``) carry nothing but the frames between their two events;
+``kernel_ms`` comes from a second, shorter pass with four events per step.  On one GPU the block copies of a
+resampling run on the filter's copy stream beside the next motion update (``kernel_ms_note``).  Clocks are sampled over
+the whole repeated window.
 
 Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput, ``e2e`` the same metric through the drop-in
 Python API (``FastSLAM.cam_cb`` with host ``VizScan`` messages plus ``summary()`` read back every frame).
 ``roofline`` describes the dominant kernel (the fused measurement update) timed with CUDA events inside the timed
-steps.  ``cpu_baseline`` times the UNMODIFIED reference (byte-compiled into ``oracle/_ref`` by ``oracle/build_ref.py``)
+steps; ``roofline.pattern_ceiling`` puts the measured cost of that kernel's memory accesses alone beside it
+(``tools/k2_mem_probe.cu``).  ``cpu_baseline`` times the UNMODIFIED reference (byte-compiled into ``oracle/_ref`` by ``oracle/build_ref.py``)
 on the host cores beside it.
 """
 from __future__ import annotations
